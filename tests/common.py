@@ -1,0 +1,47 @@
+"""Shared helpers for the parity tests (golden loading, seeded weights)."""
+import os
+
+import numpy as np
+import torch
+
+from holoscene_b200 import synthetic
+from oracle import model as om
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def cfg_from_golden(g):
+    N, Ne, Nx = (int(v) for v in g["meta_sampler"])
+    return om.StepConfig(d_out=int(g["meta_K"]), logmap=int(g["meta_logmap"]), N_samples=N, N_samples_eval=Ne,
+                         N_samples_extra=Nx)
+
+
+def seeded_state_dict(cfg, seed=42):
+    """The weights every golden vector was produced with: reference init order under
+    torch.manual_seed(42), then the fixed synthetic perturbation."""
+    torch.manual_seed(seed)
+    return synthetic.perturb_state_dict(om.init_state_dict(cfg))
+
+
+def param_checksum(sd):
+    return sum(float(v.double().abs().sum()) for v in sd.values() if v.dtype.is_floating_point)
+
+
+def golden_inputs(g):
+    uv = torch.from_numpy(g["in_uv"])
+    pose = torch.from_numpy(g["in_pose"])
+    K = torch.from_numpy(g["in_intrinsics"])
+    gt = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("gt_")}
+    draws = {k[5:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("draw_")}
+    return uv, pose, K, gt, draws
+
+
+def rel_err(a, b):
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
