@@ -1,0 +1,164 @@
+"""GPU parity: libhsb200 hash-grid kernels (through the C ABI) against the CPU oracle, against the
+reference's own kernels when oracle/_ref is present, and size-independent properties at full size."""
+import numpy as np
+import pytest
+import torch
+
+from tests import common, hash_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _product():
+    from holoscene_b200 import hashgrid
+    return hashgrid
+
+
+@pytest.mark.parametrize("kw", [dict(B=512, logmap=19, seed=1234), dict(B=768, logmap=12, seed=99),
+                                dict(B=1, logmap=12, seed=7), dict(B=4097, logmap=14, seed=11)])
+def test_kernels_match_oracle(kw):
+    hg = _product()
+    c = hash_cases.make_case(**kw)
+    o = hash_cases.oracle_all(c)
+    r = hash_cases.backend_all(hg._backend, c)
+    # fp32; device FMA contraction / exp2f vs the host -> a few ulp on O(1) values
+    for k in ("out", "dy_dx", "gx", "gg"):
+        scale = max(1.0, float(o[k].abs().max()))
+        assert float((r[k] - o[k]).abs().max()) <= 2e-5 * scale, k
+    for k in ("gemb", "g2"):
+        assert common.rel_err(r[k], o[k]) < 1e-5, k
+
+
+def test_kernels_match_reference_kernels():
+    from oracle import build_ref
+    ref = build_ref.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    hg = _product()
+    c = hash_cases.make_case(B=2048, logmap=19, seed=321)
+    a = hash_cases.backend_all(ref, c)
+    b = hash_cases.backend_all(hg._backend, c)
+    for k in ("out", "dy_dx", "gx", "gg"):
+        scale = max(1.0, float(a[k].abs().max()))
+        assert float((a[k] - b[k]).abs().max()) <= 1e-5 * scale, k
+    for k in ("gemb", "g2"):
+        assert common.rel_err(b[k], a[k]) < 1e-5, k
+
+
+def test_empty_batch_is_ok():
+    hg = _product()
+    enc = hg.HashEncoder(desired_resolution=2048, log2_hashmap_size=12).cuda()
+    y = enc(torch.empty(0, 3, device="cuda"))
+    assert y.shape == (0, 32)
+
+
+def test_module_autograd_matches_oracle_double_backward():
+    """HashEncoder module: y, dy/dx and the double-backward parameter gradient against the oracle Functions."""
+    from oracle import hashgrid as ohg
+    hg = _product()
+    torch.manual_seed(0)
+    enc = hg.HashEncoder(desired_resolution=2048, log2_hashmap_size=12)
+    enc.embeddings.data = (torch.rand_like(enc.embeddings) * 2 - 1) * 0.1
+    x = torch.rand(300, 3) * 2.2 - 1.1          # some points outside [-1,1]
+    v = torch.randn(300, 32)
+    u = torch.randn(300, 3)
+    # oracle
+    xe = x.clone().requires_grad_(True)
+    emb = enc.embeddings.detach().clone().requires_grad_(True)
+    y = ohg.encode(xe, emb, enc.offsets, enc.per_level_scale)
+    (gx,) = torch.autograd.grad(y, xe, v, create_graph=True)
+    ((gx * u).sum() + (y * y).sum()).backward()
+    # product
+    encc = enc.cuda()
+    xc = x.cuda().requires_grad_(True)
+    yc = encc(xc)
+    (gxc,) = torch.autograd.grad(yc, xc, v.cuda(), create_graph=True)
+    ((gxc * u.cuda()).sum() + (yc * yc).sum()).backward()
+    assert float((yc.cpu() - y).abs().max()) < 1e-5
+    assert common.rel_err(gxc.detach().cpu(), gx.detach()) < 1e-5
+    assert common.rel_err(encc.embeddings.grad.cpu(), emb.grad) < 1e-5
+
+
+def test_fused_layout_and_fused_scatter():
+    """Strided (MLP-row) output layout and the one-pass first+second-order scatter equal the
+    reference-layout calls."""
+    from holoscene_b200 import _lib
+    c = hash_cases.make_case(B=1000, logmap=14, seed=5)
+    B, L = c["B"], c["L"]
+    xw = (c["x"] * 2 - 1).cuda()                  # world coords; a few rows are out of range
+    x01 = ((xw + 1.0) / 2.0).contiguous()
+    emb, offs = c["emb"].cuda(), c["offsets"].cuda()
+    o = hash_cases.oracle_all(dict(c, x=x01.cpu()))
+    rows = torch.zeros(B, 72, device="cuda")
+    dy = torch.empty(B, 96, device="cuda")
+    _lib.check(_lib.hash_forward(_lib.ptr(xw), _lib.ptr(emb), _lib.ptr(offs), ctypes_off(rows, 39), 2, 72, _lib.ptr(dy), 96,
+                                 B, L, c["S"], c["H"], 1, _lib.stream()))
+    torch.cuda.synchronize()
+    want = o["out"].permute(1, 0, 2).reshape(B, 32)
+    assert float((rows[:, 39:71].cpu() - want).abs().max()) < 2e-5
+    assert float(rows[:, :39].abs().max()) == 0.0 and float(rows[:, 71].abs().max()) == 0.0
+    assert float((dy.cpu() - o["dy_dx"]).abs().max()) < 2e-5 * max(1.0, float(o["dy_dx"].abs().max()))
+    # fused scatter with 3 seeds == first-order backward + sum of 3 second-order backwards (ggx = dg/2)
+    g = torch.Generator().manual_seed(8)
+    dE = torch.randn(B, 32, generator=g)
+    q0 = torch.randn(3 * B, 72, generator=g)
+    dg = torch.randn(3 * B, 3, generator=g)
+    want_t = torch.zeros_like(c["emb"])
+    gx = torch.zeros(B, 3)
+    from oracle import hashgrid as ohg
+    ohg.hash_encode_backward(dE.view(B, L, 2).permute(1, 0, 2).contiguous(), x01.cpu(), c["emb"], c["offsets"], want_t, B, 3,
+                             2, L, c["S"], c["H"], False, o["dy_dx"], gx)
+    for s in range(3):
+        gg = torch.zeros(L, B, 2)
+        ohg.hash_encode_second_backward(q0[s * B:(s + 1) * B, 39:71].reshape(B, L, 2).permute(1, 0, 2).contiguous(), x01.cpu(),
+                                        c["emb"], c["offsets"], B, 3, 2, L, c["S"], c["H"], True, o["dy_dx"],
+                                        (0.5 * dg[s * B:(s + 1) * B]).contiguous(), gg, want_t)
+    got = torch.zeros_like(emb)
+    q0c, dgc, dEc = q0.cuda(), dg.cuda(), dE.cuda()
+    _lib.check(_lib.hash_backward_fused(_lib.ptr(xw), _lib.ptr(offs), _lib.ptr(dEc), 32, ctypes_off(q0c, 39), 72, _lib.ptr(dgc),
+                                        3, _lib.ptr(got), B, L, c["S"], c["H"], _lib.stream()))
+    torch.cuda.synchronize()
+    assert common.rel_err(got.cpu(), want_t) < 1e-5
+
+
+def ctypes_off(t, col):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr() + 4 * col)
+
+
+def test_full_size_linearity_and_partition_of_unity():
+    """Size-independent properties at the benchmark size (P = 4096 x 128 points, 2^19 tables):
+    encoding is linear in the table; with an all-ones table every in-range feature is exactly the
+    sum of the 8 smoothstep weights = 1 and dy_dx = 0; scatter of an all-ones gradient adds exactly
+    one unit of mass per in-range (point, level, channel)."""
+    from holoscene_b200 import _lib
+    P = 4096 * 128
+    g = torch.Generator().manual_seed(2)
+    c = hash_cases.make_case(B=16, logmap=19, seed=4)
+    offs = c["offsets"].cuda()
+    x = (torch.rand(P, 3, generator=g) * 2.4 - 1.2).cuda()     # ~42% of points out of range
+    inr = ((x >= -1) & (x <= 1)).all(dim=1)
+    rows = int(c["offsets"][-1])
+    ones = torch.ones(rows, 2, device="cuda")
+    out = torch.empty(P, 32, device="cuda")
+    dy = torch.empty(P, 96, device="cuda")
+    _lib.check(_lib.hash_forward(_lib.ptr(x), _lib.ptr(ones), _lib.ptr(offs), _lib.ptr(out), 2, 32, _lib.ptr(dy), 96, P, 16,
+                                 c["S"], 16, 1, _lib.stream()))
+    assert float((out[inr] - 1.0).abs().max()) < 1e-5
+    assert float(out[~inr].abs().max()) == 0.0
+    assert float(dy.abs().max()) < 2e-2          # scale (<=2047) x rounding of (1-1)
+    e1 = (torch.rand(rows, 2, generator=g) - 0.5).cuda()
+    e2 = (torch.rand(rows, 2, generator=g) - 0.5).cuda()
+    o1, o2, o3 = (torch.empty(P, 32, device="cuda") for _ in range(3))
+    for e, o in ((e1, o1), (e2, o2), ((2 * e1 - 3 * e2).contiguous(), o3)):
+        _lib.check(_lib.hash_forward(_lib.ptr(x), _lib.ptr(e), _lib.ptr(offs), _lib.ptr(o), 2, 32, None, 0, P, 16, c["S"], 16,
+                                     1, _lib.stream()))
+    assert float((o3 - (2 * o1 - 3 * o2)).abs().max()) < 1e-5
+    gt = torch.zeros(rows, 2, device="cuda")
+    gones = torch.ones(P, 32, device="cuda")
+    _lib.check(_lib.hash_backward(_lib.ptr(gones), 2, 32, _lib.ptr(x), _lib.ptr(offs), _lib.ptr(gt), None, 0, None, P, 16,
+                                  c["S"], 16, 1, _lib.stream()))
+    torch.cuda.synchronize()
+    mass = float(gt.double().sum())
+    want = float(inr.sum()) * 32
+    assert abs(mass - want) <= 1e-4 * want

@@ -1,0 +1,64 @@
+"""CPU: oracle/hash_oracle.c against the recorded outputs of the reference's own CUDA kernels
+(tests/golden/hash_ref_*.npz, produced on a B200 by tests/golden/make_hash_ref_golden.py), plus
+internal consistency checks that need no fixture."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hashgrid as ohg
+from tests import common, hash_cases
+
+
+@pytest.mark.parametrize("name,kw", [("hash_ref_full", dict(B=512, logmap=19, seed=1234)),
+                                     ("hash_ref_small", dict(B=768, logmap=12, seed=99))])
+def test_c_oracle_matches_reference_kernels(name, kw):
+    path = os.path.join(common.GOLDEN, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("reference-kernel fixture not recorded yet (needs one GPU run)")
+    z = np.load(path)
+    c = hash_cases.make_case(**kw)
+    o = hash_cases.oracle_all(c)
+    for k in ("out", "dy_dx", "gx", "gg"):
+        ref = torch.from_numpy(z[k])
+        scale = float(ref.abs().max())
+        assert float((o[k] - ref).abs().max()) <= 2e-5 * max(scale, 1.0), k
+    for k, ik, vk in (("gemb", "gemb_idx", "gemb_val"), ("g2", "g2_idx", "g2_val")):
+        ref = hash_cases.from_coo(z[ik], z[vk], o[k].shape)
+        assert common.rel_err(o[k], ref) < 1e-5, k
+
+
+def test_oob_points_give_zeros():
+    c = hash_cases.make_case(B=64, logmap=12, seed=5)
+    o = hash_cases.oracle_all(c)
+    for row in (5, 6, 7, 8):  # the out-of-range edge rows
+        assert float(o["out"][:, row].abs().max()) == 0.0
+        assert float(o["dy_dx"][row].abs().max()) == 0.0
+    assert float(o["out"][:, 0].abs().max()) > 0.0  # x = 0 is in range
+
+
+def test_dy_dx_is_the_derivative():
+    """finite differences of the forward against dy_dx, away from cell borders"""
+    offsets, pls = ohg.level_offsets(4, 16, 64, 12)
+    g = torch.Generator().manual_seed(3)
+    emb = torch.rand(int(offsets[-1]), 2, generator=g).double().float()
+    x = torch.rand(32, 3, generator=g) * 0.9 + 0.05
+    S, L, B = float(np.float32(np.log2(pls))), 4, 32
+
+    def fwd(xx, need):
+        out = torch.empty(L, B, 2)
+        dd = torch.empty(B, L * 6) if need else torch.empty(1)
+        ohg.hash_encode_forward(xx.contiguous(), emb, offsets, out, B, 3, 2, L, S, 16, need, dd)
+        return out, dd
+
+    out, dd = fwd(x, True)
+    dd = dd.view(B, L, 3, 2)
+    h = 1e-4
+    for d in range(3):
+        e = torch.zeros(3)
+        e[d] = h
+        num = (fwd(x + e, False)[0] - fwd(x - e, False)[0]) / (2 * h)  # [L,B,2]
+        ana = dd[:, :, d, :].permute(1, 0, 2)
+        ok = (num - ana).abs() <= 5e-2 * (ana.abs() + 1.0)
+        assert ok.float().mean() > 0.97  # points whose +-h stencil crosses a cell border are exempt
