@@ -1,0 +1,134 @@
+// Parameter-space kernels: weight normalisation (forward materialisation + backward), weight
+// transposes for the dgrad / input-gradient contractions, and the fused Adam update.
+//
+// Reference semantics: torch.nn.utils.weight_norm(dim=0)  w = g * v / ||v||_row
+// (model/network.py:158-159, 577-578) and torch.optim.Adam(betas=(0.9,0.99), eps=1e-15) with three
+// learning-rate groups (training/holoscene_train.py:156-164).
+#include "common.cuh"
+#include "step.cuh"
+
+namespace hsb {
+
+// one warp per output row n:  We[n, 0:cols] = g[n] * v[n,:] / ||v[n,:]||,  We[n, cols:ldw] = 0,
+// and the transposed copy WeT[k, n] (ldt >= rows; rows of WeT beyond `cols` are zeroed by the caller's memset).
+__global__ void __launch_bounds__(256) wn_forward_kernel(const float* __restrict__ v, const float* __restrict__ g, int rows,
+                                                         int cols, float* __restrict__ We, int ldw, float* __restrict__ WeT,
+                                                         int ldt) {
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= rows) return;
+    const float* vr = v + (long long)n * cols;
+    float ss = 0.0f;
+    for (int k = lane; k < cols; k += 32) ss += vr[k] * vr[k];
+    ss = warp_sum(ss);
+    const float sc = g[n] / sqrtf(ss);
+    for (int k = lane; k < ldw; k += 32) {
+        const float w = k < cols ? sc * vr[k] : 0.0f;
+        We[(long long)n * ldw + k] = w;
+        if (WeT && k < cols) WeT[(long long)k * ldt + n] = w;
+    }
+}
+
+// dv[n,:] += (g/||v||) (dW[n,:] - (dW[n,:].vhat) vhat),  dg[n] += dW[n,:].vhat
+__global__ void __launch_bounds__(256) wn_backward_kernel(const float* __restrict__ dWe, int ldw, const float* __restrict__ v,
+                                                          const float* __restrict__ g, int rows, int cols,
+                                                          float* __restrict__ dv, float* __restrict__ dg) {
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= rows) return;
+    const float* vr = v + (long long)n * cols;
+    const float* dw = dWe + (long long)n * ldw;
+    float ss = 0.0f, dot = 0.0f;
+    for (int k = lane; k < cols; k += 32) { ss += vr[k] * vr[k]; dot += dw[k] * vr[k]; }
+    ss = warp_sum(ss);
+    dot = warp_sum(dot);
+    const float inv = rsqrtf(ss);
+    const float dotn = dot * inv;               // dW . vhat
+    const float sc = g[n] * inv;
+    for (int k = lane; k < cols; k += 32) dv[(long long)n * cols + k] += sc * (dw[k] - dotn * vr[k] * inv);
+    if (lane == 0) dg[n] += dotn;
+}
+
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ WT,
+                                                        int ldt) {
+    __shared__ float tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        int r = by + j, c = bx + tx;
+        tile[j][tx] = (r < rows && c < cols) ? W[(long long)r * cols + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        int c = bx + j, r = by + tx;
+        if (c < cols && r < rows) WT[(long long)c * ldt + r] = tile[tx][j];
+    }
+}
+
+// Adam over one flat segment; optionally accumulates ||g||^2 (the trainer's grad-norm statistic,
+// holoscene_train.py:367-372) in the same pass.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                   float bc1, float bc2_sqrt, float* __restrict__ gnorm2) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    float acc = 0.0f;
+    const float step = lr / bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+        acc += gi * gi;
+    }
+    if (gnorm2) {
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) atomicAdd(gnorm2, acc);
+    }
+}
+
+__global__ void __launch_bounds__(256) add_into_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+int launch_add_into(const float* src, float* dst, int n, cudaStream_t st) {
+    if (n <= 0) return HSB_OK;
+    add_into_kernel<<<cdiv(n, 256), 256, 0, st>>>(src, dst, n);
+    return check_launch("add_into");
+}
+
+int launch_wn_forward(const float* v, const float* g, int rows, int cols, float* We, int ldw, float* WeT, int ldt,
+                      cudaStream_t st) {
+    wn_forward_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(v, g, rows, cols, We, ldw, WeT, ldt);
+    return check_launch("wn_forward");
+}
+int launch_wn_backward(const float* dWe, int ldw, const float* v, const float* g, int rows, int cols, float* dv, float* dg,
+                       cudaStream_t st) {
+    wn_backward_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(dWe, ldw, v, g, rows, cols, dv, dg);
+    return check_launch("wn_backward");
+}
+int launch_transpose(const float* W, int rows, int cols, float* WT, int ldt, cudaStream_t st) {
+    dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+    transpose_kernel<<<grid, 256, 0, st>>>(W, rows, cols, WT, ldt);
+    return check_launch("transpose");
+}
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1,
+                float bc2_sqrt, float* gnorm2, cudaStream_t st) {
+    if (n <= 0) return HSB_OK;
+    long long blocks = (n + 256 * 4 - 1) / (256 * 4);
+    long long cap = 148LL * 16;
+    if (blocks > cap) blocks = cap;
+    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2_sqrt, gnorm2);
+    return check_launch("adam");
+}
+
+}  // namespace hsb
+
+extern "C" int hsb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                             float beta1, float beta2, float eps, int step, float* grad_norm_sq, cudaStream_t stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || step < 1) { hsb::set_error("hsb_adam_step: bad argument"); return HSB_ERR_ARG; }
+    const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    return hsb::launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2),
+                            grad_norm_sq, stream);
+}

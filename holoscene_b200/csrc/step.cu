@@ -1,0 +1,452 @@
+// Orchestration of the Stage-1 train step on one GPU: SDF-only evaluation (sampler), main ray
+// pass forward / backward, eikonal pass forward / backward, background-patch pass, weight-norm
+// materialisation and backward.  Every phase is a fixed sequence of kernel launches on the caller's
+// stream over a caller-provided workspace; there is no host synchronisation and no allocation.
+//
+// What is replaced (reference file:line):
+//   ObjectImplicitNetworkGrid.forward / get_outputs / gradient / get_sdf_vals   model/network.py:169-318
+//   RenderingNetwork.forward                                                    model/network.py:585-614
+//   HoloSceneNetwork.volume_rendering / occlusion_opacity / composites          model/network.py:815-824,904-913,1803-1824
+//   and the autograd graph that loss.backward() walks through them, including the double backward
+//   through d sdf / d x (model/network.py:293-299, hashencoder/hashgrid.py:71-101).
+//
+// Backward derivation (per point; a1,a2 pre-activations, h = softplus_100(a), sg = softplus'(a)):
+//   forward chain   p2 = W2[k*] * sg2 ; q1 = W1^T p2 ; p1 = q1 * sg1 ; q0 = W0^T p1 ; g = (dh0/dx)^T q0
+//   given dg:       dq0 = (dh0/dx) dg ; dp1 = W0 dq0 ; dq1 = dp1*sg1 ; da1 += dp1*p1*100(1-sg1)
+//                   dp2 = W1 dq1 ; dq2 = dp2*sg2 ; da2 += dp2*p2*100(1-sg2) ; dW2[k*] += dq2
+//                   dW0 += p1 dq0^T ; dW1 += p2 dq1^T ; d(table) += 2nd-order scatter(q0_E, dg)
+//   given ds:       dh2 = W2^T ds ; da2 += dh2*sg2 ; dh1 = W1^T da2 ; da1 += dh1*sg1 ; dh0 = W0^T da1
+//                   dW2 += ds h2^T ; dW1 += da2 h1^T ; dW0 += da1 h0^T ; d(table) += scatter(dh0_E)
+#include "common.cuh"
+#include "step.cuh"
+#include "../../include/hsb200.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+namespace hsb {
+
+enum Seg {
+    SEG_EMB = 0, SEG_CEMB, SEG_C0W, SEG_C0B, SEG_C1W, SEG_C1B,
+    SEG_L0B, SEG_L0G, SEG_L0V, SEG_L1B, SEG_L1G, SEG_L1V, SEG_L2B, SEG_L2G, SEG_L2V,
+    SEG_R0B, SEG_R0G, SEG_R0V, SEG_R1B, SEG_R1G, SEG_R1V, SEG_R2B, SEG_R2G, SEG_R2V, SEG_BETA, SEG_COUNT
+};
+
+static void param_layout(int K, long long rows, long long* off) {
+    const long long sz[SEG_COUNT] = {rows * 2, rows * 2, 256 * 32, 256, 256 * 256, 256,
+                                     256, 256, 256 * 71, 256, 256, 256 * 256, K, K, (long long)K * 256,
+                                     256, 256, 256 * 337, 256, 256, 256 * 256, 3, 3, 3 * 256, 1};
+    long long o = 0;
+    for (int i = 0; i < SEG_COUNT; ++i) {
+        off[i] = o;
+        o += (sz[i] + 3) / 4 * 4;
+    }
+    off[SEG_COUNT] = o;
+}
+
+struct NamedBuf { std::string name; long long offset_bytes, rows, ld; };
+
+// buffers of one point batch
+struct Slot {
+    long long cap_points = 0, cap_rows = 0;   // cap_rows = points * max seeds
+    int cap_rays = 0;
+    bool with_color = false;
+    // forward state of the last call
+    long long N = 0; int R = 0, S = 0, nseed = 1, mode = 0;
+    float *X, *H0, *DY, *H1, *H2, *SR, *SDF, *P2, *P1, *Q0, *G;
+    int* KS;
+    float *EC, *C1, *RIN, *U1, *U2, *RGB, *W, *T, *WSUM, *WZSUM, *ZV, *DSCALE, *ROT;
+    // backward temporaries
+    float *dO, *dS, *dG, *dQ0, *dQ1, *dA1x, *dQ2, *dA2x, *dA2, *dA1, *dH0E, *dU2, *dU1, *dRIN, *dFEAT, *dC1, *dEC;
+};
+
+struct Ctx {
+    hsb_step_cfg cfg;
+    int K, Kp;
+    long long off[SEG_COUNT + 1];
+    float* params; float* grads;
+    const int32_t* hoffs;
+    char* ws; size_t ws_bytes; size_t ws_used;
+    std::vector<NamedBuf> names;
+    // derived weights
+    float *W0e, *W0eT, *W1e, *W1eT, *W2e, *W2eT, *C0T, *C1T, *R0e, *R0eT, *R1e, *R1eT, *R2e;
+    // effective-weight gradient accumulators (zeroed by hsb_prepare)
+    float *dW0e, *dW1e, *dW2e, *dB2e, *dR0e, *dR1e, *dR2e, *dRB2e;
+    char* dwe_begin; size_t dwe_bytes;
+    Slot slot[3];
+    float* P(int seg) const { return params + off[seg]; }
+    float* Gp(int seg) const { return grads + off[seg]; }
+};
+
+static float* carve(Ctx* c, const char* name, long long rows, long long ld, bool dry) {
+    size_t bytes = ((size_t)rows * ld * sizeof(float) + 255) / 256 * 256;
+    size_t o = c->ws_used;
+    c->ws_used += bytes;
+    if (dry) return nullptr;
+    c->names.push_back({name, (long long)o, rows, ld});
+    return reinterpret_cast<float*>(c->ws + o);
+}
+
+static void carve_slot(Ctx* c, int idx, const char* pre, long long points, int max_seeds, int rays, bool color, bool dry) {
+    Slot& s = c->slot[idx];
+    s.cap_points = points; s.cap_rows = points * max_seeds; s.cap_rays = rays; s.with_color = color;
+    const long long N = points, E = s.cap_rows;
+    const int Kp = c->Kp;
+    auto nm = [&](const char* n) { static char b[64]; snprintf(b, sizeof b, "%s.%s", pre, n); return (const char*)b; };
+    s.X = carve(c, nm("X"), N, 3, dry);        s.H0 = carve(c, nm("H0"), N, LD_H0, dry);  s.DY = carve(c, nm("DY"), N, 96, dry);
+    s.H1 = carve(c, nm("H1"), N, 256, dry);    s.H2 = carve(c, nm("H2"), N, 256, dry);    s.SR = carve(c, nm("SR"), N, Kp, dry);
+    s.SDF = carve(c, nm("SDF"), N, 1, dry);    s.KS = (int*)carve(c, nm("KS"), N, 1, dry);
+    s.P2 = carve(c, nm("P2"), E, 256, dry);    s.P1 = carve(c, nm("P1"), E, 256, dry);    s.Q0 = carve(c, nm("Q0"), E, LD_H0, dry);
+    s.G = carve(c, nm("G"), E, 3, dry);
+    s.dS = carve(c, nm("dS"), N, Kp, dry);     s.dG = carve(c, nm("dG"), E, 3, dry);      s.dQ0 = carve(c, nm("dQ0"), E, LD_H0, dry);
+    s.dQ1 = carve(c, nm("dQ1"), E, 256, dry);  s.dA1x = carve(c, nm("dA1x"), N, 256, dry);
+    s.dQ2 = carve(c, nm("dQ2"), E, 256, dry);  s.dA2x = carve(c, nm("dA2x"), N, 256, dry);
+    s.dA2 = carve(c, nm("dA2"), N, 256, dry);  s.dA1 = carve(c, nm("dA1"), N, 256, dry);  s.dH0E = carve(c, nm("dH0E"), N, 32, dry);
+    if (rays > 0) {
+        s.W = carve(c, nm("W"), N, 1, dry);    s.T = carve(c, nm("T"), N, 1, dry);        s.ZV = carve(c, nm("ZV"), N, 1, dry);
+        s.WSUM = carve(c, nm("WSUM"), rays, 1, dry); s.WZSUM = carve(c, nm("WZSUM"), rays, 1, dry);
+        s.DSCALE = carve(c, nm("DSCALE"), rays, 1, dry); s.ROT = carve(c, nm("ROT"), 16, 1, dry);
+    }
+    if (color) {
+        s.EC = carve(c, nm("EC"), N, 32, dry);     s.C1 = carve(c, nm("C1"), N, 256, dry);   s.RIN = carve(c, nm("RIN"), N, LD_RIN, dry);
+        s.U1 = carve(c, nm("U1"), N, 256, dry);    s.U2 = carve(c, nm("U2"), N, 256, dry);   s.RGB = carve(c, nm("RGB"), N, 4, dry);
+        s.dO = carve(c, nm("dO"), N, 4, dry);      s.dU2 = carve(c, nm("dU2"), N, 256, dry); s.dU1 = carve(c, nm("dU1"), N, 256, dry);
+        s.dRIN = carve(c, nm("dRIN"), N, LD_RIN, dry); s.dFEAT = carve(c, nm("dFEAT"), N, 256, dry);
+        s.dC1 = carve(c, nm("dC1"), N, 256, dry);  s.dEC = carve(c, nm("dEC"), N, 32, dry);
+    }
+}
+
+static void carve_all(Ctx* c, bool dry) {
+    c->ws_used = 0;
+    const int Kp = c->Kp;
+    c->W0e = carve(c, "W0e", 256, LD_H0, dry);   c->W0eT = carve(c, "W0eT", LD_H0, 256, dry);
+    c->W1e = carve(c, "W1e", 256, 256, dry);     c->W1eT = carve(c, "W1eT", 256, 256, dry);
+    c->W2e = carve(c, "W2e", Kp, 256, dry);      c->W2eT = carve(c, "W2eT", 256, Kp, dry);
+    c->C0T = carve(c, "C0T", 32, 256, dry);      c->C1T = carve(c, "C1T", 256, 256, dry);
+    c->R0e = carve(c, "R0e", 256, LD_RIN, dry);  c->R0eT = carve(c, "R0eT", LD_RIN, 256, dry);
+    c->R1e = carve(c, "R1e", 256, 256, dry);     c->R1eT = carve(c, "R1eT", 256, 256, dry);
+    c->R2e = carve(c, "R2e", 4, 256, dry);
+    size_t begin = c->ws_used;
+    c->dW0e = carve(c, "dW0e", 256, LD_H0, dry); c->dW1e = carve(c, "dW1e", 256, 256, dry);
+    c->dW2e = carve(c, "dW2e", Kp, 256, dry);    c->dB2e = carve(c, "dB2e", Kp, 1, dry);
+    c->dR0e = carve(c, "dR0e", 256, LD_RIN, dry); c->dR1e = carve(c, "dR1e", 256, 256, dry);
+    c->dR2e = carve(c, "dR2e", 4, 256, dry);     c->dRB2e = carve(c, "dRB2e", 4, 1, dry);
+    c->dwe_bytes = c->ws_used - begin;
+    if (!dry) c->dwe_begin = c->ws + begin;
+    carve_slot(c, HSB_SLOT_MAIN, "main", c->cfg.max_points, 1, c->cfg.max_rays, true, dry);
+    carve_slot(c, HSB_SLOT_EIK, "eik", c->cfg.max_eik_points, c->K + 1, 0, false, dry);
+    carve_slot(c, HSB_SLOT_BG, "bg", c->cfg.max_bg_points, 1, c->cfg.max_bg_rays, false, dry);
+}
+
+#define TRY(x) do { int _e = (x); if (_e != HSB_OK) return _e; } while (0)
+
+static Epi epi(int kind, float* out, long long ldo) { Epi e{}; e.kind = kind; e.out = out; e.ldo = ldo; return e; }
+
+// ---- SDF net forward: hash features -> H0[:,39:71] (+dy_dx), H1, H2, SR (PE part of H0 must be filled) ----
+static int sdf_forward(Ctx* c, Slot& s, long long N, bool need_dy, cudaStream_t st) {
+    const hsb_step_cfg& f = c->cfg;
+    const int P = f.precise;
+    TRY(hsb_hash_forward(s.X, c->P(SEG_EMB), c->hoffs, s.H0 + 39, 2, LD_H0, need_dy ? s.DY : nullptr, 96, (uint32_t)N, f.L, f.S, f.H, 1, st));
+    Epi e = epi(EPI_BIAS_SOFTPLUS, s.H1, 256); e.bias = c->P(SEG_L0B);
+    TRY(gemm_tn(s.H0, LD_H0, c->W0e, LD_H0, N, 256, LD_H0, e, P, st));
+    e = epi(EPI_BIAS_SOFTPLUS, s.H2, 256); e.bias = c->P(SEG_L1B);
+    TRY(gemm_tn(s.H1, 256, c->W1e, 256, N, 256, 256, e, P, st));
+    e = epi(EPI_BIAS, s.SR, c->Kp); e.bias = c->P(SEG_L2B);
+    TRY(gemm_tn(s.H2, 256, c->W2e, 256, N, c->K, 256, e, P, st));
+    return HSB_OK;
+}
+
+// ---- input-gradient chain forward for nseed seeds (rows = nseed*N) -> G (+PE4(g) into RIN) ----
+static int chain_forward(Ctx* c, Slot& s, long long N, int nseed, cudaStream_t st) {
+    const int P = c->cfg.precise;
+    const long long E = N * nseed;
+    TRY(launch_chain_seed(c->W2e, s.H2, s.KS, N, c->K, nseed, s.P2, st));
+    Epi e = epi(EPI_MUL_SIGMA, s.P1, 256); e.aux = s.H1; e.lda = 256; e.aux_rows = N;
+    TRY(gemm_tn(s.P2, 256, c->W1eT, 256, E, 256, 256, e, P, st));        // q1 = p2 W1 ; p1 = q1*sg1
+    e = epi(EPI_NONE, s.Q0, LD_H0);
+    TRY(gemm_tn(s.P1, 256, c->W0eT, 256, E, LD_H0, 256, e, P, st));      // q0 = p1 W0
+    TRY(launch_chain_end(s.Q0, s.H0, s.DY, N, nseed, s.G, s.with_color ? s.RIN : nullptr, st));
+    return HSB_OK;
+}
+
+// ---- backward of the chain given dG [E,3] (main pass: + PE4(g) term from dRIN) ----
+static int chain_backward(Ctx* c, Slot& s, long long N, int nseed, bool with_rin, cudaStream_t st) {
+    const hsb_step_cfg& f = c->cfg;
+    const int P = f.precise;
+    const long long E = N * nseed;
+    TRY(launch_chain_end_bwd(s.dG, with_rin ? s.dRIN : nullptr, with_rin ? s.RIN : nullptr, s.H0, s.DY, N, nseed, s.dQ0, st));
+    const int atomic = nseed > 1;
+    if (atomic) {
+        cudaMemsetAsync(s.dA1x, 0, (size_t)N * 256 * sizeof(float), st);
+        cudaMemsetAsync(s.dA2x, 0, (size_t)N * 256 * sizeof(float), st);
+    }
+    Epi e = epi(EPI_BWD_CHAIN, s.dQ1, 256);
+    e.aux = s.H1; e.lda = 256; e.aux_rows = N; e.aux2 = s.P1; e.lda2 = 256; e.out2 = s.dA1x; e.ldo2 = 256; e.atomic2 = atomic;
+    TRY(gemm_tn(s.dQ0, LD_H0, c->W0e, LD_H0, E, 256, LD_H0, e, P, st));  // dp1 = dq0 W0^T
+    TRY(gemm_wgrad(s.P1, 256, 256, s.dQ0, LD_H0, LD_H0, E, c->dW0e, LD_H0, nullptr, P, st));
+    e = epi(EPI_BWD_CHAIN, s.dQ2, 256);
+    e.aux = s.H2; e.lda = 256; e.aux_rows = N; e.aux2 = s.P2; e.lda2 = 256; e.out2 = s.dA2x; e.ldo2 = 256; e.atomic2 = atomic;
+    TRY(gemm_tn(s.dQ1, 256, c->W1e, 256, E, 256, 256, e, P, st));        // dp2 = dq1 W1^T
+    TRY(gemm_wgrad(s.P2, 256, 256, s.dQ1, 256, 256, E, c->dW1e, 256, nullptr, P, st));
+    TRY(launch_scatter_rows(s.dQ2, s.KS, N, c->K, c->Kp, nseed, c->dW2e, st));
+    return HSB_OK;
+}
+
+// ---- SDF net backward given dS [N,Kp] and the chain's extra terms dA1x / dA2x (may be absent) ----
+static int sdf_backward(Ctx* c, Slot& s, long long N, int nseed, bool have_chain, cudaStream_t st) {
+    const hsb_step_cfg& f = c->cfg;
+    const int P = f.precise;
+    Epi e = epi(EPI_BWD_SP, s.dA2, 256); e.aux = s.H2; e.lda = 256; e.aux2 = have_chain ? s.dA2x : nullptr; e.lda2 = 256;
+    TRY(gemm_tn(s.dS, c->Kp, c->W2eT, c->Kp, N, 256, c->Kp, e, P, st));  // dh2 = ds W2
+    TRY(gemm_wgrad(s.dS, c->Kp, c->Kp, s.H2, 256, 256, N, c->dW2e, 256, c->dB2e, P, st));
+    e = epi(EPI_BWD_SP, s.dA1, 256); e.aux = s.H1; e.lda = 256; e.aux2 = have_chain ? s.dA1x : nullptr; e.lda2 = 256;
+    TRY(gemm_tn(s.dA2, 256, c->W1eT, 256, N, 256, 256, e, P, st));       // dh1 = da2 W1
+    TRY(gemm_wgrad(s.dA2, 256, 256, s.H1, 256, 256, N, c->dW1e, 256, c->Gp(SEG_L1B), P, st));
+    e = epi(EPI_NONE, s.dH0E, 32);
+    TRY(gemm_tn(s.dA1, 256, c->W0eT + 39 * 256, 256, N, 32, 256, e, P, st));   // dE = (da1 W0)[:, 39:71]
+    TRY(gemm_wgrad(s.dA1, 256, 256, s.H0, LD_H0, LD_H0, N, c->dW0e, LD_H0, c->Gp(SEG_L0B), P, st));
+    TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dH0E, 32, have_chain ? s.Q0 + 39 : nullptr, LD_H0, have_chain ? s.dG : nullptr,
+                                (uint32_t)nseed, c->Gp(SEG_EMB), (uint32_t)N, f.L, f.S, f.H, st));
+    return HSB_OK;
+}
+
+static CompositeArgs composite_args(Ctx* c, Slot& s, int mode) {
+    CompositeArgs a{};
+    a.R = s.R; a.S = s.S; a.K = c->K; a.Kp = c->Kp; a.mode = mode;
+    a.Z = s.ZV; a.SDF = s.SDF; a.SR = s.SR; a.KS = s.KS; a.RGB = s.RGB; a.G = s.G;
+    a.depth_scale = s.DSCALE; a.rot = s.ROT; a.beta_param = c->P(SEG_BETA);
+    a.beta_min = c->cfg.beta_min; a.sigmoid_scale = c->cfg.sigmoid_scale;
+    a.W = s.W; a.T = s.T; a.wsum = s.WSUM; a.wzsum = s.WZSUM;
+    return a;
+}
+
+}  // namespace hsb
+
+using namespace hsb;
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" int hsb_param_layout(int32_t K, int64_t table_rows, int64_t* offsets_out) {
+    if (K < 1 || K > HSB_MAX_K || table_rows < 1 || !offsets_out) { set_error("hsb_param_layout: bad argument"); return HSB_ERR_ARG; }
+    long long off[SEG_COUNT + 1];
+    param_layout(K, table_rows, off);
+    for (int i = 0; i <= SEG_COUNT; ++i) offsets_out[i] = off[i];
+    return HSB_OK;
+}
+
+static int validate_cfg(const hsb_step_cfg* cfg) {
+    if (!cfg || cfg->K < 1 || cfg->K > HSB_MAX_K || cfg->L != 16 || cfg->table_rows < 1 || cfg->max_points < 1 ||
+        cfg->max_rays < 1 || cfg->max_eik_points < 0 || cfg->max_bg_points < 0) {
+        set_error("hsb_step_cfg: unsupported configuration (need 1 <= K <= 64, L == 16, positive capacities)");
+        return HSB_ERR_ARG;
+    }
+    return HSB_OK;
+}
+
+extern "C" int hsb_ctx_workspace_bytes(const hsb_step_cfg* cfg, uint64_t* bytes_out) {
+    TRY(validate_cfg(cfg));
+    Ctx c{};
+    c.cfg = *cfg; c.K = cfg->K; c.Kp = (cfg->K + 7) / 8 * 8;
+    carve_all(&c, true);
+    *bytes_out = c.ws_used;
+    return HSB_OK;
+}
+
+extern "C" int hsb_ctx_create(const hsb_step_cfg* cfg, float* params, float* grads, const int32_t* hash_offsets,
+                              void* workspace, uint64_t workspace_bytes, hsb_ctx** out) {
+    TRY(validate_cfg(cfg));
+    if (!params || !grads || !hash_offsets || !workspace || !out) { set_error("hsb_ctx_create: null pointer"); return HSB_ERR_ARG; }
+    Ctx* c = new Ctx();
+    c->cfg = *cfg; c->K = cfg->K; c->Kp = (cfg->K + 7) / 8 * 8;
+    param_layout(c->K, cfg->table_rows, c->off);
+    c->params = params; c->grads = grads; c->hoffs = hash_offsets;
+    c->ws = (char*)workspace; c->ws_bytes = workspace_bytes;
+    carve_all(c, true);
+    if (c->ws_used > workspace_bytes || ((uintptr_t)workspace & 255)) {
+        delete c;
+        set_error("hsb_ctx_create: workspace too small or not 256-byte aligned");
+        return HSB_ERR_ARG;
+    }
+    carve_all(c, false);
+    *out = reinterpret_cast<hsb_ctx*>(c);
+    return HSB_OK;
+}
+
+extern "C" void hsb_ctx_destroy(hsb_ctx* h) { delete reinterpret_cast<Ctx*>(h); }
+
+extern "C" int hsb_ctx_buffer(hsb_ctx* h, const char* name, int64_t* offset_bytes, int64_t* rows, int64_t* ld) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    for (auto& n : c->names)
+        if (n.name == name) { *offset_bytes = n.offset_bytes; *rows = n.rows; *ld = n.ld; return HSB_OK; }
+    set_error("hsb_ctx_buffer: unknown buffer name");
+    return HSB_ERR_ARG;
+}
+
+// derived weights for this step + zero the effective-weight gradient accumulators
+extern "C" int hsb_prepare(hsb_ctx* h, cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    cudaMemsetAsync(c->dwe_begin, 0, c->dwe_bytes, st);
+    cudaMemsetAsync(c->W0eT, 0, (size_t)LD_H0 * 256 * sizeof(float), st);
+    cudaMemsetAsync(c->R0eT, 0, (size_t)LD_RIN * 256 * sizeof(float), st);
+    cudaMemsetAsync(c->W2e, 0, (size_t)c->Kp * 256 * sizeof(float), st);
+    cudaMemsetAsync(c->W2eT, 0, (size_t)c->Kp * 256 * sizeof(float), st);
+    cudaMemsetAsync(c->R2e, 0, (size_t)4 * 256 * sizeof(float), st);
+    TRY(launch_wn_forward(c->P(SEG_L0V), c->P(SEG_L0G), 256, 71, c->W0e, LD_H0, c->W0eT, 256, st));
+    TRY(launch_wn_forward(c->P(SEG_L1V), c->P(SEG_L1G), 256, 256, c->W1e, 256, c->W1eT, 256, st));
+    TRY(launch_wn_forward(c->P(SEG_L2V), c->P(SEG_L2G), c->K, 256, c->W2e, 256, c->W2eT, c->Kp, st));
+    TRY(launch_wn_forward(c->P(SEG_R0V), c->P(SEG_R0G), 256, 337, c->R0e, LD_RIN, c->R0eT, 256, st));
+    TRY(launch_wn_forward(c->P(SEG_R1V), c->P(SEG_R1G), 256, 256, c->R1e, 256, c->R1eT, 256, st));
+    TRY(launch_wn_forward(c->P(SEG_R2V), c->P(SEG_R2G), 3, 256, c->R2e, 256, nullptr, 0, st));
+    TRY(launch_transpose(c->P(SEG_C0W), 256, 32, c->C0T, 256, st));
+    TRY(launch_transpose(c->P(SEG_C1W), 256, 256, c->C1T, 256, st));
+    return HSB_OK;
+}
+
+// weight-norm backward: effective-weight gradients -> (weight_v, weight_g, small biases) in the flat gradient buffer
+extern "C" int hsb_finish(hsb_ctx* h, cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    TRY(launch_wn_backward(c->dW0e, LD_H0, c->P(SEG_L0V), c->P(SEG_L0G), 256, 71, c->Gp(SEG_L0V), c->Gp(SEG_L0G), st));
+    TRY(launch_wn_backward(c->dW1e, 256, c->P(SEG_L1V), c->P(SEG_L1G), 256, 256, c->Gp(SEG_L1V), c->Gp(SEG_L1G), st));
+    TRY(launch_wn_backward(c->dW2e, 256, c->P(SEG_L2V), c->P(SEG_L2G), c->K, 256, c->Gp(SEG_L2V), c->Gp(SEG_L2G), st));
+    TRY(launch_wn_backward(c->dR0e, LD_RIN, c->P(SEG_R0V), c->P(SEG_R0G), 256, 337, c->Gp(SEG_R0V), c->Gp(SEG_R0G), st));
+    TRY(launch_wn_backward(c->dR1e, 256, c->P(SEG_R1V), c->P(SEG_R1G), 256, 256, c->Gp(SEG_R1V), c->Gp(SEG_R1G), st));
+    TRY(launch_wn_backward(c->dR2e, 256, c->P(SEG_R2V), c->P(SEG_R2G), 3, 256, c->Gp(SEG_R2V), c->Gp(SEG_R2G), st));
+    // padded bias accumulators -> exact-size bias gradients
+    TRY(launch_add_into(c->dB2e, c->Gp(SEG_L2B), c->K, st));
+    TRY(launch_add_into(c->dRB2e, c->Gp(SEG_R2B), 3, st));
+    return HSB_OK;
+}
+
+// SDF values (min over K, or one channel) at the points o + z d of a ray batch -- the sampler's no-grad queries
+// (model/ray_sampler.py:150-156).  Uses the main slot's forward buffers as scratch.
+extern "C" int hsb_sdf_values(hsb_ctx* h, const float* o, const float* d, const float* z, int32_t R, int32_t S, int32_t channel,
+                              float* sdf_out, cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    Slot& s = c->slot[HSB_SLOT_MAIN];
+    const long long N = (long long)R * S;
+    if (N > s.cap_points || channel >= c->K) { set_error("hsb_sdf_values: batch exceeds max_points / bad channel"); return HSB_ERR_ARG; }
+    TRY(launch_ray_points(o, d, z, R, S, s.X, s.H0, nullptr, st));
+    TRY(sdf_forward(c, s, N, false, st));
+    TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, channel, sdf_out, nullptr, st));
+    return HSB_OK;
+}
+
+extern "C" int hsb_render_forward(hsb_ctx* h, int32_t slot_id, const float* o, const float* d, const float* z, int32_t R, int32_t S,
+                                  const float* depth_scale, const float* rot, float* rgb_values, float* depth_values,
+                                  float* normal_map, float* opacity, float* semantic, cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (slot_id != HSB_SLOT_MAIN && slot_id != HSB_SLOT_BG) { set_error("hsb_render_forward: bad slot"); return HSB_ERR_ARG; }
+    Slot& s = c->slot[slot_id];
+    const long long N = (long long)R * S;
+    if (N > s.cap_points || R > s.cap_rays) { set_error("hsb_render_forward: batch exceeds slot capacity"); return HSB_ERR_ARG; }
+    const bool scene = slot_id == HSB_SLOT_MAIN;
+    const hsb_step_cfg& f = c->cfg;
+    const int P = f.precise;
+    s.N = N; s.R = R; s.S = S; s.nseed = 1; s.mode = scene ? 0 : 1;
+    cudaMemcpyAsync(s.ZV, z, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(s.DSCALE, depth_scale, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(s.ROT, rot, 9 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    TRY(launch_ray_points(o, d, z, R, S, s.X, s.H0, scene ? s.RIN : nullptr, st));
+    TRY(sdf_forward(c, s, N, true, st));
+    TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, -1, s.SDF, s.KS, st));
+    TRY(chain_forward(c, s, N, 1, st));
+    if (scene) {
+        TRY(hsb_hash_forward(s.X, c->P(SEG_CEMB), c->hoffs, s.EC, 2, 32, nullptr, 0, (uint32_t)N, f.L, f.S, f.H, 1, st));
+        Epi e = epi(EPI_BIAS_RELU, s.C1, 256); e.bias = c->P(SEG_C0B);
+        TRY(gemm_tn(s.EC, 32, c->P(SEG_C0W), 32, N, 256, 32, e, P, st));
+        e = epi(EPI_BIAS, s.RIN + 81, LD_RIN); e.bias = c->P(SEG_C1B);
+        TRY(gemm_tn(s.C1, 256, c->P(SEG_C1W), 256, N, 256, 256, e, P, st));
+        e = epi(EPI_BIAS_RELU, s.U1, 256); e.bias = c->P(SEG_R0B);
+        TRY(gemm_tn(s.RIN, LD_RIN, c->R0e, LD_RIN, N, 256, LD_RIN, e, P, st));
+        e = epi(EPI_BIAS_RELU, s.U2, 256); e.bias = c->P(SEG_R1B);
+        TRY(gemm_tn(s.U1, 256, c->R1e, 256, N, 256, 256, e, P, st));
+        TRY(launch_rgb_head(s.U2, c->R2e, c->P(SEG_R2B), N, s.RGB, st));
+    }
+    CompositeArgs a = composite_args(c, s, s.mode);
+    a.rgb_values = rgb_values; a.depth_values = depth_values; a.normal_map = normal_map; a.opacity = opacity; a.semantic = semantic;
+    if (!depth_values || !normal_map || !semantic || (scene && (!rgb_values || !opacity))) { set_error("hsb_render_forward: null output"); return HSB_ERR_ARG; }
+    TRY(launch_composite_fwd(a, st));
+    return HSB_OK;
+}
+
+extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_rgb_values, const float* d_depth_values,
+                                   const float* d_normal_map, const float* d_opacity, cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (slot_id != HSB_SLOT_MAIN && slot_id != HSB_SLOT_BG) { set_error("hsb_render_backward: bad slot"); return HSB_ERR_ARG; }
+    Slot& s = c->slot[slot_id];
+    if (s.N == 0) { set_error("hsb_render_backward: no forward recorded in this slot"); return HSB_ERR_ARG; }
+    const bool scene = slot_id == HSB_SLOT_MAIN;
+    const hsb_step_cfg& f = c->cfg;
+    const int P = f.precise;
+    const long long N = s.N;
+    CompositeArgs a = composite_args(c, s, s.mode);
+    CompositeGrads g{};
+    g.d_rgb_values = d_rgb_values; g.d_depth_values = d_depth_values; g.d_normal_map = d_normal_map; g.d_opacity = d_opacity;
+    g.dO = s.dO; g.dS = s.dS; g.dGn = s.dG; g.d_beta = c->Gp(SEG_BETA);
+    TRY(launch_composite_bwd(a, g, st));
+    if (scene) {
+        // render net
+        TRY(launch_rgb_head_bwd(s.dO, c->R2e, s.U2, N, s.dU2, st));
+        TRY(gemm_wgrad(s.dO, 4, 4, s.U2, 256, 256, N, c->dR2e, 256, c->dRB2e, P, st));
+        Epi e = epi(EPI_BWD_RELU, s.dU1, 256); e.aux = s.U1; e.lda = 256;
+        TRY(gemm_tn(s.dU2, 256, c->R1eT, 256, N, 256, 256, e, P, st));
+        TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, c->Gp(SEG_R1B), P, st));
+        e = epi(EPI_NONE, s.dRIN + 54, LD_RIN);
+        TRY(gemm_tn(s.dU1, 256, c->R0eT + 54 * 256, 256, N, 27, 256, e, P, st));     // d PE4(grad)
+        e = epi(EPI_NONE, s.dFEAT, 256);
+        TRY(gemm_tn(s.dU1, 256, c->R0eT + 81 * 256, 256, N, 256, 256, e, P, st));    // d feature
+        TRY(gemm_wgrad(s.dU1, 256, 256, s.RIN, LD_RIN, LD_RIN, N, c->dR0e, LD_RIN, c->Gp(SEG_R0B), P, st));
+        // colour-feature MLP + colour hash grid
+        TRY(gemm_wgrad(s.dFEAT, 256, 256, s.C1, 256, 256, N, c->Gp(SEG_C1W), 256, c->Gp(SEG_C1B), P, st));
+        e = epi(EPI_BWD_RELU, s.dC1, 256); e.aux = s.C1; e.lda = 256;
+        TRY(gemm_tn(s.dFEAT, 256, c->C1T, 256, N, 256, 256, e, P, st));
+        TRY(gemm_wgrad(s.dC1, 256, 256, s.EC, 32, 32, N, c->Gp(SEG_C0W), 32, c->Gp(SEG_C0B), P, st));
+        e = epi(EPI_NONE, s.dEC, 32);
+        TRY(gemm_tn(s.dC1, 256, c->C0T, 256, N, 32, 256, e, P, st));
+        TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dEC, 32, nullptr, 0, nullptr, 1, c->Gp(SEG_CEMB), (uint32_t)N, f.L, f.S, f.H, st));
+    }
+    TRY(chain_backward(c, s, N, 1, scene, st));
+    TRY(sdf_backward(c, s, N, 1, true, st));
+    return HSB_OK;
+}
+
+// Eikonal pass (network.py:843-866): K per-channel gradients + the min-SDF gradient at Ne points,
+// stacked [(K+1)*Ne, 3] (channel-major, min last), plus sample_sdf [Ne,K] and sample_minsdf [Ne].
+extern "C" int hsb_eikonal_forward(hsb_ctx* h, const float* x, int64_t Ne, float* grad_theta, float* sample_sdf,
+                                   float* sample_minsdf, cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    Slot& s = c->slot[HSB_SLOT_EIK];
+    if (Ne > s.cap_points || !x || !grad_theta) { set_error("hsb_eikonal_forward: batch exceeds max_eik_points / null pointer"); return HSB_ERR_ARG; }
+    const int ns = c->K + 1;
+    s.N = Ne; s.nseed = ns;
+    cudaMemcpyAsync(s.X, x, (size_t)Ne * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    TRY(launch_points_pe(s.X, Ne, s.H0, st));
+    TRY(sdf_forward(c, s, Ne, true, st));
+    TRY(launch_sdf_min(s.SR, Ne, c->K, c->Kp, -1, s.SDF, s.KS, st));
+    TRY(chain_forward(c, s, Ne, ns, st));
+    cudaMemcpyAsync(grad_theta, s.G, (size_t)Ne * ns * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (sample_sdf)
+        cudaMemcpy2DAsync(sample_sdf, (size_t)c->K * sizeof(float), s.SR, (size_t)c->Kp * sizeof(float), (size_t)c->K * sizeof(float),
+                          (size_t)Ne, cudaMemcpyDeviceToDevice, st);
+    if (sample_minsdf) cudaMemcpyAsync(sample_minsdf, s.SDF, (size_t)Ne * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    return check_launch("hsb_eikonal_forward");
+}
+
+extern "C" int hsb_eikonal_backward(hsb_ctx* h, const float* d_grad_theta, const float* d_sample_sdf, cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    Slot& s = c->slot[HSB_SLOT_EIK];
+    if (s.N == 0 || !d_grad_theta) { set_error("hsb_eikonal_backward: no forward recorded / null gradient"); return HSB_ERR_ARG; }
+    const long long Ne = s.N;
+    const int ns = s.nseed;
+    cudaMemcpyAsync(s.dG, d_grad_theta, (size_t)Ne * ns * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    cudaMemsetAsync(s.dS, 0, (size_t)Ne * c->Kp * sizeof(float), st);
+    if (d_sample_sdf)
+        cudaMemcpy2DAsync(s.dS, (size_t)c->Kp * sizeof(float), d_sample_sdf, (size_t)c->K * sizeof(float), (size_t)c->K * sizeof(float),
+                          (size_t)Ne, cudaMemcpyDeviceToDevice, st);
+    TRY(chain_backward(c, s, Ne, ns, false, st));
+    TRY(sdf_backward(c, s, Ne, ns, true, st));
+    return HSB_OK;
+}

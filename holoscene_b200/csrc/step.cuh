@@ -1,0 +1,55 @@
+// Internal declarations shared by the train-step kernels and their orchestration (step.cu).
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+#define HSB_MAX_K 64
+
+namespace hsb {
+
+constexpr int LD_H0 = 72;    // SDF-net input row: PE6(x) [0,39) | hash features [39,71) | pad
+constexpr int LD_RIN = 344;  // render-net input row: PE4(x) [0,27) | PE4(view) [27,54) | PE4(grad) [54,81) | feature [81,337) | pad
+constexpr int HID = 256;
+
+struct CompositeArgs {
+    int R, S, K, Kp, mode;
+    const float* Z;        // [R,S]
+    const float* SDF;      // [P]   scene (min) sdf
+    const float* SR;       // [P,Kp] per-object sdf
+    const int* KS;         // [P]   arg-min channel
+    const float* RGB;      // [P,4]
+    const float* G;        // [P,3]  d sdf / d x
+    const float* depth_scale;  // [R]
+    const float* rot;      // [9] row-major pose[:3,:3]^T
+    const float* beta_param;
+    float beta_min, sigmoid_scale;
+    float* W; float* T;    // [P]
+    float* rgb_values; float* depth_values; float* normal_map; float* opacity; float* semantic;
+    float* wsum; float* wzsum;   // [R]
+};
+struct CompositeGrads {
+    const float* d_rgb_values; const float* d_depth_values; const float* d_normal_map; const float* d_opacity;
+    float* dO; float* dS; float* dGn; float* d_beta;
+};
+
+int launch_ray_points(const float* o, const float* d, const float* z, int R, int S, float* X, float* H0, float* RIN, cudaStream_t st);
+int launch_points_pe(const float* X, long long N, float* H0, cudaStream_t st);
+int launch_sdf_min(const float* SR, long long N, int K, int Kp, int channel, float* sdf, int* kstar, cudaStream_t st);
+int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long long N, int K, int nseed, float* P2, cudaStream_t st);
+int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN, cudaStream_t st);
+int launch_chain_end_bwd(float* dG, const float* dRIN, const float* RIN, const float* H0, const float* DY, long long N, int nseed, float* dQ0, cudaStream_t st);
+int launch_rgb_head(const float* U2, const float* R2e, const float* bias, long long N, float* RGB, cudaStream_t st);
+int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, cudaStream_t st);
+int launch_scatter_rows(const float* dQ2, const int* kstar, long long N, int K, int Kp, int nseed, float* dW2e, cudaStream_t st);
+int launch_add_min_grad(const float* dsdf, const int* kstar, long long N, int Kp, float* dS, cudaStream_t st);
+int launch_composite_fwd(const CompositeArgs& a, cudaStream_t st);
+int launch_composite_bwd(const CompositeArgs& a, const CompositeGrads& g, cudaStream_t st);
+
+// optim.cu
+int launch_wn_forward(const float* v, const float* g, int rows, int cols, float* We, int ldw, float* WeT, int ldt, cudaStream_t st);
+int launch_wn_backward(const float* dWe, int ldw, const float* v, const float* g, int rows, int cols, float* dv, float* dg, cudaStream_t st);
+int launch_add_into(const float* src, float* dst, int n, cudaStream_t st);
+int launch_transpose(const float* W, int rows, int cols, float* WT, int ldt, cudaStream_t st);
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float* gnorm2, cudaStream_t st);
+
+}  // namespace hsb

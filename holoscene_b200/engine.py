@@ -1,0 +1,180 @@
+"""Host-side handle on the fused train-step context of libhsb200 (include/hsb200.h, section B3).
+
+Owns (as torch CUDA tensors, so PyTorch stays the allocator) the flat parameter / gradient buffers
+and the workspace, and exposes one thin method per C-ABI phase.  No computation happens here.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import c_f32, c_f32p, c_int, c_ll, c_stream, c_u32, check, declare, ptr, stream
+
+NUM_SEGMENTS = 25
+SLOT_MAIN, SLOT_EIK, SLOT_BG = 0, 1, 2
+
+SEGMENT_NAMES = [
+    "implicit_network.encoding.embeddings", "implicit_network.color_encoding.embeddings",
+    "implicit_network.color_grid_feature_map_mlp.0.weight", "implicit_network.color_grid_feature_map_mlp.0.bias",
+    "implicit_network.color_grid_feature_map_mlp.2.weight", "implicit_network.color_grid_feature_map_mlp.2.bias",
+    "implicit_network.lin0.bias", "implicit_network.lin0.weight_g", "implicit_network.lin0.weight_v",
+    "implicit_network.lin1.bias", "implicit_network.lin1.weight_g", "implicit_network.lin1.weight_v",
+    "implicit_network.lin2.bias", "implicit_network.lin2.weight_g", "implicit_network.lin2.weight_v",
+    "rendering_network.lin0.bias", "rendering_network.lin0.weight_g", "rendering_network.lin0.weight_v",
+    "rendering_network.lin1.bias", "rendering_network.lin1.weight_g", "rendering_network.lin1.weight_v",
+    "rendering_network.lin2.bias", "rendering_network.lin2.weight_g", "rendering_network.lin2.weight_v",
+    "density.beta",
+]
+
+
+class StepCfg(ctypes.Structure):
+    _fields_ = [("K", ctypes.c_int32), ("L", ctypes.c_int32), ("H", ctypes.c_int32), ("S", ctypes.c_float),
+                ("table_rows", ctypes.c_int64), ("beta_min", ctypes.c_float), ("sigmoid_scale", ctypes.c_float),
+                ("max_points", ctypes.c_int64), ("max_rays", ctypes.c_int32), ("max_eik_points", ctypes.c_int64),
+                ("max_bg_points", ctypes.c_int64), ("max_bg_rays", ctypes.c_int32), ("precise", ctypes.c_int32)]
+
+
+_vp = ctypes.c_void_p
+_param_layout = declare("hsb_param_layout", [ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)])
+_ws_bytes = declare("hsb_ctx_workspace_bytes", [ctypes.POINTER(StepCfg), ctypes.POINTER(ctypes.c_uint64)])
+_ctx_create = declare("hsb_ctx_create", [ctypes.POINTER(StepCfg), _vp, _vp, _vp, _vp, ctypes.c_uint64, ctypes.POINTER(_vp)])
+_lib.lib.hsb_ctx_destroy.argtypes = [_vp]
+_lib.lib.hsb_ctx_destroy.restype = None
+_ctx_buffer = declare("hsb_ctx_buffer", [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                                         ctypes.POINTER(ctypes.c_int64)])
+_prepare = declare("hsb_prepare", [_vp, c_stream])
+_finish = declare("hsb_finish", [_vp, c_stream])
+_sdf_values = declare("hsb_sdf_values", [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, c_stream])
+_render_fwd = declare("hsb_render_forward", [_vp, ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp,
+                                             _vp, _vp, _vp, _vp, _vp, c_stream])
+_render_bwd = declare("hsb_render_backward", [_vp, ctypes.c_int32, _vp, _vp, _vp, _vp, c_stream])
+_eik_fwd = declare("hsb_eikonal_forward", [_vp, _vp, ctypes.c_int64, _vp, _vp, _vp, c_stream])
+_eik_bwd = declare("hsb_eikonal_backward", [_vp, _vp, _vp, c_stream])
+_adam = declare("hsb_adam_step", [_vp, _vp, _vp, _vp, c_ll, c_f32, c_f32, c_f32, c_f32, c_int, _vp, c_stream])
+gemm_tn = declare("hsb_gemm_tn", [_vp, c_ll, _vp, c_ll, c_ll, c_int, c_int, c_int, _vp, c_ll, _vp, _vp, c_ll, c_ll, _vp, c_ll,
+                                  _vp, c_ll, c_int, c_int, c_stream])
+gemm_wgrad = declare("hsb_gemm_wgrad", [_vp, c_ll, c_int, _vp, c_ll, c_int, c_ll, _vp, c_ll, _vp, c_int, c_stream])
+
+
+def param_layout(K: int, table_rows: int) -> list[int]:
+    arr = (ctypes.c_int64 * (NUM_SEGMENTS + 1))()
+    check(_param_layout(K, table_rows, arr))
+    return list(arr)
+
+
+class StepEngine:
+    """One fused-step context on the current CUDA device."""
+
+    def __init__(self, K, table_rows, hash_offsets, S, H=16, L=16, beta_min=1e-4, sigmoid_scale=10.0, max_rays=1024,
+                 max_samples=128, max_sampler_samples=128, max_bg_rays=1024, precise=False, flat_params=None,
+                 flat_grads=None):
+        if not torch.cuda.is_available():
+            raise _lib.HsbError("StepEngine needs a CUDA device (the hot path has no CPU fallback)")
+        self.K, self.L, self.H, self.S = int(K), int(L), int(H), float(S)
+        self.table_rows = int(table_rows)
+        self.offsets = param_layout(self.K, self.table_rows)
+        self.total = self.offsets[-1]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.params = flat_params if flat_params is not None else torch.zeros(self.total, device=dev)
+        self.grads = flat_grads if flat_grads is not None else torch.zeros(self.total, device=dev)
+        assert self.params.numel() == self.total and self.grads.numel() == self.total
+        self.hash_offsets = hash_offsets.to(dev, torch.int32).contiguous()
+        self.max_rays = int(max_rays)
+        self.max_samples = int(max_samples)
+        cfg = StepCfg()
+        cfg.K, cfg.L, cfg.H, cfg.S = self.K, self.L, self.H, self.S
+        cfg.table_rows = self.table_rows
+        cfg.beta_min, cfg.sigmoid_scale = float(beta_min), float(sigmoid_scale)
+        cfg.max_points = self.max_rays * max(int(max_samples), int(max_sampler_samples))
+        cfg.max_rays = self.max_rays
+        cfg.max_eik_points = 4 * self.max_rays
+        cfg.max_bg_points = int(max_bg_rays) * int(max_samples)
+        cfg.max_bg_rays = int(max_bg_rays)
+        cfg.precise = 1 if precise else 0
+        self.cfg = cfg
+        nbytes = ctypes.c_uint64()
+        check(_ws_bytes(ctypes.byref(cfg), ctypes.byref(nbytes)))
+        self.workspace = torch.empty(int(nbytes.value) + 256, dtype=torch.uint8, device=dev)
+        base = self.workspace.data_ptr()
+        self._ws_shift = (-base) % 256
+        self._ws_ptr = base + self._ws_shift
+        h = _vp()
+        check(_ctx_create(ctypes.byref(cfg), ptr(self.params), ptr(self.grads), ptr(self.hash_offsets), _vp(self._ws_ptr),
+                          ctypes.c_uint64(int(nbytes.value)), ctypes.byref(h)))
+        self._h = h
+        self.launch_phases = 0
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            _lib.lib.hsb_ctx_destroy(h)
+            self._h = None
+
+    # ---- views -------------------------------------------------------------------------------------
+    def segment(self, i, flat=None):
+        flat = self.params if flat is None else flat
+        return flat[self.offsets[i]: self.offsets[i + 1]]
+
+    def buffer(self, name: str, dtype=torch.float32):
+        """A workspace buffer as a [rows, ld] tensor view (tests / outputs)."""
+        off, rows, ld = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(_ctx_buffer(self._h, name.encode(), ctypes.byref(off), ctypes.byref(rows), ctypes.byref(ld)))
+        start = self._ws_shift + off.value
+        n = rows.value * ld.value
+        return self.workspace[start: start + 4 * n].view(dtype).view(rows.value, ld.value)
+
+    # ---- phases ------------------------------------------------------------------------------------
+    def prepare(self):
+        check(_prepare(self._h, stream()))
+
+    def finish(self):
+        check(_finish(self._h, stream()))
+
+    def sdf_values(self, o, d, z, channel=-1):
+        R, S = z.shape
+        out = torch.empty(R, S, device=z.device)
+        check(_sdf_values(self._h, ptr(o), ptr(d), ptr(z), R, S, int(channel), ptr(out), stream()))
+        return out
+
+    def render_forward(self, slot, o, d, z, depth_scale, rot):
+        R, S = z.shape
+        dev = z.device
+        K = self.K
+        rgbv = torch.empty(R, 3, device=dev) if slot == SLOT_MAIN else None
+        depth = torch.empty(R, 1, device=dev)
+        nmap = torch.empty(R, 3, device=dev)
+        opac = torch.empty(R, K, device=dev) if slot == SLOT_MAIN else None
+        sem = torch.empty(R, K, device=dev)
+        check(_render_fwd(self._h, slot, ptr(o), ptr(d), ptr(z), R, S, ptr(depth_scale), ptr(rot), ptr(rgbv), ptr(depth), ptr(nmap),
+                          ptr(opac), ptr(sem), stream()))
+        return rgbv, depth, nmap, opac, sem
+
+    def render_backward(self, slot, d_rgb, d_depth, d_normal, d_opacity):
+        c = lambda t: None if t is None else t.contiguous()
+        a, b, e, f = c(d_rgb), c(d_depth), c(d_normal), c(d_opacity)
+        check(_render_bwd(self._h, slot, ptr(a), ptr(b), ptr(e), ptr(f), stream()))
+
+    def eikonal_forward(self, x):
+        Ne = x.shape[0]
+        K = self.K
+        gt = torch.empty((K + 1) * Ne, 3, device=x.device)
+        ssdf = torch.empty(Ne, K, device=x.device)
+        smin = torch.empty(Ne, 1, device=x.device)
+        check(_eik_fwd(self._h, ptr(x), Ne, ptr(gt), ptr(ssdf), ptr(smin), stream()))
+        return gt, ssdf, smin
+
+    def eikonal_backward(self, d_grad_theta, d_sample_sdf=None):
+        a = d_grad_theta.contiguous()
+        b = None if d_sample_sdf is None else d_sample_sdf.contiguous()
+        check(_eik_bwd(self._h, ptr(a), ptr(b), stream()))
+
+    def adam(self, lo, hi, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.99), eps=1e-15, grad_norm_sq=None):
+        """Adam over params[lo:hi] (one learning-rate group is a contiguous range of segments)."""
+        n = hi - lo
+        off = lambda t: _vp(t.data_ptr() + 4 * lo)
+        check(_adam(off(self.params), off(self.grads), off(exp_avg), off(exp_avg_sq), n, float(lr), float(betas[0]),
+                    float(betas[1]), float(eps), int(step), ptr(grad_norm_sq), stream()))

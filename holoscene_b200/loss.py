@@ -1,0 +1,177 @@
+"""Drop-in `train.loss_class` for Stage 1:  holoscene_b200.loss.HoloSceneLoss
+
+Same constructor keywords (conf `loss{}` block), same call signature and the same output keys as
+the reference (model/loss.py:196-346 MonoSDFLoss, :349-666 HoloSceneLoss).  The loss terms act on the
+per-ray outputs of the fused kernels ([R,3], [R,1], [R,K], [(K+1)*4R,3] -- a few hundred KB), so
+they are evaluated with device tensor ops and differentiated by autograd; the resulting
+d(loss)/d(output) tensors are what hsb_render_backward / hsb_eikonal_backward consume.
+Ground-truth tensors may arrive on the CPU (the reference trainer passes them that way) and are moved
+to the outputs' device.
+"""
+from __future__ import annotations
+
+import importlib
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def get_class(kls: str):
+    parts = kls.split(".")
+    return getattr(importlib.import_module(".".join(parts[:-1])), parts[-1])
+
+
+def compute_scale_and_shift_batch(prediction, target):
+    """Closed-form least squares  min_{w,q} sum (w d + q - g)^2  via the 2x2 normal equations and an
+    explicit inverse, as the reference does (loss.py:181-193)."""
+    B, N = prediction.shape
+    dr = torch.stack([prediction, torch.ones_like(prediction)], dim=-1)          # [B,N,2]
+    A = torch.einsum("bni,bnj->bij", dr, dr)
+    rhs = torch.einsum("bni,bn->bi", dr, target).unsqueeze(-1)
+    rs = (torch.inverse(A) @ rhs).reshape(B, 2)
+    return rs[:, 0], rs[:, 1]
+
+
+class MonoSDFLoss(nn.Module):
+    def __init__(self, rgb_loss, eikonal_weight, smooth_weight=0.005, depth_weight=0.1, normal_l1_weight=0.05,
+                 normal_cos_weight=0.05, uncertainty_begin_iter=20000000, depth_type="marigold", phy_un_weight=50,
+                 end_step=-1):
+        super().__init__()
+        self.eikonal_weight = eikonal_weight
+        self.smooth_weight = smooth_weight
+        self.depth_weight = depth_weight
+        self.normal_l1_weight = normal_l1_weight
+        self.normal_cos_weight = normal_cos_weight
+        self.depth_type = depth_type
+        self.rgb_loss = get_class(rgb_loss)(reduction="mean") if isinstance(rgb_loss, str) else rgb_loss
+        self.step = 0
+        self.end_step = end_step
+
+    def get_rgb_loss(self, rgb_values, rgb_gt):
+        return self.rgb_loss(rgb_values, rgb_gt.reshape(-1, 3))
+
+    def get_eikonal_loss(self, grad_theta):
+        return ((grad_theta.norm(2, dim=1) - 1) ** 2).mean()
+
+    def get_smooth_loss(self, model_outputs):
+        g1, g2 = model_outputs["grad_theta"], model_outputs["grad_theta_nei"]
+        n1 = g1 / (g1.norm(2, dim=1).unsqueeze(-1) + 1e-5)
+        n2 = g2 / (g2.norm(2, dim=1).unsqueeze(-1) + 1e-5)
+        return torch.norm(n1 - n2, dim=-1).mean()
+
+    def get_depth_loss(self, depth_pred, depth_gt):
+        depth_pred = depth_pred.reshape(1, -1)
+        depth_gt = depth_gt.reshape(1, -1)
+        w, q = compute_scale_and_shift_batch(depth_pred, depth_gt)
+        diff = ((w.reshape(-1, 1) * depth_pred + q.reshape(-1, 1)) - depth_gt) ** 2
+        return torch.clip(diff, max=1).reshape(-1).mean()
+
+    def get_normal_loss(self, normal_pred, normal_gt):
+        normal_gt = F.normalize(normal_gt, p=2, dim=-1)
+        normal_pred = F.normalize(normal_pred, p=2, dim=-1)
+        l1 = torch.abs(normal_pred - normal_gt).sum(dim=-1).mean()
+        cos = (1.0 - torch.sum(normal_pred * normal_gt, dim=-1)).mean()
+        return l1, cos
+
+    def forward(self, model_outputs, ground_truth):
+        dev = model_outputs["rgb_values"].device
+        zero = torch.zeros((), device=dev)
+        rgb_gt = ground_truth["rgb"].to(dev)
+        depth_gt = ground_truth["depth"].to(dev)
+        normal_gt = ground_truth["normal"].to(dev)
+        depth_pred = model_outputs["depth_values"]
+        normal_pred = model_outputs["normal_map"][None]
+        rgb_loss = self.get_rgb_loss(model_outputs["rgb_values"], rgb_gt)
+        eikonal_loss = self.get_eikonal_loss(model_outputs["grad_theta"]) if "grad_theta" in model_outputs else zero
+        sdf = model_outputs["sdf"]
+        mask = ((sdf > 0.0).any(dim=-1) & (sdf < 0.0).any(dim=-1))[None, :, None]
+        mask = (ground_truth["mask"].to(dev) > 0.5) & mask
+        depth_loss = self.get_depth_loss(depth_pred, depth_gt) if self.depth_weight > 0 else zero
+        normal_l1, normal_cos = self.get_normal_loss(normal_pred * mask, normal_gt)
+        smooth_loss = self.get_smooth_loss(model_outputs)
+        decay = math.exp(-self.step / self.end_step * 10.0) if self.end_step > 0 else 1.0
+        self.step += 1
+        loss = (rgb_loss + self.eikonal_weight * eikonal_loss + self.smooth_weight * smooth_loss
+                + decay * self.depth_weight * depth_loss + decay * self.normal_l1_weight * normal_l1
+                + decay * self.normal_cos_weight * normal_cos)
+        return {"loss": loss, "rgb_loss": rgb_loss, "eikonal_loss": eikonal_loss, "smooth_loss": smooth_loss,
+                "depth_loss": depth_loss, "normal_l1": normal_l1, "normal_cos": normal_cos}
+
+
+class HoloSceneLoss(MonoSDFLoss):
+    def __init__(self, rgb_loss, eikonal_weight, semantic_weight=0.04, smooth_weight=0.005, semantic_loss=None,
+                 depth_weight=0.1, normal_l1_weight=0.05, normal_cos_weight=0.05, reg_vio_weight=0.1,
+                 use_obj_opacity=True, bg_reg_weight=0.1, depth_type="marigold", end_step=-1):
+        super().__init__(rgb_loss=rgb_loss, eikonal_weight=eikonal_weight, smooth_weight=smooth_weight,
+                         depth_weight=depth_weight, normal_l1_weight=normal_l1_weight,
+                         normal_cos_weight=normal_cos_weight, depth_type=depth_type, end_step=end_step)
+        self.semantic_weight = semantic_weight
+        self.bg_reg_weight = bg_reg_weight
+        self.reg_vio_weight = reg_vio_weight
+        self.use_obj_opacity = use_obj_opacity
+        if not use_obj_opacity:
+            raise NotImplementedError("Stage-1 confs use use_obj_opacity = True (ObjectSDF++ opacity loss)")
+
+    def object_distinct_loss(self, sdf_value, min_sdf):
+        _, min_indice = torch.min(sdf_value, dim=1, keepdim=True)
+        v = torch.relu(-sdf_value - min_sdf.detach())
+        keep = torch.ones_like(v, dtype=torch.bool)
+        keep[torch.arange(v.shape[0], device=v.device), min_indice.reshape(-1)] = False
+        v = v[keep].reshape(-1)
+        cnt = torch.count_nonzero(v > 0)
+        # sum/count without a host sync: the reference branches on cnt > 0 (loss.py:399-403) and returns 0 otherwise
+        return torch.where(cnt > 0, v.sum() / cnt.clamp(min=1), torch.zeros((), device=v.device))
+
+    def object_opacity_loss(self, predict_opacity, gt_opacity, weight=None):
+        target = F.one_hot(gt_opacity.reshape(-1), num_classes=predict_opacity.shape[1]).float()
+        predict_opacity = torch.clip(predict_opacity, 1e-4, 1 - (1e-4))
+        return F.binary_cross_entropy(predict_opacity, target, reduction="none").mean(dim=-1).mean()
+
+    def compute_grad_error(self, x, mask):
+        grad_loss = torch.zeros((), device=x.device)
+        for i in range(4):
+            step = 2 ** i
+            m, xs = mask[:, ::step, ::step], x[:, ::step, ::step]
+            M = torch.sum(m[:1], (1, 2))
+            diff = m * xs
+            gx = torch.abs(diff[:, :, 1:] - diff[:, :, :-1]) * (m[:, :, 1:] * m[:, :, :-1])
+            gy = torch.abs(diff[:, 1:, :] - diff[:, :-1, :]) * (m[:, 1:, :] * m[:, :-1, :])
+            image_loss = torch.sum(gx, (1, 2)) + torch.sum(gy, (1, 2))
+            divisor = torch.sum(M)
+            grad_loss = grad_loss + torch.where(divisor == 0, torch.zeros((), device=x.device),
+                                                torch.sum(image_loss) / divisor.clamp(min=1))
+        return grad_loss
+
+    def get_bg_render_loss(self, bg_depth, bg_normal, mask):
+        bg_depth = bg_depth.reshape(1, 32, 32)
+        bg_normal = bg_normal.reshape(32, 32, 3).permute(2, 0, 1)
+        mask = mask.reshape(1, 32, 32)
+        return self.compute_grad_error(bg_depth, mask) + self.compute_grad_error(bg_normal, mask.repeat(3, 1, 1))
+
+    def forward(self, model_outputs, ground_truth, call_reg=False, call_bg_reg=False):
+        output = super().forward(model_outputs, ground_truth)
+        dev = model_outputs["rgb_values"].device
+        zero = torch.zeros((), device=dev)
+        if "object_opacity" in model_outputs:
+            semantic_gt = ground_truth["segs"].to(dev).long()
+            semantic_loss = self.object_opacity_loss(model_outputs["object_opacity"], semantic_gt)
+        else:
+            semantic_loss = zero
+        if "sample_sdf" in model_outputs and call_reg:
+            sample_sdf_loss = self.object_distinct_loss(model_outputs["sample_sdf"], model_outputs["sample_minsdf"])
+        else:
+            sample_sdf_loss = zero
+        if "bg_depth_values" in model_outputs:
+            bg_mask = (model_outputs["bg_mask"] != 0).int()
+            background_reg_loss = self.get_bg_render_loss(model_outputs["bg_depth_values"], model_outputs["bg_normal_map"],
+                                                          bg_mask)
+        else:
+            background_reg_loss = zero
+        output["semantic_loss"] = semantic_loss
+        output["collision_reg_loss"] = sample_sdf_loss
+        output["background_reg_loss"] = background_reg_loss
+        output["loss"] = (output["loss"] + self.semantic_weight * semantic_loss + self.reg_vio_weight * sample_sdf_loss
+                          + self.bg_reg_weight * background_reg_loss)
+        return output

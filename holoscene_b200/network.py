@@ -1,0 +1,359 @@
+"""Drop-in `train.model_class` for Stage 1:  holoscene_b200.network.HoloSceneNetwork
+
+Mirrors the reference model interface (model/network.py:748-971): same constructor
+(conf, plots_dir, graph_node_dict, ft_folder, num_images), same forward(input, indices, iter_step)
+-> dict with the same keys, same sub-module / parameter names (state_dict compatible),
+same initialisation order (torch.manual_seed(s) gives the reference's weights).  All arithmetic of
+the step runs in libhsb200's sm_100a kernels through the C ABI (include/hsb200.h); this file only
+wires tensors.  There is no CPU path: forward() raises without a CUDA device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine as _engine
+from . import rend_util
+from .density import LaplaceDensity
+from .hashgrid import HashEncoder
+from .ray_sampler import ErrorBoundSampler
+from .rng import LiveDraws, ReplayDraws
+
+
+def _embed_dim(multires):
+    return 3 + 3 * 2 * multires
+
+
+class ObjectImplicitNetworkGrid(nn.Module):
+    """Parameter container + point-query helpers with the reference's names (network.py:19-532)."""
+
+    def __init__(self, feature_vector_size, sdf_bounding_sphere, d_in, d_out, dims, geometric_init=True, bias=1.0,
+                 skip_in=(), weight_norm=True, multires=0, sphere_scale=1.0, inside_outside=False, base_size=16,
+                 end_size=2048, logmap=19, num_levels=16, level_dim=2, divide_factor=1.5, use_grid_feature=True,
+                 sigmoid=20, color_grid_feature=False):
+        super().__init__()
+        if not (d_in == 3 and list(dims) == [256, 256] and multires == 6 and weight_norm and use_grid_feature
+                and color_grid_feature and geometric_init and feature_vector_size == 256 and num_levels == 16
+                and level_dim == 2 and float(divide_factor) == 1.0):
+            raise NotImplementedError(
+                "libhsb200 implements the Stage-1 architecture of confs/*: d_in=3, dims=[256,256], multires=6, "
+                "weight_norm, use_grid_feature, color_grid_feature, 16x2 hash grid, divide_factor=1.0")
+        self.d_out = d_out
+        self.sigmoid = sigmoid
+        self.sdf_bounding_sphere = sdf_bounding_sphere
+        self.sphere_scale = sphere_scale
+        self.color_grid_feature = True
+        self.divide_factor = divide_factor
+        self.use_grid_feature = True
+        dims = [d_in] + list(dims) + [d_out]
+        self.encoding = HashEncoder(input_dim=3, num_levels=num_levels, level_dim=level_dim, per_level_scale=2,
+                                    base_resolution=base_size, log2_hashmap_size=logmap, desired_resolution=end_size)
+        self.grid_feature_dim = num_levels * level_dim
+        dims[0] += self.grid_feature_dim
+        self.color_encoding = HashEncoder(input_dim=3, num_levels=num_levels, level_dim=level_dim, per_level_scale=2,
+                                          base_resolution=base_size, log2_hashmap_size=logmap, desired_resolution=end_size)
+        self.color_grid_feature_dim = num_levels * level_dim
+        self.color_grid_feature_map_mlp = nn.Sequential(nn.Linear(self.color_grid_feature_dim, 256), nn.ReLU(),
+                                                        nn.Linear(256, feature_vector_size))
+        dims[0] += _embed_dim(multires) - 3
+        self.num_layers = len(dims)
+        self.skip_in = skip_in   # conf says [4]; with three layers it never fires (network.py:125-133)
+        for l in range(self.num_layers - 1):
+            out_dim = dims[l + 1]
+            lin = nn.Linear(dims[l], out_dim)
+            if l == self.num_layers - 2:
+                # channel 0 = background (positive inside), 1.. = objects (network.py:136-144)
+                torch.nn.init.normal_(lin.weight[:1, :], mean=-np.sqrt(np.pi) / np.sqrt(dims[l]), std=0.0001)
+                torch.nn.init.constant_(lin.bias[:1], bias)
+                torch.nn.init.normal_(lin.weight[1:, :], mean=np.sqrt(np.pi) / np.sqrt(dims[l]), std=0.0001)
+                torch.nn.init.constant_(lin.bias[1:], -0.5 * bias)
+            elif l == 0:
+                torch.nn.init.constant_(lin.bias, 0.0)
+                torch.nn.init.constant_(lin.weight[:, 3:], 0.0)
+                torch.nn.init.normal_(lin.weight[:, :3], 0.0, np.sqrt(2) / np.sqrt(out_dim))
+            else:
+                torch.nn.init.constant_(lin.bias, 0.0)
+                torch.nn.init.normal_(lin.weight, 0.0, np.sqrt(2) / np.sqrt(out_dim))
+            lin = nn.utils.weight_norm(lin)
+            setattr(self, "lin" + str(l), lin)
+        self._owner = None   # set by HoloSceneNetwork (not a submodule reference: avoids a cycle in .modules())
+
+    # ---- parameter groups the trainer builds its optimizer from (holoscene_train.py:157-163) ----
+    def mlp_parameters(self):
+        parameters = []
+        for l in range(self.num_layers - 1):
+            parameters += list(getattr(self, "lin" + str(l)).parameters())
+        parameters += list(self.color_grid_feature_map_mlp.parameters())
+        return parameters
+
+    def grid_parameters(self, verbose=False):
+        return list(self.encoding.parameters()) + list(self.color_encoding.parameters())
+
+    # ---- point queries used by plotting / mesh extraction (utils/plots.py:152-175) ----
+    def _raw(self, x):
+        model = self._owner[0]
+        eng = model.engine()
+        eng.prepare()
+        x = x.reshape(-1, 3).contiguous().float()
+        outs = []
+        step = eng.cfg.max_points
+        for i in range(0, x.shape[0], step):
+            xb = x[i:i + step]
+            n = xb.shape[0]
+            zeros = torch.zeros(n, 3, device=x.device)
+            eng.sdf_values(xb, zeros, torch.zeros(n, 1, device=x.device), -1)
+            outs.append(eng.buffer("main.SR")[:n, : self.d_out].clone())
+        return torch.cat(outs, 0) if outs else torch.empty(0, self.d_out, device=x.device)
+
+    @torch.no_grad()
+    def get_sdf_raw(self, x):
+        return self._raw(x)
+
+    @torch.no_grad()
+    def get_sdf_vals(self, x):
+        return self._raw(x).min(dim=1, keepdim=True)[0]
+
+    @torch.no_grad()
+    def get_object_sdf_vals(self, x, idx):
+        return self._raw(x)[:, idx]
+
+    @torch.no_grad()
+    def get_shift_sdf_raw(self, x):
+        """network.py:460-479"""
+        sdf_raw = self._raw(x)
+        sdf, indices = sdf_raw.min(dim=1, keepdim=True)
+        shift = torch.where((sdf < 0).expand_as(sdf_raw), torch.max(sdf_raw, (-sdf).expand_as(sdf_raw)), sdf_raw)
+        shift[torch.arange(indices.size(0), device=x.device), indices.squeeze(-1)] = sdf.squeeze(-1)
+        return shift
+
+
+class RenderingNetwork(nn.Module):
+    """Parameter container with the reference's names (network.py:535-583)."""
+
+    def __init__(self, feature_vector_size, mode, d_in, d_out, dims, weight_norm=True, multires_view=0, multires_point=0,
+                 multires_normal=0, num_images=1024):
+        super().__init__()
+        if not (mode == "idr" and d_in == 9 and d_out == 3 and list(dims) == [256, 256] and weight_norm
+                and multires_view == 4 and multires_point == 4 and multires_normal == 4 and feature_vector_size == 256):
+            raise NotImplementedError("libhsb200 implements rendering_network {mode=idr, d_in=9, dims=[256,256], multires 4/4/4}")
+        self.mode = mode
+        dims = [d_in + feature_vector_size + 3 * (_embed_dim(4) - 3)] + list(dims) + [d_out]
+        self.num_layers = len(dims)
+        for l in range(self.num_layers - 1):
+            lin = nn.utils.weight_norm(nn.Linear(dims[l], dims[l + 1]))
+            setattr(self, "lin" + str(l), lin)
+
+
+class _StepFn(torch.autograd.Function):
+    """One autograd node for the whole differentiable part of the step.  forward() has already run
+    in the kernels; backward() launches the fused backward phases, which accumulate straight into
+    the flat gradient buffer that every Parameter's .grad is a view of."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, outs, has_eik, has_bg):
+        ctx.model = model
+        ctx.has_eik, ctx.has_bg = has_eik, has_bg
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_depth, d_normal, d_opacity, d_gt, d_ssdf, d_bg_depth, d_bg_normal):
+        eng = ctx.model.engine()
+        if ctx.has_eik and (d_gt is not None or d_ssdf is not None):
+            if d_gt is None:
+                d_gt = torch.zeros((eng.K + 1) * ctx.model._last_ne, 3, device=eng.device)
+            eng.eikonal_backward(d_gt, d_ssdf)
+        eng.render_backward(_engine.SLOT_MAIN, d_rgb, d_depth, d_normal, d_opacity)
+        if ctx.has_bg and (d_bg_depth is not None or d_bg_normal is not None):
+            eng.render_backward(_engine.SLOT_BG, None, d_bg_depth, d_bg_normal, None)
+        eng.finish()
+        return None, None, None, None, None
+
+
+class HoloSceneNetwork(nn.Module):
+    def __init__(self, conf, plots_dir=None, graph_node_dict=None, ft_folder=None, num_images=1024):
+        super().__init__()
+        self.feature_vector_size = conf.get_int("feature_vector_size")
+        self.scene_bounding_sphere = conf.get_float("scene_bounding_sphere", default=1.0)
+        self.white_bkgd = conf.get_bool("white_bkgd", default=False)
+        if self.white_bkgd:
+            raise NotImplementedError("white_bkgd is not part of the Stage-1 conf")
+        self.use_bg_reg = conf.get_bool("use_bg_reg", default=False)
+        self.render_bg_iter = conf.get_int("render_bg_iter", default=10)
+        self.graph_node_dict = graph_node_dict
+        self.implicit_network = ObjectImplicitNetworkGrid(self.feature_vector_size, self.scene_bounding_sphere,
+                                                          **conf.get_config("implicit_network"))
+        self.num_semantic = conf.get_int("implicit_network.d_out")
+        self.rendering_network = RenderingNetwork(self.feature_vector_size, num_images=num_images,
+                                                  **conf.get_config("rendering_network"))
+        self.density = LaplaceDensity(**conf.get_config("density"))
+        self.ray_sampler = ErrorBoundSampler(self.scene_bounding_sphere, **conf.get_config("ray_sampler"))
+        self.plots_dir = plots_dir
+        self.ft_folder = ft_folder
+        self.all_mesh_bbox_dict = None
+        self.implicit_network._owner = [self]
+        self.precise = bool(conf.get_bool("hsb_precise", default=False))   # 3xTF32 contractions
+        self.max_rays = conf.get_int("hsb_max_rays", default=1024)
+        self._eng = None
+        self._flat = None
+        self._flat_grad = None
+        self.draws = None
+        self._last_ne = 0
+
+    # ---- flat parameter storage -----------------------------------------------------------------------
+    def _named_segments(self):
+        named = dict(self.named_parameters())
+        return [named[n] for n in _engine.SEGMENT_NAMES]
+
+    def _flatten(self, device):
+        enc = self.implicit_network.encoding
+        rows = enc.embeddings.shape[0]
+        offs = _engine.param_layout(self.implicit_network.d_out, rows)
+        params = self._named_segments()
+        ok = self._flat is not None and self._flat.device == device
+        if ok:
+            base = self._flat.data_ptr()
+            ok = all(p.data.data_ptr() == base + 4 * offs[i] and p.device == device for i, p in enumerate(params))
+        if ok:
+            return False
+        flat = torch.zeros(offs[-1], device=device)
+        for i, p in enumerate(params):
+            seg = flat[offs[i]: offs[i] + p.numel()].view(p.shape)
+            seg.copy_(p.data)
+            p.data = seg
+            p.grad = None
+        self._flat = flat
+        self._flat_grad = torch.zeros(offs[-1], device=device)
+        self._offs = offs
+        self._eng = None
+        return True
+
+    def _attach_grads(self):
+        """Every Parameter's .grad is a view of the flat gradient buffer.  A .grad that optimizer.zero_grad()
+        reset to None means 'zero': the whole buffer is cleared once and the views re-attached."""
+        params = self._named_segments()
+        if any(p.grad is None for p in params):
+            self._flat_grad.zero_()
+            for i, p in enumerate(params):
+                p.grad = self._flat_grad[self._offs[i]: self._offs[i] + p.numel()].view(p.shape)
+
+    def engine(self) -> _engine.StepEngine:
+        if not torch.cuda.is_available():
+            raise RuntimeError("holoscene_b200 needs a CUDA device: the Stage-1 hot path has no CPU fallback")
+        dev = self.density.beta.device
+        if dev.type != "cuda":
+            raise RuntimeError("call model.cuda() first: holoscene_b200 runs the hot path on the GPU only")
+        rebuilt = self._flatten(dev)
+        if self._eng is None or rebuilt:
+            enc = self.implicit_network.encoding
+            rs = self.ray_sampler
+            S = rs.N_samples + rs.N_samples_extra + 2
+            self._eng = _engine.StepEngine(
+                K=self.implicit_network.d_out, table_rows=enc.embeddings.shape[0], hash_offsets=enc.offsets,
+                S=float(np.float32(np.log2(enc.per_level_scale))), H=enc.base_resolution, L=enc.num_levels,
+                beta_min=self.density.beta_min, sigmoid_scale=float(self.implicit_network.sigmoid),
+                max_rays=max(self.max_rays, 1024 if self.use_bg_reg else 1), max_samples=S, max_sampler_samples=rs.N_samples_eval, max_bg_rays=1024,
+                precise=self.precise, flat_params=self._flat, flat_grads=self._flat_grad)
+        return self._eng
+
+    # ---- forward (network.py:778-971) --------------------------------------------------------------------
+    def forward(self, input, indices, iter_step=-1):
+        intrinsics, uv, pose = input["intrinsics"], input["uv"], input["pose"]
+        if not uv.is_cuda:
+            raise RuntimeError("holoscene_b200.HoloSceneNetwork.forward needs CUDA tensors (no CPU fallback)")
+        dev = uv.device
+        eng = self.engine()
+        if uv.shape[1] > eng.max_rays:
+            raise RuntimeError(f"{uv.shape[1]} rays exceed hsb_max_rays={eng.max_rays} (set model.hsb_max_rays in the conf)")
+        draws = self.draws if self.draws is not None else LiveDraws(dev)
+        self.draws = draws
+        try:
+            return self._forward(eng, intrinsics, uv, pose, iter_step, draws, dev)
+        finally:
+            if isinstance(draws, LiveDraws):
+                self.draws = None
+
+    def _forward(self, eng, intrinsics, uv, pose, iter_step, draws, dev):
+        training = self.training
+        if training:
+            self._attach_grads()
+        eng.prepare()
+        ray_offset = draws.rand("ray_offset", uv.shape) - 0.5 if training else None
+        ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics, ray_offset=ray_offset)
+        # second call with the identity pose: unnormalised z of the (again jittered) pixel -> depth scale
+        ray_dirs_tmp, _ = rend_util.get_camera_params(uv, torch.eye(4, device=dev)[None], intrinsics, ray_offset=ray_offset)
+        depth_scale = ray_dirs_tmp[0, :, 2:].contiguous()
+        batch_size, num_pixels, _ = ray_dirs.shape
+        cam_loc = cam_loc.unsqueeze(1).repeat(1, num_pixels, 1).reshape(-1, 3).contiguous()
+        ray_dirs = ray_dirs.reshape(-1, 3).contiguous()
+        R = ray_dirs.shape[0]
+
+        z_vals, z_samples_eik = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self)
+        z_vals = z_vals.contiguous()
+        S = z_vals.shape[1]
+        rot = pose[0, :3, :3].permute(1, 0).contiguous()
+        rgbv, depth, nmap, opac, sem = eng.render_forward(_engine.SLOT_MAIN, cam_loc, ray_dirs, z_vals, depth_scale, rot)
+        P = R * S
+        output = {
+            "rgb": eng.buffer("main.RGB")[:P].view(R, S, 4)[..., :3].clone(),
+            "semantic_values": sem,
+            "z_vals": z_vals,
+            "depth_vals": z_vals * depth_scale,
+            "sdf": eng.buffer("main.SDF")[:P].view(R, S).clone(),
+            "weights": eng.buffer("main.W")[:P].view(R, S).clone(),
+        }
+        gt = ssdf = smin = None
+        if training:
+            n_eik = batch_size * num_pixels
+            eik = draws.uniform("eik_uniform", (n_eik, 3), -self.scene_bounding_sphere, self.scene_bounding_sphere)
+            near_pts = (cam_loc.unsqueeze(1) + z_samples_eik.unsqueeze(2) * ray_dirs.unsqueeze(1)).reshape(-1, 3)
+            eik = torch.cat([eik, near_pts], 0)
+            nei = eik + (draws.rand("nei_noise", eik.shape) - 0.5) * 0.01
+            eik = torch.cat([eik, nei], 0).contiguous()
+            self._last_ne = eik.shape[0]
+            gt, ssdf, smin = eng.eikonal_forward(eik)
+            output["sample_minsdf"] = smin
+        bg = None
+        if self.use_bg_reg and iter_step % self.render_bg_iter == 0:
+            ps = 32
+            cx_2 = float(intrinsics[:, 0, 2].reshape(-1)[0]) * 2.0
+            cy_2 = float(intrinsics[:, 1, 2].reshape(-1)[0]) * 2.0
+            x0 = draws.np_randint("patch_x0", int(cx_2) - ps + 1)
+            y0 = draws.np_randint("patch_y0", int(cy_2) - ps + 1)
+            gx, gy = np.meshgrid(np.arange(ps), np.arange(ps), indexing="xy")
+            uv0 = torch.from_numpy(np.stack([gx + x0, gy + y0], -1).reshape(1, -1, 2)).float().to(dev)
+            d0, c0 = rend_util.get_camera_params(uv0, pose, intrinsics)
+            d0t, _ = rend_util.get_camera_params(uv0, torch.eye(4, device=dev)[None], intrinsics)
+            ds0 = d0t[0, :, 2:].contiguous()
+            c0 = c0.unsqueeze(1).repeat(1, d0.shape[1], 1).reshape(-1, 3).contiguous()
+            d0 = d0.reshape(-1, 3).contiguous()
+            bz, _ = self.ray_sampler.get_z_vals(d0, c0, self, idx=0)
+            bz = bz.contiguous()
+            _, bdepth, bnmap, _, bsem = eng.render_forward(_engine.SLOT_BG, c0, d0, bz, ds0, rot)
+            output["bg_mask"] = torch.argmax(bsem, dim=-1, keepdim=True)
+            bg = (bdepth, bnmap)
+
+        if torch.is_grad_enabled() and training:
+            outs = [rgbv, depth, nmap, opac,
+                    gt if gt is not None else torch.empty(0, device=dev),
+                    ssdf if ssdf is not None else torch.empty(0, device=dev),
+                    bg[0] if bg is not None else torch.empty(0, device=dev),
+                    bg[1] if bg is not None else torch.empty(0, device=dev)]
+            rgbv, depth, nmap, opac, gt_, ssdf_, bgd, bgn = _StepFn.apply(self.density.beta, self, outs, gt is not None,
+                                                                          bg is not None)
+            if gt is not None:
+                gt, ssdf = gt_, ssdf_
+            if bg is not None:
+                bg = (bgd, bgn)
+        output.update({"object_opacity": opac, "rgb_values": rgbv, "depth_values": depth, "normal_map": nmap})
+        if gt is not None:
+            output["sample_sdf"] = ssdf
+            output["grad_theta"] = gt[: gt.shape[0] // 2]
+            output["grad_theta_nei"] = gt[gt.shape[0] // 2:]
+        if bg is not None:
+            output["bg_depth_values"], output["bg_normal_map"] = bg
+        return output
+
+    def get_parameters(self):
+        return list(self.parameters())

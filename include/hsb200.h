@@ -78,6 +78,100 @@ int hsb_hash_backward_fused(const float* x_world, const int32_t* offsets, const 
                             float* grad_embeddings, uint32_t B, uint32_t L, float S, uint32_t H,
                             hsb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * B3: fused train-step interface.
+ *
+ * Architecture fixed to the Stage-1 conf (confs/replica/room_0/replica_room_0.conf:46-84): SDF net
+ * [PE6(x) 39 | hash 32] -> 256 -> 256 -> K (softplus beta=100, weight_norm), colour-feature MLP
+ * hash 32 -> 256 (ReLU) -> 256, render net [PE4(x) | PE4(view) | PE4(grad) | feature 256] = 337 -> 256
+ * -> 256 -> 3 (ReLU, sigmoid, weight_norm), Laplace density with one learned beta.  K (= d_out,
+ * background + objects) is free, 1..64.
+ *
+ * Parameters and their gradients live in two flat fp32 buffers owned by the caller; segment i
+ * starts at offsets[i] floats (hsb_param_layout), in this order (names = reference state_dict keys):
+ *    0 implicit_network.encoding.embeddings        1 implicit_network.color_encoding.embeddings
+ *    2 ...color_grid_feature_map_mlp.0.weight      3 ....0.bias     4 ....2.weight     5 ....2.bias
+ *    6 implicit_network.lin0.bias   7 .lin0.weight_g   8 .lin0.weight_v    9-11 lin1   12-14 lin2
+ *   15 rendering_network.lin0.bias 16 .lin0.weight_g  17 .lin0.weight_v   18-20 lin1   21-23 lin2
+ *   24 density.beta                25 = end
+ * The step accumulates d(loss)/d(param) INTO the gradient buffer (caller zero-fills = zero_grad()).
+ *
+ * Per step:  hsb_prepare -> [hsb_sdf_values ...] -> hsb_render_forward(MAIN) -> hsb_eikonal_forward
+ *            [-> hsb_render_forward(BG)] -> (loss on the per-ray outputs, gives d_* ) ->
+ *            hsb_eikonal_backward, hsb_render_backward(MAIN) [, (BG)] -> hsb_finish -> hsb_adam_step
+ * ---------------------------------------------------------------------------------------------- */
+#define HSB_NUM_SEGMENTS 25
+#define HSB_SLOT_MAIN 0 /* scene pass: colour, opacity, semantics             network.py:799-841,904-913 */
+#define HSB_SLOT_EIK 1  /* eikonal points                                      network.py:843-866 */
+#define HSB_SLOT_BG 2   /* background patch: channel-0 weights, no colour      network.py:915-968 */
+
+typedef struct hsb_step_cfg {
+    int32_t K;              /* implicit_network.d_out */
+    int32_t L;              /* hash levels (16) */
+    int32_t H;              /* base resolution (16) */
+    float S;                /* log2(per_level_scale) */
+    int64_t table_rows;     /* rows of one hash table (offsets[L]) */
+    float beta_min;         /* density.beta_min */
+    float sigmoid_scale;    /* implicit_network.sigmoid (semantic = s*sigmoid(-s*sdf)) */
+    int64_t max_points;     /* capacity of the MAIN slot in points (rays*samples; also bounds hsb_sdf_values) */
+    int32_t max_rays;
+    int64_t max_eik_points; /* capacity of the EIK slot in points (4 * rays) */
+    int64_t max_bg_points;  /* capacity of the BG slot (1024 * samples); 0 = unused */
+    int32_t max_bg_rays;
+    int32_t precise;        /* 1: 3xTF32 error-compensated contractions (fp32-grade), 0: single-pass TF32 */
+} hsb_step_cfg;
+
+typedef struct hsb_ctx hsb_ctx;
+
+int hsb_param_layout(int32_t K, int64_t table_rows, int64_t* offsets_out /* [HSB_NUM_SEGMENTS+1] */);
+int hsb_ctx_workspace_bytes(const hsb_step_cfg* cfg, uint64_t* bytes_out);
+/* workspace: device memory, 256-byte aligned, >= hsb_ctx_workspace_bytes; hash_offsets: device int32 [L+1]. */
+int hsb_ctx_create(const hsb_step_cfg* cfg, float* params, float* grads, const int32_t* hash_offsets, void* workspace,
+                   uint64_t workspace_bytes, hsb_ctx** out);
+void hsb_ctx_destroy(hsb_ctx* ctx);
+/* Introspection for tests: byte offset / rows / row stride (floats) of a named workspace buffer, e.g. "main.H1". */
+int hsb_ctx_buffer(hsb_ctx* ctx, const char* name, int64_t* offset_bytes, int64_t* rows, int64_t* ld);
+
+/* weight_norm materialisation (w = g v/|v|), transposes, zero of the effective-weight gradient accumulators. */
+int hsb_prepare(hsb_ctx* ctx, hsb_stream_t stream);
+/* weight_norm backward + bias fix-ups into the flat gradient buffer; call once after all *_backward. */
+int hsb_finish(hsb_ctx* ctx, hsb_stream_t stream);
+
+/* No-grad SDF at the points o[r] + z[r,i] d[r]: min over the K channels (channel < 0) or one channel.
+ * Replaces implicit_network.get_sdf_vals / get_object_sdf_vals inside the sampler (ray_sampler.py:150-156). */
+int hsb_sdf_values(hsb_ctx* ctx, const float* o, const float* d, const float* z, int32_t R, int32_t S, int32_t channel,
+                   float* sdf_out, hsb_stream_t stream);
+
+/* Ray pass forward.  o, d [R,3]; z [R,S] sorted sample depths; depth_scale [R]; rot [9] = pose[:3,:3]^T row-major.
+ * Outputs (per ray): rgb_values [R,3], depth_values [R], normal_map [R,3], opacity [R,K], semantic [R,K]
+ * (BG slot: rgb_values / opacity unused, may be NULL).  Per-sample state stays in the workspace
+ * (buffers "<slot>.SDF", ".W", ".RGB", ".G", ... via hsb_ctx_buffer). */
+int hsb_render_forward(hsb_ctx* ctx, int32_t slot, const float* o, const float* d, const float* z, int32_t R, int32_t S,
+                       const float* depth_scale, const float* rot, float* rgb_values, float* depth_values, float* normal_map,
+                       float* opacity, float* semantic, hsb_stream_t stream);
+/* Ray pass backward from d(loss)/d(per-ray outputs) (NULL = zero). */
+int hsb_render_backward(hsb_ctx* ctx, int32_t slot, const float* d_rgb_values, const float* d_depth_values,
+                        const float* d_normal_map, const float* d_opacity, hsb_stream_t stream);
+
+/* Eikonal pass: x [Ne,3] -> grad_theta [(K+1)*Ne, 3] (K per-channel gradients, then the min-SDF gradient;
+ * network.py:212-254), sample_sdf [Ne,K], sample_minsdf [Ne] (either may be NULL). */
+int hsb_eikonal_forward(hsb_ctx* ctx, const float* x, int64_t Ne, float* grad_theta, float* sample_sdf, float* sample_minsdf,
+                        hsb_stream_t stream);
+int hsb_eikonal_backward(hsb_ctx* ctx, const float* d_grad_theta, const float* d_sample_sdf /* may be NULL */,
+                         hsb_stream_t stream);
+
+/* torch.optim.Adam semantics over one flat segment (holoscene_train.py:156-164); grad_norm_sq (may be NULL)
+ * accumulates sum(g^2) in the same pass (the trainer's total_norm statistic, :367-372). */
+int hsb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                  float beta2, float eps, int step, float* grad_norm_sq, hsb_stream_t stream);
+
+/* Contraction kernels, exposed for their parity tests (epilogue kinds: csrc/gemm.cuh). */
+int hsb_gemm_tn(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K, int epi_kind, float* out,
+                long long ldo, const float* bias, const float* aux, long long ld_aux, long long aux_rows, const float* aux2,
+                long long ld_aux2, float* out2, long long ldo2, int atomic2, int precise, hsb_stream_t stream);
+int hsb_gemm_wgrad(const float* A, long long lda, int N1, const float* B, long long ldb, int N2, long long M, float* C,
+                   long long ldc, float* bias, int precise, hsb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,104 @@
+"""GPU parity: contraction kernels (through the C ABI) against fp64 torch references.
+`precise` = 3xTF32 must reproduce fp32-grade results (1e-5); single-pass TF32 gets the TF32 bound."""
+import ctypes
+
+import pytest
+import torch
+
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+EPI = dict(NONE=0, BIAS=1, SOFTPLUS=2, RELU=3, SIGMOID=4, MUL_SIGMA=5, BWD_CHAIN=6, BWD_SP=7, BWD_RELU=8)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _run_tn(A, B, kind, N, bias=None, aux=None, aux_rows=0, aux2=None, atomic2=0, precise=1, out2_rows=None):
+    from holoscene_b200 import _lib, engine
+    M, K = A.shape
+    out = torch.zeros(M, N, device="cuda")
+    out2 = torch.zeros(out2_rows or M, N, device="cuda") if kind == EPI["BWD_CHAIN"] else None
+    _lib.check(engine.gemm_tn(_p(A), A.stride(0), _p(B), B.stride(0), M, N, K, kind, _p(out), N, _p(bias), _p(aux),
+                              aux.stride(0) if aux is not None else 0, aux_rows, _p(aux2), aux2.stride(0) if aux2 is not None else 0,
+                              _p(out2), N, atomic2, precise, _lib.stream()))
+    torch.cuda.synchronize()
+    return out, out2
+
+
+def _sigma(h):
+    return 1.0 - torch.exp(-100.0 * h)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 72), (1, 256, 256), (4097, 32, 256), (513, 27, 256), (129, 256, 344), (1000, 256, 8)])
+@pytest.mark.parametrize("precise", [1, 0])
+def test_gemm_tn_linear_epilogues(M, N, K, precise):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = A.double() @ B.double().t()
+    tol = 2e-5 if precise else 3e-3
+    out, _ = _run_tn(A, B, EPI["NONE"], N, precise=precise)
+    assert common.rel_err(out.cpu(), ref.cpu()) < tol
+    out, _ = _run_tn(A, B, EPI["BIAS"], N, bias=bias, precise=precise)
+    assert common.rel_err(out.cpu(), (ref + bias.double()).cpu()) < tol
+    out, _ = _run_tn(A, B, EPI["RELU"], N, bias=bias, precise=precise)
+    assert common.rel_err(out.cpu(), torch.relu(ref + bias.double()).cpu()) < tol
+    out, _ = _run_tn(A, B, EPI["SIGMOID"], N, bias=bias, precise=precise)
+    assert common.rel_err(out.cpu(), torch.sigmoid(ref + bias.double()).cpu()) < tol
+    out, _ = _run_tn(A, B * 0.05, EPI["SOFTPLUS"], N, bias=bias * 0.02, precise=precise)
+    sp = torch.nn.functional.softplus(ref * 0.05 + 0.02 * bias.double(), beta=100)
+    assert float((out.cpu().double() - sp.cpu()).abs().max()) < (2e-6 if precise else 3e-4)
+
+
+def test_gemm_tn_chain_epilogues():
+    g = torch.Generator().manual_seed(5)
+    M, N, K, rows = 700, 256, 256, 100          # aux indexed modulo `rows` (eikonal seed blocks)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = (torch.randn(N, K, generator=g) / 16).cuda()
+    h = (torch.rand(rows, N, generator=g) * 0.05).cuda()
+    pfull = torch.randn(M, N, generator=g).cuda()
+    ref = (A.double() @ B.double().t())
+    sg = _sigma(h.double()).repeat(7, 1)
+    out, _ = _run_tn(A, B, EPI["MUL_SIGMA"], N, aux=h, aux_rows=rows)
+    assert common.rel_err(out.cpu(), (ref * sg).cpu()) < 2e-5
+    out, out2 = _run_tn(A, B, EPI["BWD_CHAIN"], N, aux=h, aux_rows=rows, aux2=pfull, atomic2=1, out2_rows=rows)
+    assert common.rel_err(out.cpu(), (ref * sg).cpu()) < 2e-5
+    want2 = (ref * pfull.double() * 100.0 * (1.0 - sg)).view(7, rows, N).sum(0)
+    assert common.rel_err(out2.cpu(), want2.cpu()) < 2e-5
+    hM = h.repeat(7, 1).contiguous()
+    out, out2 = _run_tn(A, B, EPI["BWD_CHAIN"], N, aux=hM, aux2=pfull)
+    assert common.rel_err(out2.cpu(), (ref * pfull.double() * 100.0 * (1.0 - sg)).cpu()) < 2e-5
+    out, _ = _run_tn(A, B, EPI["BWD_SP"], N, aux=hM, aux2=pfull)
+    assert common.rel_err(out.cpu(), (ref * sg + pfull.double()).cpu()) < 2e-5
+    out, _ = _run_tn(A, B, EPI["BWD_RELU"], N, aux=pfull)
+    assert common.rel_err(out.cpu(), (ref * (pfull.double() > 0)).cpu()) < 2e-5
+
+
+@pytest.mark.parametrize("M,N1,N2", [(5000, 256, 72), (33, 256, 344), (100000, 32, 256), (777, 4, 256), (4096, 256, 32)])
+@pytest.mark.parametrize("precise", [1, 0])
+def test_gemm_wgrad(M, N1, N2, precise):
+    from holoscene_b200 import _lib, engine
+    g = torch.Generator().manual_seed(M)
+    A = torch.randn(M, N1, generator=g).cuda()
+    B = torch.randn(M, N2, generator=g).cuda()
+    C = torch.ones(N1, N2, device="cuda")            # accumulate semantics
+    bias = torch.full((N1,), 2.0, device="cuda")
+    _lib.check(engine.gemm_wgrad(_p(A), N1, N1, _p(B), N2, N2, M, _p(C), N2, _p(bias), precise, _lib.stream()))
+    torch.cuda.synchronize()
+    ref = A.double().t() @ B.double() + 1.0
+    tol = 2e-5 if precise else 3e-3
+    assert common.rel_err(C.cpu(), ref.cpu()) < tol
+    assert common.rel_err(bias.cpu(), (A.double().sum(0) + 2.0).cpu()) < 1e-5
+
+
+def test_gemm_rejects_misaligned_operands():
+    from holoscene_b200 import _lib, engine
+    A = torch.zeros(8, 70, device="cuda")
+    B = torch.zeros(8, 70, device="cuda")
+    out = torch.zeros(8, 8, device="cuda")
+    st = engine.gemm_tn(_p(A), 70, _p(B), 70, 8, 8, 70, 0, _p(out), 8, None, None, 0, 0, None, 0, None, 0, 0, 1, _lib.stream())
+    assert st == 1 and b"multiples of 4" in _lib.lib.hsb_last_error()

@@ -1,0 +1,150 @@
+"""CPU: host-side logic that needs no GPU -- C-ABI exports, conf reader, reference-identical
+initialisation / state_dict layout, parameter-segment layout."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from holoscene_b200 import conf as hconf
+from tests import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CONF_TEXT = """
+train{
+    expname = holoscene_replica_room_0
+    model_class = holoscene_b200.network.HoloSceneNetwork   # drop-in
+    loss_class = holoscene_b200.loss.HoloSceneLoss
+    learning_rate = 5.0e-4
+    num_pixels = 1024
+}
+loss{
+    rgb_loss = torch.nn.L1Loss
+    eikonal_weight = 0.1
+    semantic_weight = 5.0
+}
+model{
+    feature_vector_size = 256
+    scene_bounding_sphere = 1.0
+    use_bg_reg = True
+    render_bg_iter = 10
+    implicit_network
+    {
+        d_in = 3
+        d_out = 4
+        dims = [256, 256]
+        geometric_init = True
+        bias = 0.9
+        skip_in = [4]
+        weight_norm = True
+        multires = 6
+        inside_outside = True
+        use_grid_feature = True
+        divide_factor = 1.0
+        sigmoid = 10
+        color_grid_feature = True
+        logmap = 12
+    }
+    rendering_network
+    {
+        mode = idr
+        d_in = 9
+        d_out = 3                       # 3 for rgb
+        dims = [256, 256]
+        weight_norm = True
+        multires_view = 4
+        multires_point = 4
+        multires_normal = 4
+    }
+    density
+    {
+        params_init{
+            beta = 0.1
+        }
+        beta_min = 0.0001
+    }
+    ray_sampler
+    {
+        near = 0.0
+        N_samples = 16
+        N_samples_eval = 32
+        N_samples_extra = 8
+        eps = 0.1
+        beta_iters = 10
+        max_total_iters = 5
+    }
+}
+"""
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hsb200.h")).read()
+    names = set(re.findall(r"\b(hsb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 18
+    lib = ctypes.CDLL(os.path.join(ROOT, "holoscene_b200", "libhsb200.so"))
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/hsb200.h but not exported"
+    lib.hsb_abi_version.restype = ctypes.c_int
+    assert lib.hsb_abi_version() == 1
+
+
+def test_conf_reader_matches_reference_conf_format():
+    c = hconf.parse_string(CONF_TEXT)
+    assert c.get_string("train.model_class") == "holoscene_b200.network.HoloSceneNetwork"
+    assert c.get_float("train.learning_rate") == 5.0e-4
+    assert c.get_int("model.ray_sampler.N_samples") == 16
+    assert c.get_list("model.implicit_network.dims") == [256, 256]
+    assert c.get_bool("model.use_bg_reg") is True
+    assert c.get_float("model.density.params_init.beta") == 0.1
+    assert c.get_string("model.rendering_network.mode") == "idr"
+    assert c.get_int("train.missing", default=7) == 7
+    with pytest.raises(KeyError):
+        c.get_int("train.missing")
+    sub = c.get_config("model.implicit_network")
+    assert sub["d_out"] == 4 and sub["skip_in"] == [4]
+
+
+def test_model_init_and_state_dict_match_reference_layout():
+    """Same seed -> same weights as the reference model (checked against the oracle's init, which
+    tests/golden/make_golden.py asserts equal to the reference's own state_dict)."""
+    from holoscene_b200.network import HoloSceneNetwork
+    from oracle import model as om
+    c = hconf.parse_string(CONF_TEXT)
+    torch.manual_seed(42)
+    m = HoloSceneNetwork(c.get_config("model"))
+    cfg = om.StepConfig(d_out=4, logmap=12, N_samples=16, N_samples_eval=32, N_samples_extra=8)
+    torch.manual_seed(42)
+    sd = om.init_state_dict(cfg)
+    msd = m.state_dict()
+    assert list(msd.keys()) == list(sd.keys())
+    for k in sd:
+        assert msd[k].shape == sd[k].shape, k
+        assert torch.equal(msd[k], sd[k]), k
+    # trainer-facing accessors (training/holoscene_train.py:157-163)
+    assert len(m.implicit_network.grid_parameters()) == 2
+    assert len(m.implicit_network.mlp_parameters()) == 13
+    assert len(list(m.rendering_network.parameters())) == 9
+    assert float(m.density.get_beta()) == pytest.approx(0.1001)
+
+
+def test_param_segment_layout_is_aligned_and_ordered():
+    lib = ctypes.CDLL(os.path.join(ROOT, "holoscene_b200", "libhsb200.so"))
+    arr = (ctypes.c_int64 * 26)()
+    lib.hsb_param_layout.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]
+    assert lib.hsb_param_layout(32, 6098108, arr) == 0
+    offs = list(arr)
+    assert offs[0] == 0 and all(o % 4 == 0 for o in offs) and all(b > a for a, b in zip(offs, offs[1:]))
+    assert offs[2] - offs[0] == 2 * 2 * 6098108            # the two hash tables lead the buffer
+    assert lib.hsb_param_layout(65, 10, arr) == 1           # K > 64 rejected with a status, not a crash
+
+
+def test_forward_without_cuda_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from holoscene_b200.network import HoloSceneNetwork
+    c = hconf.parse_string(CONF_TEXT)
+    m = HoloSceneNetwork(c.get_config("model"))
+    with pytest.raises(RuntimeError):
+        m({"uv": torch.zeros(1, 4, 2), "intrinsics": torch.eye(4)[None], "pose": torch.eye(4)[None]}, torch.tensor([0]))
