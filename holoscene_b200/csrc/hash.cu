@@ -68,6 +68,9 @@ __device__ __forceinline__ float corner_w(const Cell& c, int i) {
     return w;
 }
 
+// 2-float load from a row that is only guaranteed 4-byte aligned
+__device__ __forceinline__ float2 ld2(const float* __restrict__ p) { return make_float2(p[0], p[1]); }
+
 __device__ __forceinline__ void load_xyz(const float* __restrict__ x, long long p, int map01, float& a, float& b, float& c) {
     a = x[p * 3 + 0]; b = x[p * 3 + 1]; c = x[p * 3 + 2];
     if (map01) { a = (a + 1.0f) * 0.5f; b = (b + 1.0f) * 0.5f; c = (c + 1.0f) * 0.5f; }
@@ -88,10 +91,10 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
     load_xyz(x, p, map01, xa, xb, xc);
     Cell c;
     locate(xa, xb, xc, offsets, level, S, H, c);
-    float2* o = reinterpret_cast<float2*>(out + (long long)level * out_ls + (long long)p * out_ps);
+    float* o = out + (long long)level * out_ls + (long long)p * out_ps;   // may be only 4-byte aligned (MLP row, column 39)
     float* dd = dy_dx ? dy_dx + (long long)p * dy_ps + level * 6 : nullptr;
     if (c.oob) {
-        *o = make_float2(0.f, 0.f);
+        o[0] = 0.f; o[1] = 0.f;
         if (dd) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) reinterpret_cast<float2*>(dd)[i] = make_float2(0.f, 0.f);
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
         r.x += w * v[i].x;
         r.y += w * v[i].y;
     }
-    *o = r;
+    o[0] = r.x; o[1] = r.y;
     if (!dd) return;
     // d/dx_gd = sum over the 4 corners of the other two axes of scale*w_other*(right-left)*smoothstep'
 #pragma unroll
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const float* __restrict__
     Cell c;
     locate(xa, xb, xc, offsets, level, S, H, c);
     if (c.oob) return;
-    const float2 g = *reinterpret_cast<const float2*>(grad + (long long)level * g_ls + (long long)p * g_ps);
+    const float2 g = ld2(grad + (long long)level * g_ls + (long long)p * g_ps);
     float2* tab = grad_table + (uint32_t)offsets[level];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256) hash_input_bwd_kernel(const float* __rest
     const float* dd = dy_dx + (long long)p * dy_ps;
     float r = 0.f;
     for (uint32_t l = 0; l < L; ++l) {
-        const float2 g = *reinterpret_cast<const float2*>(grad + (long long)l * g_ls + (long long)p * g_ps);
+        const float2 g = ld2(grad + (long long)l * g_ls + (long long)p * g_ps);
         r += g.x * dd[l * 6 + d * 2 + 0];
         r += g.y * dd[l * 6 + d * 2 + 1];
     }
@@ -208,13 +211,14 @@ __global__ void __launch_bounds__(256) hash_bwd2_kernel(const float* __restrict_
     float2 gg = make_float2(0.f, 0.f);
 #pragma unroll
     for (int d = 0; d < 3; ++d) { gg.x += gx[d] * dd[d * 2]; gg.y += gx[d] * dd[d * 2 + 1]; }
-    *reinterpret_cast<float2*>(grad_grad + (long long)level * gg_ls + (long long)p * gg_ps) = gg;
+    float* ggo = grad_grad + (long long)level * gg_ls + (long long)p * gg_ps;
+    ggo[0] = gg.x; ggo[1] = gg.y;
     float xa, xb, xc;
     load_xyz(x, p, map01, xa, xb, xc);
     Cell c;
     locate(xa, xb, xc, offsets, level, S, H, c);
     if (c.oob) return;
-    const float2 g = *reinterpret_cast<const float2*>(grad + (long long)level * g_ls + (long long)p * g_ps);
+    const float2 g = ld2(grad + (long long)level * g_ls + (long long)p * g_ps);
     float2 cache[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) cache[i] = make_float2(0.f, 0.f);
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(256) hash_bwd_fused_kernel(const float* __rest
     if (c.oob) return;
     float2 cache[8];
     float2 g1 = make_float2(0.f, 0.f);
-    if (dE) g1 = *reinterpret_cast<const float2*>(dE + (long long)p * e_ps + level * 2);
+    if (dE) g1 = ld2(dE + (long long)p * e_ps + level * 2);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float w = corner_w(c, i);
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(256) hash_bwd_fused_kernel(const float* __rest
     if (q0E) {
         for (uint32_t s = 0; s < nseed; ++s) {
             const long long r = (long long)s * B + p;
-            float2 q = *reinterpret_cast<const float2*>(q0E + r * q_ps + level * 2);
+            float2 q = ld2(q0E + r * q_ps + level * 2);
             q.x *= 0.5f; q.y *= 0.5f;
             const float gx[3] = {dg[r * 3 + 0], dg[r * 3 + 1], dg[r * 3 + 2]};
             second_order_cache(c, q, gx, cache);
@@ -278,8 +282,8 @@ extern "C" int hsb_hash_forward(const float* inputs, const float* embeddings, co
                                 long long out_level_stride, long long out_point_stride, float* dy_dx,
                                 long long dy_point_stride, uint32_t B, uint32_t L, float S, uint32_t H, int map01,
                                 cudaStream_t stream) {
-    if (!inputs || !embeddings || !offsets || !outputs || L == 0 || L > 32) { set_error("hsb_hash_forward: bad argument"); return HSB_ERR_ARG; }
     if (B == 0) return HSB_OK;
+    if (!inputs || !embeddings || !offsets || !outputs || L == 0 || L > 32) { set_error("hsb_hash_forward: bad argument"); return HSB_ERR_ARG; }
     dim3 grid(cdiv(B, 256), L);
     hash_fwd_kernel<<<grid, 256, 0, stream>>>(inputs, reinterpret_cast<const float2*>(embeddings), offsets, outputs,
                                               out_level_stride, out_point_stride, dy_dx, dy_point_stride, B, L, S, H, map01);
@@ -290,8 +294,8 @@ extern "C" int hsb_hash_backward(const float* grad, long long g_level_stride, lo
                                  const float* inputs, const int32_t* offsets, float* grad_embeddings,
                                  const float* dy_dx, long long dy_point_stride, float* grad_inputs, uint32_t B, uint32_t L,
                                  float S, uint32_t H, int map01, cudaStream_t stream) {
-    if (!grad || !inputs || !offsets || !grad_embeddings || L == 0 || L > 32) { set_error("hsb_hash_backward: bad argument"); return HSB_ERR_ARG; }
     if (B == 0) return HSB_OK;
+    if (!grad || !inputs || !offsets || !grad_embeddings || L == 0 || L > 32) { set_error("hsb_hash_backward: bad argument"); return HSB_ERR_ARG; }
     dim3 grid(cdiv(B, 256), L);
     hash_bwd_kernel<<<grid, 256, 0, stream>>>(grad, g_level_stride, g_point_stride, inputs, offsets,
                                               reinterpret_cast<float2*>(grad_embeddings), B, L, S, H, map01);
@@ -307,6 +311,7 @@ extern "C" int hsb_hash_second_backward(const float* grad, long long g_level_str
                                         long long gg_level_stride, long long gg_point_stride, float* grad2_embeddings,
                                         uint32_t B, uint32_t L, float S, uint32_t H, int map01, cudaStream_t stream) {
     if (!grad || !inputs || !offsets || !dy_dx || !grad_grad_inputs || !grad_grad || !grad2_embeddings || L == 0 || L > 32) {
+        if (B == 0) return HSB_OK;
         set_error("hsb_hash_second_backward: bad argument");
         return HSB_ERR_ARG;
     }
@@ -322,8 +327,8 @@ extern "C" int hsb_hash_backward_fused(const float* x_world, const int32_t* offs
                                        const float* q0E, long long q_point_stride, const float* dg, uint32_t nseed,
                                        float* grad_embeddings, uint32_t B, uint32_t L, float S, uint32_t H,
                                        cudaStream_t stream) {
-    if (!x_world || !offsets || !grad_embeddings || L == 0 || L > 32 || (q0E && !dg)) { set_error("hsb_hash_backward_fused: bad argument"); return HSB_ERR_ARG; }
     if (B == 0) return HSB_OK;
+    if (!x_world || !offsets || !grad_embeddings || L == 0 || L > 32 || (q0E && !dg)) { set_error("hsb_hash_backward_fused: bad argument"); return HSB_ERR_ARG; }
     dim3 grid(cdiv(B, 256), L);
     hash_bwd_fused_kernel<<<grid, 256, 0, stream>>>(x_world, offsets, dE, e_point_stride, q0E, q_point_stride, dg, nseed,
                                                     reinterpret_cast<float2*>(grad_embeddings), B, L, S, H);

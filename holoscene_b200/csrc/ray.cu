@@ -63,7 +63,11 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(CompositeArgs a) {
         }
         const float E = ok ? delta * laplace_density(s_w, beta) : 0.0f;
         const float incl = warp_scan_incl(E, lane);
-        const float F = carry + incl - E;
+        // exclusive prefix through a shuffle, NOT incl - E: the last interval is 1e10 long, so E ~ 1e11 there and
+        // (prefix + E) - E cancels to 0 in fp32
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.0f;
+        const float F = carry + excl;
         const float T = expf(-F);
         const float w = ok ? (1.0f - expf(-E)) * T : 0.0f;
         carry += __shfl_sync(0xffffffffu, incl, 31);
@@ -71,7 +75,9 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(CompositeArgs a) {
         if (a.mode == 1) {        // scene weights for the semantic composite
             const float E2 = ok ? delta * laplace_density(s_scene, beta) : 0.0f;
             const float incl2 = warp_scan_incl(E2, lane);
-            T2 = expf(-(carry2 + incl2 - E2));
+            float excl2 = __shfl_up_sync(0xffffffffu, incl2, 1);
+            if (lane == 0) excl2 = 0.0f;
+            T2 = expf(-(carry2 + excl2));
             w2 = ok ? (1.0f - expf(-E2)) * T2 : 0.0f;
             carry2 += __shfl_sync(0xffffffffu, incl2, 31);
         }
@@ -206,7 +212,9 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeArgs a, Com
         }
         const float v = aw + cj;
         const float sfx = warp_scan_incl_rev(v, lane);
-        const float after = carry + sfx - v;                       // sum over j > i
+        float after = __shfl_down_sync(0xffffffffu, sfx, 1);       // sum over j > i within the chunk
+        if (lane == 31) after = 0.0f;
+        after += carry;
         carry += __shfl_sync(0xffffffffu, sfx, 0);
         if (ok) {
             const float dE = ai * T * expf(-E) - after;

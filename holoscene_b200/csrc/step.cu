@@ -76,6 +76,7 @@ struct Ctx {
     float *dW0e, *dW1e, *dW2e, *dB2e, *dR0e, *dR1e, *dR2e, *dRB2e;
     char* dwe_begin; size_t dwe_bytes;
     Slot slot[3];
+    Slot scratch;   // X, H0, H1, H2, SR only: hsb_sdf_values between a slot's forward and its backward
     float* P(int seg) const { return params + off[seg]; }
     float* Gp(int seg) const { return grads + off[seg]; }
 };
@@ -118,6 +119,14 @@ static void carve_slot(Ctx* c, int idx, const char* pre, long long points, int m
     }
 }
 
+static void carve_scratch(Ctx* c, long long points, bool dry) {
+    Slot& s = c->scratch;
+    s.cap_points = points;
+    s.X = carve(c, "samp.X", points, 3, dry);       s.H0 = carve(c, "samp.H0", points, LD_H0, dry);
+    s.H1 = carve(c, "samp.H1", points, 256, dry);   s.H2 = carve(c, "samp.H2", points, 256, dry);
+    s.SR = carve(c, "samp.SR", points, c->Kp, dry);
+}
+
 static void carve_all(Ctx* c, bool dry) {
     c->ws_used = 0;
     const int Kp = c->Kp;
@@ -138,6 +147,7 @@ static void carve_all(Ctx* c, bool dry) {
     carve_slot(c, HSB_SLOT_MAIN, "main", c->cfg.max_points, 1, c->cfg.max_rays, true, dry);
     carve_slot(c, HSB_SLOT_EIK, "eik", c->cfg.max_eik_points, c->K + 1, 0, false, dry);
     carve_slot(c, HSB_SLOT_BG, "bg", c->cfg.max_bg_points, 1, c->cfg.max_bg_rays, false, dry);
+    carve_scratch(c, c->cfg.max_points, dry);
 }
 
 #define TRY(x) do { int _e = (x); if (_e != HSB_OK) return _e; } while (0)
@@ -321,11 +331,12 @@ extern "C" int hsb_finish(hsb_ctx* h, cudaStream_t st) {
 }
 
 // SDF values (min over K, or one channel) at the points o + z d of a ray batch -- the sampler's no-grad queries
-// (model/ray_sampler.py:150-156).  Uses the main slot's forward buffers as scratch.
+// (model/ray_sampler.py:150-156).  Runs in its own scratch buffers ("samp.*"): the background-patch sampler is
+// called between the main pass forward and its backward and must not touch the saved activations.
 extern "C" int hsb_sdf_values(hsb_ctx* h, const float* o, const float* d, const float* z, int32_t R, int32_t S, int32_t channel,
                               float* sdf_out, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
-    Slot& s = c->slot[HSB_SLOT_MAIN];
+    Slot& s = c->scratch;
     const long long N = (long long)R * S;
     if (N > s.cap_points || channel >= c->K) { set_error("hsb_sdf_values: batch exceeds max_points / bad channel"); return HSB_ERR_ARG; }
     TRY(launch_ray_points(o, d, z, R, S, s.X, s.H0, nullptr, st));

@@ -103,7 +103,7 @@ class ObjectImplicitNetworkGrid(nn.Module):
             n = xb.shape[0]
             zeros = torch.zeros(n, 3, device=x.device)
             eng.sdf_values(xb, zeros, torch.zeros(n, 1, device=x.device), -1)
-            outs.append(eng.buffer("main.SR")[:n, : self.d_out].clone())
+            outs.append(eng.buffer("samp.SR")[:n, : self.d_out].clone())
         return torch.cat(outs, 0) if outs else torch.empty(0, self.d_out, device=x.device)
 
     @torch.no_grad()

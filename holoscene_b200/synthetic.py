@@ -11,8 +11,10 @@ from __future__ import annotations
 import torch
 
 
-def camera(fx: float = 300.0, cx: float = 256.0, origin=(0.1, 0.0, -0.2)):
-    """Replica-like pinhole camera inside the unit cube: returns (intrinsics [1,4,4], pose [1,4,4])."""
+def camera(fx: float = 300.0, cx: float = 256.0, origin=(0.05, 0.1, -0.43)):
+    """Replica-like pinhole camera inside the unit cube: returns (intrinsics [1,4,4], pose [1,4,4]).
+    The default origin sits in the free-space shell of the geometric initialisation (objects: |x| < ~0.27,
+    background wall: |x| > ~0.6), so rays start at positive SDF and cross object / wall surfaces."""
     K = torch.eye(4)[None].clone()
     K[0, 0, 0] = fx
     K[0, 1, 1] = fx
@@ -37,13 +39,15 @@ def rays_and_gt(R: int, K: int, seed: int = 44, img: int = 512):
     return uv, gt
 
 
-def perturb_state_dict(sd: dict, seed: int = 43, emb_std: float = 0.01, w0_std: float = 0.05,
-                       b2_std: float = 0.1, w2_std: float = 0.01) -> dict:
+def perturb_state_dict(sd: dict, seed: int = 43, emb_std: float = 0.05, w0_std: float = 0.004,
+                       b2_std: float = 0.05, w2_std: float = 0.005) -> dict:
     """Geometric init zeroes every SDF-net input weight except xyz (reference model/network.py:146-149)
     and makes all object channels near-identical spheres, so a freshly initialised model never
     exercises the hash grid, the positional encoding or the arg-min over objects.  This adds fixed
     Gaussian noise (own generator, so the global RNG stream is untouched) to the hash tables, to the
-    PE/hash columns of lin0 and to lin2 so that every term of the step carries signal."""
+    PE/hash columns of lin0 and to lin2 so that every term of the step carries signal, while keeping the
+    field SDF-like (|grad| ~ 1.2, two to three sign changes per ray, three refinement rounds of the sampler):
+    a rougher field makes PE4(gradient) -> ReLU masks chaotic and turns 1e-4 of fp32 noise into percents."""
     g = torch.Generator().manual_seed(seed)
     sd = {k: v.clone() for k, v in sd.items()}
     for k in sorted(sd):

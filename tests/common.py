@@ -45,3 +45,14 @@ def rel_err(a, b):
     a = torch.as_tensor(a).double()
     b = torch.as_tensor(b).double()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def grad_tol(name, base):
+    """Relative-L2 tolerance for d(loss)/d(param).  The render net eats PE4 of the RAW sdf gradient
+    (reference network.py:596, up to sin/cos(8 g)) followed by ReLUs: a 1e-4 relative change of g flips
+    enough ReLU masks to move the colour-path gradients by 1-2 % -- measured between the reference's own
+    CPU run and this repo's CPU oracle (tests/test_oracle_model.py), i.e. it is the fp32 noise floor of the
+    reference graph itself, not a property of the kernels.  Everything upstream of that input (SDF net, SDF
+    hash table, beta, lin2 of the render net) is well conditioned and held to `base`."""
+    chaotic = ("color_encoding", "color_grid_feature_map_mlp", "rendering_network.lin0", "rendering_network.lin1")
+    return 5e-2 if any(c in name for c in chaotic) else base

@@ -15,7 +15,8 @@ def make_case(B=512, logmap=19, seed=1234, emb_scale=0.1):
     edge = torch.tensor([[0, 0, 0], [1, 1, 1], [1, 0, 0.5], [0.5, 1, 0], [0, 0.25, 1], [1.0000001, 0.5, 0.5],
                          [-1e-7, 0.5, 0.5], [0.5, 2.25, 0.5], [0.5, 0.5, -3.0], [0.999999, 0.999999, 0.999999]],
                         dtype=torch.float32)
-    x[: edge.shape[0]] = edge
+    n_edge = min(B, edge.shape[0])
+    x[:n_edge] = edge[:n_edge]
     grad = torch.randn(16, B, 2, generator=g)
     ggx = torch.randn(B, 3, generator=g)
     S = float(np.float32(np.log2(pls)))

@@ -98,7 +98,7 @@ def test_step_matches_reference_golden_precise(name):
                 rows.append((k, abs(float(losses[k[5:]]) - float(ref)) / max(1.0, abs(float(ref))), 1e-3))
         for k, ref in g.items():
             if k.startswith("grad_"):
-                rows.append((k, common.rel_err(grads[k[5:]], ref), 1e-2))
+                rows.append((k, common.rel_err(grads[k[5:]], ref), common.grad_tol(k, 1e-2)))
     report(name + " precise", rows)
     bad = [r for r in rows if not (r[1] <= r[2])]
     assert not bad, bad
@@ -114,7 +114,7 @@ def test_step_fast_tf32_within_stated_tolerance():
     rows.append(("loss", abs(float(losses["loss"]) - float(g["loss_loss"])) / abs(float(g["loss_loss"])), 1e-2))
     for k, ref in g.items():
         if k.startswith("grad_"):
-            rows.append((k, common.rel_err(grads[k[5:]], ref), 5e-2))
+            rows.append((k, common.rel_err(grads[k[5:]], ref), 3 * common.grad_tol(k, 2e-2)))
     report("step_train fast", rows)
     bad = [r for r in rows if not (r[1] <= r[2])]
     assert not bad, bad
@@ -176,3 +176,96 @@ def test_adam_matches_torch():
         torch.cuda.synchronize()
         assert abs(float(nrm) - float((gr.double() ** 2).sum())) < 1e-4 * float((gr.double() ** 2).sum())
     assert float((eng_p.cpu() - pt.detach()).abs().max()) < 1e-5
+
+
+def _oracle_main_pass(sd, cfg, o, d, z, rot, ds):
+    """Scene pass of the oracle on given rays / sample depths -> differentiable per-ray outputs."""
+    from oracle import model as om
+    R, S = z.shape
+    pts = (o.unsqueeze(1) + z.unsqueeze(2) * d.unsqueeze(1)).reshape(-1, 3)
+    sdf, feat, grads, sem, raw = om.get_outputs(sd, cfg, pts)
+    rgb = om.rendering_forward(sd, cfg, pts, grads, d.unsqueeze(1).repeat(1, S, 1).reshape(-1, 3), feat).reshape(R, S, 3)
+    beta = om.get_beta(sd, cfg)
+    w, T, dists = om.volume_weights(z, sdf, beta)
+    dens = om.laplace_density(raw, beta).transpose(0, 1).reshape(-1, R, S)
+    opac = ((1 - torch.exp(-dists * dens)) * T).sum(-1).transpose(0, 1)
+    rgbv = (w.unsqueeze(-1) * rgb).sum(1)
+    depth = ds * ((w * z).sum(1, keepdim=True) / (w.sum(1, keepdim=True) + 1e-8))
+    n = grads / (grads.norm(2, -1, keepdim=True) + 1e-6)
+    nmap = ((w.unsqueeze(-1) * n.reshape(R, S, 3)).sum(1) @ rot.t())
+    return rgbv, depth, nmap, opac
+
+
+@pytest.mark.parametrize("precise,tol", [(True, 2e-3), (False, 2e-2)])
+def test_main_pass_backward_matches_oracle_on_identical_samples(precise, tol):
+    """Kernel-level gradient parity, isolated from sampler noise and from the loss: the SAME z_vals on both
+    sides and RANDOM cotangents for the four differentiable per-ray outputs; every parameter gradient of the
+    fused backward (incl. the double backward through d sdf/dx and both hash tables) against autograd on the oracle."""
+    from holoscene_b200 import engine as E
+    from oracle import model as om
+    g = common.load_golden("step_train")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    m = build_model(cfg, sd, precise)
+    m.train()
+    eng = m.engine()
+    m._attach_grads()
+    eng.prepare()
+    R, S = g["out_z_vals"].shape
+    z = torch.from_numpy(g["out_z_vals"])
+    gen = torch.Generator().manual_seed(3)
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=gen), dim=1)
+    o = torch.tensor([[0.1, 0.0, -0.2]]).repeat(R, 1)
+    ds = torch.rand(R, 1, generator=gen) + 0.5
+    rot = torch.linalg.qr(torch.randn(3, 3, generator=gen))[0].contiguous()
+    cot = [torch.randn(R, 3, generator=gen), torch.randn(R, 1, generator=gen), torch.randn(R, 3, generator=gen),
+           torch.randn(R, cfg.d_out, generator=gen)]
+    p = om.trainable(sd)
+    outs = _oracle_main_pass(p, cfg, o, d, z, rot, ds)
+    sum((a * b).sum() for a, b in zip(outs, cot)).backward()
+    got = eng.render_forward(E.SLOT_MAIN, o.cuda(), d.cuda(), z.cuda().contiguous(), ds.cuda(), rot.cuda())
+    eng.render_backward(E.SLOT_MAIN, *[c.cuda() for c in cot])
+    eng.finish()
+    torch.cuda.synchronize()
+    rows = [(f"out{i}", common.rel_err(got[i].cpu(), outs[i].detach()), 1e-4 if precise else 2e-2) for i in range(4)]
+    for n, prm in m.named_parameters():
+        ref = p[n].grad if p[n].grad is not None else torch.zeros_like(p[n])
+        rows.append(("grad_" + n, common.rel_err(prm.grad.cpu(), ref), common.grad_tol(n, tol) if precise else 3 * common.grad_tol(n, tol)))
+    report(f"main pass backward, identical samples, precise={precise}", rows)
+    bad = [r for r in rows if not (r[1] <= r[2])]
+    assert not bad, bad
+
+
+def test_eikonal_pass_backward_matches_oracle():
+    """Same idea for the eikonal pass: K+1 stacked gradients at fixed points, random cotangents on grad_theta and sample_sdf."""
+    from oracle import model as om
+    g = common.load_golden("step_train_k3")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    m = build_model(cfg, sd, True)
+    m.train()
+    eng = m.engine()
+    m._attach_grads()
+    eng.prepare()
+    gen = torch.Generator().manual_seed(11)
+    x = torch.rand(200, 3, generator=gen) * 2.1 - 1.05         # a few points outside the hash grid's range
+    K = cfg.d_out
+    cot_g = torch.randn((K + 1) * 200, 3, generator=gen)
+    cot_s = torch.randn(200, K, generator=gen)
+    p = om.trainable(sd)
+    gt = om.all_gradients(p, cfg, x)
+    raw, _ = om.implicit_forward(p, cfg, x)
+    ((gt * cot_g).sum() + (raw * cot_s).sum()).backward()
+    ggt, ssdf, smin = eng.eikonal_forward(x.cuda())
+    eng.eikonal_backward(cot_g.cuda(), cot_s.cuda())
+    eng.finish()
+    torch.cuda.synchronize()
+    rows = [("grad_theta", common.rel_err(ggt.cpu(), gt.detach()), 1e-3), ("sample_sdf", common.rel_err(ssdf.cpu(), raw.detach()), 1e-4),
+            ("sample_minsdf", common.rel_err(smin.cpu()[:, 0], raw.detach().min(1)[0]), 1e-4)]
+    for n, prm in m.named_parameters():
+        if p[n].grad is None:
+            continue
+        rows.append(("grad_" + n, common.rel_err(prm.grad.cpu(), p[n].grad), 2e-3))
+    report("eikonal pass backward", rows)
+    bad = [r for r in rows if not (r[1] <= r[2])]
+    assert not bad, bad
