@@ -39,7 +39,7 @@ def rays_and_gt(R: int, K: int, seed: int = 44, img: int = 512):
     return uv, gt
 
 
-def perturb_state_dict(sd: dict, seed: int = 43, emb_std: float = 0.05, w0_std: float = 0.004,
+def perturb_state_dict(sd: dict, seed: int = 43, emb_std: float = 0.2, w0_std: float = 0.006,
                        b2_std: float = 0.05, w2_std: float = 0.005) -> dict:
     """Geometric init zeroes every SDF-net input weight except xyz (reference model/network.py:146-149)
     and makes all object channels near-identical spheres, so a freshly initialised model never
@@ -52,7 +52,14 @@ def perturb_state_dict(sd: dict, seed: int = 43, emb_std: float = 0.05, w0_std: 
     sd = {k: v.clone() for k, v in sd.items()}
     for k in sorted(sd):
         if k.endswith("embeddings"):
-            sd[k] += emb_std * torch.randn(sd[k].shape, generator=g)
+            # 1/f spectrum: level l (cell size ~ 1/res_l) gets std = emb_std * res_0 / res_l, so every level adds
+            # the same gradient magnitude and the field stays smooth at the scale of the finest cells
+            offs = sd[k.replace("embeddings", "offsets")].tolist()
+            L = len(offs) - 1
+            noise = torch.randn(sd[k].shape, generator=g)
+            for l in range(L):
+                noise[offs[l]: offs[l + 1]] *= emb_std * (2.0 ** (-7.0 * l / max(L - 1, 1)))
+            sd[k] += noise
     w0 = sd["implicit_network.lin0.weight_v"]
     w0[:, 3:] += w0_std * torch.randn(w0.shape[0], w0.shape[1] - 3, generator=g)
     sd["implicit_network.lin0.weight_g"] = w0.norm(dim=1, keepdim=True)

@@ -47,12 +47,22 @@ def rel_err(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def grad_tol(name, base):
-    """Relative-L2 tolerance for d(loss)/d(param).  The render net eats PE4 of the RAW sdf gradient
-    (reference network.py:596, up to sin/cos(8 g)) followed by ReLUs: a 1e-4 relative change of g flips
-    enough ReLU masks to move the colour-path gradients by 1-2 % -- measured between the reference's own
-    CPU run and this repo's CPU oracle (tests/test_oracle_model.py), i.e. it is the fp32 noise floor of the
-    reference graph itself, not a property of the kernels.  Everything upstream of that input (SDF net, SDF
-    hash table, beta, lin2 of the render net) is well conditioned and held to `base`."""
+def grad_tol(name, base, e2e=False):
+    """Relative-L2 tolerance for d(loss)/d(param).
+
+    Kernel-level tests (identical sample positions on both sides) hold every gradient to `base`, except the
+    colour path: the render net eats PE4 of the RAW sdf gradient (reference network.py:596, up to sin/cos(8 g))
+    followed by ReLUs, so a 1e-4 relative change of g flips enough ReLU masks to move those gradients by up to
+    2 % on a rough field (measured on the CPU oracle by perturbing g) -- the fp32 noise floor of the reference
+    graph itself; they get max(base, 2e-2).
+
+    End-to-end tests against the reference's golden run (`e2e`) additionally inherit the sampler's noise: z_vals
+    are reproducible to ~1e-4 only (the CDF inversion divides by bin masses down to 1e-5, ray_sampler.py:250-252),
+    i.e. ~20 % of a finest-level cell, which re-distributes the hash-table gradients between neighbouring rows and
+    feeds the same ReLU chaos; table and colour-path gradients get 5e-2 there (measured 1.3e-2 .. 4e-2)."""
     chaotic = ("color_encoding", "color_grid_feature_map_mlp", "rendering_network.lin0", "rendering_network.lin1")
-    return 5e-2 if any(c in name for c in chaotic) else base
+    if any(c in name for c in chaotic):
+        return 5e-2 if e2e else max(2e-2, base)
+    if e2e and "embeddings" in name:
+        return 5e-2
+    return base
