@@ -38,6 +38,12 @@ def _load():
 
 lib = _load()
 ABI_VERSION = lib.hsb_abi_version()
+lib.hsb_launch_count.restype = ctypes.c_ulonglong
+
+
+def launch_count() -> int:
+    """Kernels launched by libhsb200 in this process so far."""
+    return int(lib.hsb_launch_count())
 
 
 def check(status: int):

@@ -10,7 +10,9 @@
 namespace hsb {
 
 void set_error(const char* msg);
-int check_launch(const char* what);
+int check_launch(const char* what);   // also counts one kernel launch (hsb_launch_count)
+int check_cuda(const char* what);     // error check without counting (memcpy / memset only)
+void count_launch(int n);             // extra launches that share one check_launch
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -299,6 +299,7 @@ extern "C" int hsb_hash_backward(const float* grad, long long g_level_stride, lo
     dim3 grid(cdiv(B, 256), L);
     hash_bwd_kernel<<<grid, 256, 0, stream>>>(grad, g_level_stride, g_point_stride, inputs, offsets,
                                               reinterpret_cast<float2*>(grad_embeddings), B, L, S, H, map01);
+    if (grad_inputs && dy_dx) count_launch(1);
     if (grad_inputs && dy_dx)
         hash_input_bwd_kernel<<<cdiv((long long)B * 3, 256), 256, 0, stream>>>(grad, g_level_stride, g_point_stride, dy_dx,
                                                                                dy_point_stride, grad_inputs, B, L);

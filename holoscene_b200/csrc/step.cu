@@ -443,7 +443,7 @@ extern "C" int hsb_eikonal_forward(hsb_ctx* h, const float* x, int64_t Ne, float
         cudaMemcpy2DAsync(sample_sdf, (size_t)c->K * sizeof(float), s.SR, (size_t)c->Kp * sizeof(float), (size_t)c->K * sizeof(float),
                           (size_t)Ne, cudaMemcpyDeviceToDevice, st);
     if (sample_minsdf) cudaMemcpyAsync(sample_minsdf, s.SDF, (size_t)Ne * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    return check_launch("hsb_eikonal_forward");
+    return check_cuda("hsb_eikonal_forward");
 }
 
 extern "C" int hsb_eikonal_backward(hsb_ctx* h, const float* d_grad_theta, const float* d_sample_sdf, cudaStream_t st) {

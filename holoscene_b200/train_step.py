@@ -1,0 +1,41 @@
+"""The body of the Stage-1 hot loop (reference training/holoscene_train.py:332-428) as one callable:
+H2D of the ray batch -> zero_grad -> model -> loss -> backward -> [gradient all-reduce] -> Adam -> LR decay.
+
+Multi-GPU: one process per GPU, identical replicas, each rank renders its own shard of
+the rays; after backward ONE all-reduce(sum) over the flat fp32 gradient buffer (hash tables + MLPs + beta,
+~99 MB at the full conf) through torch.distributed/NCCL, scaled by 1/world so that per-shard mean losses
+average to the global mean; every rank then applies the identical Adam update (no parameter broadcast).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .optim import StageOneAdam
+
+
+class TrainStep:
+    def __init__(self, model, loss_fn, optimizer: StageOneAdam, add_objectvio_iter=25000, world_size=1):
+        self.model, self.loss_fn, self.opt = model, loss_fn, optimizer
+        self.add_objectvio_iter = add_objectvio_iter
+        self.world_size = world_size
+        self.iter_step = 0
+
+    def __call__(self, model_input, ground_truth, indices=None):
+        """model_input / ground_truth may live in (pinned) host memory; they are copied to the device here."""
+        dev = self.model.density.beta.device
+        mi = {k: v.to(dev, non_blocking=True) for k, v in model_input.items()}
+        gt = {k: v.to(dev, non_blocking=True) for k, v in ground_truth.items()}
+        self.opt.zero_grad()
+        out = self.model(mi, indices, iter_step=self.iter_step)
+        out["iter_step"] = self.iter_step
+        losses = self.loss_fn(out, gt, call_reg=self.iter_step >= self.add_objectvio_iter)
+        losses["loss"].backward()
+        if self.world_size > 1:
+            g = self.model.engine().grads
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            g.mul_(1.0 / self.world_size)
+        self.opt.step()
+        self.opt.scheduler_step()
+        self.iter_step += 1
+        return out, losses

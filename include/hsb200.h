@@ -35,6 +35,8 @@ typedef struct CUstream_st* hsb_stream_t; /* == cudaStream_t */
 
 const char* hsb_last_error(void);
 int hsb_abi_version(void);
+/* number of kernels this library has launched in this process (bench.py reports the per-step delta) */
+unsigned long long hsb_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * B2: hash-grid operator
