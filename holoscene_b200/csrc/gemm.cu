@@ -45,47 +45,6 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 // ---------------------------------------------------------------------------------------------
-// epilogue (runtime kind; uniform branch)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_store(const Epi& e, long long m, int n, float acc) {
-    const long long ma = e.aux_rows > 0 ? (m % e.aux_rows) : m;
-    switch (e.kind) {
-        case EPI_NONE:
-            e.out[m * e.ldo + n] = acc;
-            break;
-        case EPI_BIAS:
-            e.out[m * e.ldo + n] = acc + e.bias[n];
-            break;
-        case EPI_BIAS_SOFTPLUS:
-            e.out[m * e.ldo + n] = softplus100(acc + e.bias[n]);
-            break;
-        case EPI_BIAS_RELU:
-            e.out[m * e.ldo + n] = fmaxf(acc + e.bias[n], 0.0f);
-            break;
-        case EPI_BIAS_SIGMOID:
-            e.out[m * e.ldo + n] = 1.0f / (1.0f + expf(-(acc + e.bias[n])));
-            break;
-        case EPI_MUL_SIGMA:   // forward input-gradient chain: p = q * softplus'(a), a known through h = aux
-            e.out[m * e.ldo + n] = acc * sp_sigma(e.aux[ma * e.lda + n]);
-            break;
-        case EPI_BWD_CHAIN: {  // acc = d p ; out = d q = dp*sigma ; out2 += dp * p * 100*(1-sigma)   (softplus'' term)
-            float sg = sp_sigma(e.aux[ma * e.lda + n]);
-            e.out[m * e.ldo + n] = acc * sg;
-            float v = acc * e.aux2[m * e.lda2 + n] * 100.0f * (1.0f - sg);
-            if (e.atomic2) atomicAdd(e.out2 + ma * e.ldo2 + n, v);
-            else e.out2[m * e.ldo2 + n] = v;
-            break;
-        }
-        case EPI_BWD_SP:      // d a = d h * sigma(h) + extra
-            e.out[m * e.ldo + n] = acc * sp_sigma(e.aux[ma * e.lda + n]) + (e.aux2 ? e.aux2[m * e.lda2 + n] : 0.0f);
-            break;
-        case EPI_BWD_RELU:
-            e.out[m * e.ldo + n] = e.aux[ma * e.lda + n] > 0.0f ? acc : 0.0f;
-            break;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // C = epi(A . B^T):  A [M,K] row-major (lda), B [N,K] row-major (ldb); K, lda, ldb multiples of 4
 // ---------------------------------------------------------------------------------------------
 template <bool PRECISE>
@@ -311,6 +270,9 @@ int num_sms() {
 int gemm_tn(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K, const Epi& epi,
             int precise, cudaStream_t stream) {
     if (M <= 0 || N <= 0) return HSB_OK;
+    // precise: 0 = tcgen05 TF32 (Blackwell tensor cores, TMA-fed), 1 = 3xTF32 mma.sync (fp32-grade parity mode),
+    //          2 = single-pass TF32 mma.sync (legacy tensor path, kept as the A/B baseline of the tcgen05 kernel)
+    if (precise == 0 && gemm_tn_tc_eligible(A, lda, B, ldb, M, N, K)) return gemm_tn_tc(A, lda, B, ldb, M, N, K, epi, stream);
     if ((K & 3) || (lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)B) & 15)) {
         set_error("gemm_tn: K, lda, ldb must be multiples of 4 floats and A, B 16-byte aligned");
         return HSB_ERR_ARG;
@@ -324,7 +286,7 @@ int gemm_tn(const float* A, long long lda, const float* B, long long ldb, long l
         cudaFuncSetAttribute(gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    if (precise) gemm_tn_kernel<true><<<grid, 256, smem, stream>>>(A, lda, B, ldb, M, N, K, epi);
+    if (precise == 1) gemm_tn_kernel<true><<<grid, 256, smem, stream>>>(A, lda, B, ldb, M, N, K, epi);
     else gemm_tn_kernel<false><<<grid, 256, smem, stream>>>(A, lda, B, ldb, M, N, K, epi);
     return check_launch("gemm_tn");
 }
@@ -351,7 +313,7 @@ int gemm_wgrad(const float* A, long long lda, int N1, const float* B, long long 
         cudaFuncSetAttribute(gemm_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    if (precise) gemm_wgrad_kernel<true><<<grid, 256, smem, stream>>>(A, lda, N1, B, ldb, N2, M, rps, C, ldc, bias);
+    if (precise == 1) gemm_wgrad_kernel<true><<<grid, 256, smem, stream>>>(A, lda, N1, B, ldb, N2, M, rps, C, ldc, bias);
     else gemm_wgrad_kernel<false><<<grid, 256, smem, stream>>>(A, lda, N1, B, ldb, N2, M, rps, C, ldc, bias);
     return check_launch("gemm_wgrad");
 }

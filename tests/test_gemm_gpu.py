@@ -1,5 +1,9 @@
 """GPU parity: contraction kernels (through the C ABI) against fp64 torch references.
-`precise` = 3xTF32 must reproduce fp32-grade results (1e-5); single-pass TF32 gets the TF32 bound."""
+precise = 1: 3xTF32 mma.sync, must reproduce fp32-grade results (2e-5);
+precise = 0: tcgen05 kind::tf32 (TMA-fed, TMEM accumulator) -- the tensor core truncates fp32 operands to TF32
+             (10-bit mantissa), bound 5e-3 relative L2;
+precise = 2: single-pass TF32 mma.sync with round-to-nearest operands (legacy tensor path), bound 3e-3."""
+TOL = {1: 2e-5, 0: 5e-3, 2: 3e-3}
 import ctypes
 
 import pytest
@@ -33,14 +37,14 @@ def _sigma(h):
 
 
 @pytest.mark.parametrize("M,N,K", [(300, 256, 72), (1, 256, 256), (4097, 32, 256), (513, 27, 256), (129, 256, 344), (1000, 256, 8)])
-@pytest.mark.parametrize("precise", [1, 0])
+@pytest.mark.parametrize("precise", [1, 0, 2])
 def test_gemm_tn_linear_epilogues(M, N, K, precise):
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g).cuda()
     B = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
     bias = torch.randn(N, generator=g).cuda()
     ref = A.double() @ B.double().t()
-    tol = 2e-5 if precise else 3e-3
+    tol = TOL[precise]
     out, _ = _run_tn(A, B, EPI["NONE"], N, precise=precise)
     assert common.rel_err(out.cpu(), ref.cpu()) < tol
     out, _ = _run_tn(A, B, EPI["BIAS"], N, bias=bias, precise=precise)
@@ -51,10 +55,12 @@ def test_gemm_tn_linear_epilogues(M, N, K, precise):
     assert common.rel_err(out.cpu(), torch.sigmoid(ref + bias.double()).cpu()) < tol
     out, _ = _run_tn(A, B * 0.05, EPI["SOFTPLUS"], N, bias=bias * 0.02, precise=precise)
     sp = torch.nn.functional.softplus(ref * 0.05 + 0.02 * bias.double(), beta=100)
-    assert float((out.cpu().double() - sp.cpu()).abs().max()) < (2e-6 if precise else 3e-4)
+    assert float((out.cpu().double() - sp.cpu()).abs().max()) < (2e-6 if precise == 1 else 5e-4)
 
 
-def test_gemm_tn_chain_epilogues():
+@pytest.mark.parametrize("precise", [1, 0])
+def test_gemm_tn_chain_epilogues(precise):
+    tol = TOL[precise]
     g = torch.Generator().manual_seed(5)
     M, N, K, rows = 700, 256, 256, 100          # aux indexed modulo `rows` (eikonal seed blocks)
     A = torch.randn(M, K, generator=g).cuda()
@@ -63,23 +69,23 @@ def test_gemm_tn_chain_epilogues():
     pfull = torch.randn(M, N, generator=g).cuda()
     ref = (A.double() @ B.double().t())
     sg = _sigma(h.double()).repeat(7, 1)
-    out, _ = _run_tn(A, B, EPI["MUL_SIGMA"], N, aux=h, aux_rows=rows)
-    assert common.rel_err(out.cpu(), (ref * sg).cpu()) < 2e-5
-    out, out2 = _run_tn(A, B, EPI["BWD_CHAIN"], N, aux=h, aux_rows=rows, aux2=pfull, atomic2=1, out2_rows=rows)
-    assert common.rel_err(out.cpu(), (ref * sg).cpu()) < 2e-5
+    out, _ = _run_tn(A, B, EPI["MUL_SIGMA"], N, aux=h, aux_rows=rows, precise=precise)
+    assert common.rel_err(out.cpu(), (ref * sg).cpu()) < tol
+    out, out2 = _run_tn(A, B, EPI["BWD_CHAIN"], N, aux=h, aux_rows=rows, aux2=pfull, atomic2=1, out2_rows=rows, precise=precise)
+    assert common.rel_err(out.cpu(), (ref * sg).cpu()) < tol
     want2 = (ref * pfull.double() * 100.0 * (1.0 - sg)).view(7, rows, N).sum(0)
-    assert common.rel_err(out2.cpu(), want2.cpu()) < 2e-5
+    assert common.rel_err(out2.cpu(), want2.cpu()) < tol
     hM = h.repeat(7, 1).contiguous()
-    out, out2 = _run_tn(A, B, EPI["BWD_CHAIN"], N, aux=hM, aux2=pfull)
-    assert common.rel_err(out2.cpu(), (ref * pfull.double() * 100.0 * (1.0 - sg)).cpu()) < 2e-5
-    out, _ = _run_tn(A, B, EPI["BWD_SP"], N, aux=hM, aux2=pfull)
-    assert common.rel_err(out.cpu(), (ref * sg + pfull.double()).cpu()) < 2e-5
-    out, _ = _run_tn(A, B, EPI["BWD_RELU"], N, aux=pfull)
-    assert common.rel_err(out.cpu(), (ref * (pfull.double() > 0)).cpu()) < 2e-5
+    out, out2 = _run_tn(A, B, EPI["BWD_CHAIN"], N, aux=hM, aux2=pfull, precise=precise)
+    assert common.rel_err(out2.cpu(), (ref * pfull.double() * 100.0 * (1.0 - sg)).cpu()) < tol
+    out, _ = _run_tn(A, B, EPI["BWD_SP"], N, aux=hM, aux2=pfull, precise=precise)
+    assert common.rel_err(out.cpu(), (ref * sg + pfull.double()).cpu()) < tol
+    out, _ = _run_tn(A, B, EPI["BWD_RELU"], N, aux=pfull, precise=precise)
+    assert common.rel_err(out.cpu(), (ref * (pfull.double() > 0)).cpu()) < tol
 
 
 @pytest.mark.parametrize("M,N1,N2", [(5000, 256, 72), (33, 256, 344), (100000, 32, 256), (777, 4, 256), (4096, 256, 32)])
-@pytest.mark.parametrize("precise", [1, 0])
+@pytest.mark.parametrize("precise", [1, 2])
 def test_gemm_wgrad(M, N1, N2, precise):
     from holoscene_b200 import _lib, engine
     g = torch.Generator().manual_seed(M)
@@ -90,7 +96,7 @@ def test_gemm_wgrad(M, N1, N2, precise):
     _lib.check(engine.gemm_wgrad(_p(A), N1, N1, _p(B), N2, N2, M, _p(C), N2, _p(bias), precise, _lib.stream()))
     torch.cuda.synchronize()
     ref = A.double().t() @ B.double() + 1.0
-    tol = 2e-5 if precise else 3e-3
+    tol = TOL[precise]
     assert common.rel_err(C.cpu(), ref.cpu()) < tol
     assert common.rel_err(bias.cpu(), (A.double().sum(0) + 2.0).cpu()) < 1e-5
 
@@ -102,3 +108,19 @@ def test_gemm_rejects_misaligned_operands():
     out = torch.zeros(8, 8, device="cuda")
     st = engine.gemm_tn(_p(A), 70, _p(B), 70, 8, 8, 70, 0, _p(out), 8, None, None, 0, 0, None, 0, None, 0, 0, 1, _lib.stream())
     assert st == 1 and b"multiples of 4" in _lib.lib.hsb_last_error()
+
+
+def test_tcgen05_kernel_is_the_fast_path_and_matches_legacy_tensor_path():
+    """precise=0 must run the tcgen05 kernel (not silently fall back) and agree with the mma.sync TF32 path."""
+    from holoscene_b200 import _lib
+    g = torch.Generator().manual_seed(9)
+    M, N, K = 70000, 256, 256
+    A = torch.randn(M, K, generator=g).cuda()
+    B = (torch.randn(N, K, generator=g) / 16).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    a, _ = _run_tn(A, B, EPI["BIAS"], N, bias=bias, precise=0)
+    b, _ = _run_tn(A, B, EPI["BIAS"], N, bias=bias, precise=2)
+    ref = (A.double() @ B.double().t() + bias.double()).cpu()
+    assert common.rel_err(a.cpu(), ref) < 5e-3 and common.rel_err(b.cpu(), ref) < 3e-3
+    assert common.rel_err(a.cpu(), b.cpu()) < 5e-3
+    assert not torch.equal(a, b)     # different arithmetic (operand truncation vs rounding): not the same kernel
