@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precise", action="store_true", help="3xTF32 contractions (parity mode)")
     ap.add_argument("--rays", type=int, default=WORKLOAD["R"])
+    ap.add_argument("--phases", action="store_true", help="after the timed runs, print a per-phase breakdown (synchronising)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -225,6 +226,16 @@ def main():
     ms_e2e, _ = timed(args.steps, host_in, host_gt, read_loss=True)
     clk = clocks.stop() if rank == 0 else None
     rounds = model.ray_sampler.last_rounds
+    if args.phases and rank == 0:
+        step.phase_ms, model.phase_ms = {}, {}
+        n = 5
+        step.iter_step = 1
+        for _ in range(n):
+            step(dict(dev_in, uv=dev_in["uv"].clone()), dev_gt)
+        ph = {k: v / n for k, v in step.phase_ms.items()}
+        ph["  of which sampler"] = model.phase_ms.get("sampler", 0.0) / n
+        print("[phases ms/step, synchronised] " + json.dumps(ph), file=sys.stderr, flush=True)
+        step.phase_ms, model.phase_ms = None, None
 
     # ---- roofline of the dominant kernel: the 256x256 fc contraction (gemm_tn_kernel) over the P = R*S points ----
     import ctypes

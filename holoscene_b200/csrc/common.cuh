@@ -33,6 +33,16 @@ __device__ __forceinline__ float laplace_density(float s, float beta) {
     return (1.0f / beta) * (0.5f + 0.5f * sg * e);
 }
 
+// Round-to-nearest to TF32 (10-bit mantissa) when `on`.  The tcgen05 kind::tf32 MMA TRUNCATES fp32 operands; every
+// tensor the fast mode feeds to it is therefore stored already rounded by its producer, which makes the truncation
+// a no-op and the operand error unbiased (TF32 storage discipline).
+__device__ __forceinline__ float rtf32(float x, int on) {
+    if (!on) return x;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(const float* __restrict__ 
             for (int r = 0; r < 4; ++r) {
                 long long m = m0 + wm * 64 + mt * 16 + g + ((r & 2) ? 8 : 0);
                 int n = n0 + wn * 32 + nt * 8 + 2 * t + (r & 1);
-                if (m < M && n < N) epilogue_store(epi, m, n, acc[mt][nt][r]);
+                if (m < M && n < N) epilogue_store<!PRECISE>(epi, m, n, acc[mt][nt][r]);
             }
 }
 

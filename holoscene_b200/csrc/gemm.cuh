@@ -24,47 +24,108 @@ struct Epi {
     const float* aux2; long long lda2;
     float* out2; long long ldo2;
     int atomic2;                                           // out2[m % aux_rows] += (atomic) instead of store
+    int round_out;                                         // store `out` rounded to TF32 (it is a later tcgen05 operand)
 };
 
-// epilogue shared by the mma.sync and the tcgen05 contraction kernels (runtime kind; warp-uniform branch)
+// ---- epilogue math -----------------------------------------------------------------------------------
+// FAST = false: libm-grade expf / log1pf (the 3xTF32 parity mode).  FAST = true: MUFU-based __expf / __logf
+// (abs error ~1e-7 on softplus outputs of O(1e-2..1), far below the TF32 operand error of the fast mode).
+template <bool FAST> __device__ __forceinline__ float epi_softplus(float a) {
+    const float t = 100.0f * a;
+    if (t > 20.0f) return a;
+    return FAST ? __logf(1.0f + __expf(t)) * 0.01f : log1pf(expf(t)) * 0.01f;
+}
+template <bool FAST> __device__ __forceinline__ float epi_sigma(float h) {      // softplus'(a) from h = softplus(a)
+    return FAST ? 1.0f - __expf(-100.0f * h) : -expm1f(-100.0f * h);
+}
+template <bool FAST> __device__ __forceinline__ float epi_sigmoid(float x) {
+    return FAST ? __fdividef(1.0f, 1.0f + __expf(-x)) : 1.0f / (1.0f + expf(-x));
+}
+
+// one element (used by the mma.sync kernels, whose accumulator fragments are scattered over rows)
+template <bool FAST>
 __device__ __forceinline__ void epilogue_store(const Epi& e, long long m, int n, float acc) {
-    const long long ma = e.aux_rows > 0 ? (m % e.aux_rows) : m;
     switch (e.kind) {
-        case EPI_NONE:
-            e.out[m * e.ldo + n] = acc;
+        case EPI_NONE: e.out[m * e.ldo + n] = rtf32(acc, e.round_out); break;
+        case EPI_BIAS: e.out[m * e.ldo + n] = rtf32(acc + e.bias[n], e.round_out); break;
+        case EPI_BIAS_SOFTPLUS: e.out[m * e.ldo + n] = rtf32(epi_softplus<FAST>(acc + e.bias[n]), e.round_out); break;
+        case EPI_BIAS_RELU: e.out[m * e.ldo + n] = rtf32(fmaxf(acc + e.bias[n], 0.0f), e.round_out); break;
+        case EPI_BIAS_SIGMOID: e.out[m * e.ldo + n] = epi_sigmoid<FAST>(acc + e.bias[n]); break;
+        case EPI_MUL_SIGMA: {
+            const long long ma = e.aux_rows > 0 ? (m % e.aux_rows) : m;
+            e.out[m * e.ldo + n] = rtf32(acc * epi_sigma<FAST>(e.aux[ma * e.lda + n]), e.round_out);
             break;
-        case EPI_BIAS:
-            e.out[m * e.ldo + n] = acc + e.bias[n];
-            break;
-        case EPI_BIAS_SOFTPLUS:
-            e.out[m * e.ldo + n] = softplus100(acc + e.bias[n]);
-            break;
-        case EPI_BIAS_RELU:
-            e.out[m * e.ldo + n] = fmaxf(acc + e.bias[n], 0.0f);
-            break;
-        case EPI_BIAS_SIGMOID:
-            e.out[m * e.ldo + n] = 1.0f / (1.0f + expf(-(acc + e.bias[n])));
-            break;
-        case EPI_MUL_SIGMA:   // forward input-gradient chain: p = q * softplus'(a), a known through h = aux
-            e.out[m * e.ldo + n] = acc * sp_sigma(e.aux[ma * e.lda + n]);
-            break;
-        case EPI_BWD_CHAIN: {  // acc = d p ; out = d q = dp*sigma ; out2 += dp * p * 100*(1-sigma)   (softplus'' term)
-            float sg = sp_sigma(e.aux[ma * e.lda + n]);
-            e.out[m * e.ldo + n] = acc * sg;
-            float v = acc * e.aux2[m * e.lda2 + n] * 100.0f * (1.0f - sg);
+        }
+        case EPI_BWD_CHAIN: {
+            const long long ma = e.aux_rows > 0 ? (m % e.aux_rows) : m;
+            const float sg = epi_sigma<FAST>(e.aux[ma * e.lda + n]);
+            e.out[m * e.ldo + n] = rtf32(acc * sg, e.round_out);
+            const float v = acc * e.aux2[m * e.lda2 + n] * 100.0f * (1.0f - sg);
             if (e.atomic2) atomicAdd(e.out2 + ma * e.ldo2 + n, v);
             else e.out2[m * e.ldo2 + n] = v;
             break;
         }
-        case EPI_BWD_SP:      // d a = d h * sigma(h) + extra
-            e.out[m * e.ldo + n] = acc * sp_sigma(e.aux[ma * e.lda + n]) + (e.aux2 ? e.aux2[m * e.lda2 + n] : 0.0f);
+        case EPI_BWD_SP: {
+            const long long ma = e.aux_rows > 0 ? (m % e.aux_rows) : m;
+            e.out[m * e.ldo + n] = rtf32(acc * epi_sigma<FAST>(e.aux[ma * e.lda + n]) + (e.aux2 ? e.aux2[m * e.lda2 + n] : 0.0f), e.round_out);
             break;
-        case EPI_BWD_RELU:
-            e.out[m * e.ldo + n] = e.aux[ma * e.lda + n] > 0.0f ? acc : 0.0f;
+        }
+        case EPI_BWD_RELU: {
+            const long long ma = e.aux_rows > 0 ? (m % e.aux_rows) : m;
+            e.out[m * e.ldo + n] = e.aux[ma * e.lda + n] > 0.0f ? rtf32(acc, e.round_out) : 0.0f;
             break;
+        }
     }
 }
 
+// `rows` consecutive rows m_first.. of ONE column n (the tcgen05 epilogue: a warp holds a 32x32 tile transposed in
+// smem, lane = column).  vals[r * vstride] is the accumulator of row m_first + r.  Pointers advance incrementally;
+// the aux row index wraps modulo aux_rows without a per-element 64-bit division.
+template <bool FAST>
+__device__ __forceinline__ void epilogue_rows(const Epi& e, long long m_first, int rows, int n, const float* vals, int vstride) {
+    float* out = e.out + m_first * e.ldo + n;
+    long long ma = 0;
+    if (e.aux) ma = e.aux_rows > 0 ? (m_first % e.aux_rows) : m_first;
+    const long long wrap = e.aux_rows > 0 ? e.aux_rows : (1LL << 62);
+    const float* aux = e.aux ? e.aux + ma * e.lda + n : nullptr;
+    const float b = e.bias ? e.bias[n] : 0.0f;
+    const int ro = e.round_out;
+#define HSB_ROWS(BODY)                                                           \
+    _Pragma("unroll 4") for (int r = 0; r < rows; ++r) {                        \
+        const float acc = vals[r * vstride];                                     \
+        BODY;                                                                    \
+        out += e.ldo;                                                            \
+    }
+#define HSB_AUX_NEXT                                                             \
+    { ++ma; if (ma == wrap) { ma = 0; aux = e.aux + n; } else aux += e.lda; }
+    switch (e.kind) {
+        case EPI_NONE: HSB_ROWS(*out = rtf32(acc, ro)) break;
+        case EPI_BIAS: HSB_ROWS(*out = rtf32(acc + b, ro)) break;
+        case EPI_BIAS_SOFTPLUS: HSB_ROWS(*out = rtf32(epi_softplus<FAST>(acc + b), ro)) break;
+        case EPI_BIAS_RELU: HSB_ROWS(*out = rtf32(fmaxf(acc + b, 0.0f), ro)) break;
+        case EPI_BIAS_SIGMOID: HSB_ROWS(*out = epi_sigmoid<FAST>(acc + b)) break;
+        case EPI_MUL_SIGMA: HSB_ROWS(*out = rtf32(acc * epi_sigma<FAST>(*aux), ro); HSB_AUX_NEXT) break;
+        case EPI_BWD_CHAIN: {
+            const float* a2 = e.aux2 + m_first * e.lda2 + n;
+            float* o2 = e.out2 + (e.atomic2 ? ma : m_first) * e.ldo2 + n;
+            HSB_ROWS(const float sg = epi_sigma<FAST>(*aux); *out = rtf32(acc * sg, ro);
+                     const float v = acc * (*a2) * 100.0f * (1.0f - sg);
+                     if (e.atomic2) atomicAdd(o2, v); else *o2 = v;
+                     a2 += e.lda2;
+                     { ++ma; if (ma == wrap) { ma = 0; aux = e.aux + n; if (e.atomic2) o2 = e.out2 + n; else o2 += e.ldo2; }
+                       else { aux += e.lda; o2 += e.ldo2; } })
+            break;
+        }
+        case EPI_BWD_SP: {
+            const float* a2 = e.aux2 ? e.aux2 + m_first * e.lda2 + n : nullptr;
+            HSB_ROWS(float x = acc * epi_sigma<FAST>(*aux); if (a2) { x += *a2; a2 += e.lda2; } *out = rtf32(x, ro); HSB_AUX_NEXT)
+            break;
+        }
+        case EPI_BWD_RELU: HSB_ROWS(*out = (*aux > 0.0f) ? rtf32(acc, ro) : 0.0f; HSB_AUX_NEXT) break;
+    }
+#undef HSB_ROWS
+#undef HSB_AUX_NEXT
+}
 
 int num_sms();
 bool gemm_tn_tc_eligible(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K);

@@ -16,6 +16,7 @@
 
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace hsb {
 
@@ -173,13 +174,9 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = v[j];
             __syncwarp();
             const int n = c * 32 + lane;
-            if (n < N) {
-#pragma unroll 4
-                for (int r = 0; r < 32; ++r) {
-                    const long long m = m0 + q * 32 + r;
-                    if (m < M) epilogue_store(epi, m, n, buf[r * 33 + lane]);
-                }
-            }
+            const long long m_first = m0 + q * 32;
+            const long long left = M - m_first;
+            if (n < N && left > 0) epilogue_rows<true>(epi, m_first, left < 32 ? (int)left : 32, n, buf + lane, 33);
             __syncwarp();
         }
     }
@@ -202,6 +199,7 @@ static bool tc_init() {
     std::lock_guard<std::mutex> lk(g_tc_mu);
     if (g_tc_checked) return g_tc_ok;
     g_tc_checked = true;
+    if (getenv("HSB_DISABLE_TCGEN05")) return false;     // A/B switch: run the fast mode on the legacy mma.sync TF32 path
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||

@@ -16,6 +16,7 @@
 //   * output / gradient tensors are addressed through (level stride, point stride) so features land
 //     directly inside the MLP input rows -- no [L,B,C] -> [B,L*C] permute pass.
 #include "common.cuh"
+#include "step.cuh"
 #include "../../include/hsb200.h"
 
 namespace hsb {
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
                                                        const int* __restrict__ offsets, float* __restrict__ out,
                                                        long long out_ls, long long out_ps, float* __restrict__ dy_dx,
                                                        long long dy_ps, uint32_t B, uint32_t L, float S, uint32_t H,
-                                                       int map01) {
+                                                       int map01, int rtf) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     const uint32_t level = blockIdx.y;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
         r.x += w * v[i].x;
         r.y += w * v[i].y;
     }
-    o[0] = r.x; o[1] = r.y;
+    o[0] = rtf32(r.x, rtf); o[1] = rtf32(r.y, rtf);      // features are a tcgen05 operand in the fast mode
     if (!dd) return;
     // d/dx_gd = sum over the 4 corners of the other two axes of scale*w_other*(right-left)*smoothstep'
 #pragma unroll
@@ -278,16 +279,23 @@ __global__ void __launch_bounds__(256) hash_bwd_fused_kernel(const float* __rest
 
 using namespace hsb;
 
-extern "C" int hsb_hash_forward(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs,
-                                long long out_level_stride, long long out_point_stride, float* dy_dx,
-                                long long dy_point_stride, uint32_t B, uint32_t L, float S, uint32_t H, int map01,
-                                cudaStream_t stream) {
+int hsb::hash_forward_ex(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs,
+                         long long out_level_stride, long long out_point_stride, float* dy_dx, long long dy_point_stride,
+                         uint32_t B, uint32_t L, float S, uint32_t H, int map01, int rtf, cudaStream_t stream) {
     if (B == 0) return HSB_OK;
     if (!inputs || !embeddings || !offsets || !outputs || L == 0 || L > 32) { set_error("hsb_hash_forward: bad argument"); return HSB_ERR_ARG; }
     dim3 grid(cdiv(B, 256), L);
     hash_fwd_kernel<<<grid, 256, 0, stream>>>(inputs, reinterpret_cast<const float2*>(embeddings), offsets, outputs,
-                                              out_level_stride, out_point_stride, dy_dx, dy_point_stride, B, L, S, H, map01);
+                                              out_level_stride, out_point_stride, dy_dx, dy_point_stride, B, L, S, H, map01, rtf);
     return check_launch("hsb_hash_forward");
+}
+
+extern "C" int hsb_hash_forward(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs,
+                                long long out_level_stride, long long out_point_stride, float* dy_dx,
+                                long long dy_point_stride, uint32_t B, uint32_t L, float S, uint32_t H, int map01,
+                                cudaStream_t stream) {
+    return hash_forward_ex(inputs, embeddings, offsets, outputs, out_level_stride, out_point_stride, dy_dx, dy_point_stride, B, L,
+                           S, H, map01, 0, stream);
 }
 
 extern "C" int hsb_hash_backward(const float* grad, long long g_level_stride, long long g_point_stride,

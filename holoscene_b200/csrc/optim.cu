@@ -13,7 +13,7 @@ namespace hsb {
 // and the transposed copy WeT[k, n] (ldt >= rows; rows of WeT beyond `cols` are zeroed by the caller's memset).
 __global__ void __launch_bounds__(256) wn_forward_kernel(const float* __restrict__ v, const float* __restrict__ g, int rows,
                                                          int cols, float* __restrict__ We, int ldw, float* __restrict__ WeT,
-                                                         int ldt) {
+                                                         int ldt, int rtf) {
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n >= rows) return;
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) wn_forward_kernel(const float* __restrict
     ss = warp_sum(ss);
     const float sc = g[n] / sqrtf(ss);
     for (int k = lane; k < ldw; k += 32) {
-        const float w = k < cols ? sc * vr[k] : 0.0f;
+        const float w = k < cols ? rtf32(sc * vr[k], rtf) : 0.0f;
         We[(long long)n * ldw + k] = w;
         if (WeT && k < cols) WeT[(long long)k * ldt + n] = w;
     }
@@ -50,13 +50,15 @@ __global__ void __launch_bounds__(256) wn_backward_kernel(const float* __restric
 }
 
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ WT,
-                                                        int ldt) {
+                                                        int ldt, float* __restrict__ Wcopy, int rtf) {
     __shared__ float tile[32][33];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     for (int j = ty; j < 32; j += 8) {
         int r = by + j, c = bx + tx;
-        tile[j][tx] = (r < rows && c < cols) ? W[(long long)r * cols + c] : 0.0f;
+        const float v = (r < rows && c < cols) ? rtf32(W[(long long)r * cols + c], rtf) : 0.0f;
+        tile[j][tx] = v;
+        if (Wcopy && r < rows && c < cols) Wcopy[(long long)r * cols + c] = v;
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
@@ -98,9 +100,9 @@ int launch_add_into(const float* src, float* dst, int n, cudaStream_t st) {
     return check_launch("add_into");
 }
 
-int launch_wn_forward(const float* v, const float* g, int rows, int cols, float* We, int ldw, float* WeT, int ldt,
+int launch_wn_forward(const float* v, const float* g, int rows, int cols, float* We, int ldw, float* WeT, int ldt, int rtf,
                       cudaStream_t st) {
-    wn_forward_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(v, g, rows, cols, We, ldw, WeT, ldt);
+    wn_forward_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(v, g, rows, cols, We, ldw, WeT, ldt, rtf);
     return check_launch("wn_forward");
 }
 int launch_wn_backward(const float* dWe, int ldw, const float* v, const float* g, int rows, int cols, float* dv, float* dg,
@@ -108,9 +110,9 @@ int launch_wn_backward(const float* dWe, int ldw, const float* v, const float* g
     wn_backward_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(dWe, ldw, v, g, rows, cols, dv, dg);
     return check_launch("wn_backward");
 }
-int launch_transpose(const float* W, int rows, int cols, float* WT, int ldt, cudaStream_t st) {
+int launch_transpose(const float* W, int rows, int cols, float* WT, int ldt, float* Wcopy, int rtf, cudaStream_t st) {
     dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
-    transpose_kernel<<<grid, 256, 0, st>>>(W, rows, cols, WT, ldt);
+    transpose_kernel<<<grid, 256, 0, st>>>(W, rows, cols, WT, ldt, Wcopy, rtf);
     return check_launch("transpose");
 }
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1,

@@ -10,14 +10,14 @@
 namespace hsb {
 
 // PE of a 3-vector with m octaves into dst[0 .. 3+6m)
-__device__ __forceinline__ void pe_write(float* __restrict__ dst, float x, float y, float z, int m) {
-    dst[0] = x; dst[1] = y; dst[2] = z;
+__device__ __forceinline__ void pe_write(float* __restrict__ dst, float x, float y, float z, int m, int rtf) {
+    dst[0] = rtf32(x, rtf); dst[1] = rtf32(y, rtf); dst[2] = rtf32(z, rtf);
     float f = 1.0f;
     for (int i = 0; i < m; ++i) {
         float s, c;
-        sincosf(x * f, &s, &c); dst[3 + 6 * i + 0] = s; dst[3 + 6 * i + 3] = c;
-        sincosf(y * f, &s, &c); dst[3 + 6 * i + 1] = s; dst[3 + 6 * i + 4] = c;
-        sincosf(z * f, &s, &c); dst[3 + 6 * i + 2] = s; dst[3 + 6 * i + 5] = c;
+        sincosf(x * f, &s, &c); dst[3 + 6 * i + 0] = rtf32(s, rtf); dst[3 + 6 * i + 3] = rtf32(c, rtf);
+        sincosf(y * f, &s, &c); dst[3 + 6 * i + 1] = rtf32(s, rtf); dst[3 + 6 * i + 4] = rtf32(c, rtf);
+        sincosf(z * f, &s, &c); dst[3 + 6 * i + 2] = rtf32(s, rtf); dst[3 + 6 * i + 5] = rtf32(c, rtf);
         f *= 2.0f;
     }
 }
@@ -26,7 +26,7 @@ __device__ __forceinline__ void pe_write(float* __restrict__ dst, float x, float
 // RIN[:, 0:27] = PE4(x), RIN[:, 27:54] = PE4(d), RIN[:, 337:344] = 0   (RIN may be null: SDF-only use)
 __global__ void __launch_bounds__(256) ray_points_kernel(const float* __restrict__ o, const float* __restrict__ d,
                                                          const float* __restrict__ z, int R, int S, float* __restrict__ X,
-                                                         float* __restrict__ H0, float* __restrict__ RIN) {
+                                                         float* __restrict__ H0, float* __restrict__ RIN, int rtf) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long long)R * S) return;
     const int r = (int)(p / S);
@@ -35,23 +35,23 @@ __global__ void __launch_bounds__(256) ray_points_kernel(const float* __restrict
     const float x = o[r * 3 + 0] + zz * dx, y = o[r * 3 + 1] + zz * dy, w = o[r * 3 + 2] + zz * dz;
     X[p * 3 + 0] = x; X[p * 3 + 1] = y; X[p * 3 + 2] = w;
     float* h = H0 + p * LD_H0;
-    pe_write(h, x, y, w, 6);
+    pe_write(h, x, y, w, 6, rtf);
     h[71] = 0.0f;
     if (RIN) {
         float* q = RIN + p * LD_RIN;
-        pe_write(q, x, y, w, 4);
-        pe_write(q + 27, dx, dy, dz, 4);
+        pe_write(q, x, y, w, 4, rtf);
+        pe_write(q + 27, dx, dy, dz, 4, rtf);
 #pragma unroll
         for (int i = 337; i < LD_RIN; ++i) q[i] = 0.0f;
     }
 }
 
 // explicit points (eikonal samples): H0[:, 0:39] = PE6(x), H0[:, 71] = 0
-__global__ void __launch_bounds__(256) points_pe_kernel(const float* __restrict__ X, long long N, float* __restrict__ H0) {
+__global__ void __launch_bounds__(256) points_pe_kernel(const float* __restrict__ X, long long N, float* __restrict__ H0, int rtf) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     float* h = H0 + p * LD_H0;
-    pe_write(h, X[p * 3 + 0], X[p * 3 + 1], X[p * 3 + 2], 6);
+    pe_write(h, X[p * 3 + 0], X[p * 3 + 1], X[p * 3 + 2], 6, rtf);
     h[71] = 0.0f;
 }
 
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) sdf_min_kernel(const float* __restrict__ 
 // (nseed == 1: key = kstar[p], the min-SDF gradient of the main pass)
 __global__ void __launch_bounds__(256) chain_seed_kernel(const float* __restrict__ W2e, const float* __restrict__ H2,
                                                          const int* __restrict__ kstar, long long N, int K, int nseed,
-                                                         float* __restrict__ P2) {
+                                                         float* __restrict__ P2, int rtf) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over N * 64 float4s
     if (t >= N * 64) return;
     const long long p = t >> 6;
@@ -88,14 +88,15 @@ __global__ void __launch_bounds__(256) chain_seed_kernel(const float* __restrict
     const float4 w = reinterpret_cast<const float4*>(W2e + (long long)key * 256)[j];
     const float4 h = reinterpret_cast<const float4*>(H2 + p * 256)[j];
     float4 r;
-    r.x = w.x * sp_sigma(h.x); r.y = w.y * sp_sigma(h.y); r.z = w.z * sp_sigma(h.z); r.w = w.w * sp_sigma(h.w);
+    r.x = rtf32(w.x * sp_sigma(h.x), rtf); r.y = rtf32(w.y * sp_sigma(h.y), rtf);
+    r.z = rtf32(w.z * sp_sigma(h.z), rtf); r.w = rtf32(w.w * sp_sigma(h.w), rtf);
     reinterpret_cast<float4*>(P2 + ((long long)s * N + p) * 256)[j] = r;
 }
 
 // end of the chain: g = (dh0/dx)^T q0.  rows m = s*N + p.  Optionally writes PE4(g) into RIN[:, 54:81].
 __global__ void __launch_bounds__(256) chain_end_kernel(const float* __restrict__ Q0, const float* __restrict__ H0,
                                                         const float* __restrict__ DY, long long N, int nseed,
-                                                        float* __restrict__ G, float* __restrict__ RIN) {
+                                                        float* __restrict__ G, float* __restrict__ RIN, int rtf) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= N * nseed) return;
     const long long p = m % N;
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(256) chain_end_kernel(const float* __restrict_
 #pragma unroll
     for (int d = 0; d < 3; ++d) g[d] += 0.5f * e[d];
     G[m * 3 + 0] = g[0]; G[m * 3 + 1] = g[1]; G[m * 3 + 2] = g[2];
-    if (RIN) pe_write(RIN + p * LD_RIN + 54, g[0], g[1], g[2], 4);
+    if (RIN) pe_write(RIN + p * LD_RIN + 54, g[0], g[1], g[2], 4, rtf);
 }
 
 // backward of chain_end: dQ0 = (dh0/dx) dG, where for the main pass
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) chain_end_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) chain_end_bwd_kernel(float* __restrict__ dG, const float* __restrict__ dRIN,
                                                             const float* __restrict__ RIN, const float* __restrict__ H0,
                                                             const float* __restrict__ DY, long long N, int nseed,
-                                                            float* __restrict__ dQ0) {
+                                                            float* __restrict__ dQ0, int rtf) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= N * nseed) return;
     const long long p = m % N;
@@ -156,15 +157,15 @@ __global__ void __launch_bounds__(256) chain_end_bwd_kernel(float* __restrict__ 
     const float* h = H0 + p * LD_H0;
     const float* dy = DY + p * 96;
     float* q = dQ0 + m * LD_H0;
-    q[0] = dg[0]; q[1] = dg[1]; q[2] = dg[2];
+    q[0] = rtf32(dg[0], rtf); q[1] = rtf32(dg[1], rtf); q[2] = rtf32(dg[2], rtf);
     float f = 1.0f;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             float sn = h[3 + 6 * i + d], cs = h[3 + 6 * i + 3 + d];
-            q[3 + 6 * i + d] = f * cs * dg[d];
-            q[3 + 6 * i + 3 + d] = -f * sn * dg[d];
+            q[3 + 6 * i + d] = rtf32(f * cs * dg[d], rtf);
+            q[3 + 6 * i + 3 + d] = rtf32(-f * sn * dg[d], rtf);
         }
         f *= 2.0f;
     }
@@ -172,8 +173,8 @@ __global__ void __launch_bounds__(256) chain_end_bwd_kernel(float* __restrict__ 
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int d = 0; d < 3; ++d) { a += dy[l * 6 + d * 2] * dg[d]; b += dy[l * 6 + d * 2 + 1] * dg[d]; }
-        q[39 + 2 * l] = 0.5f * a;
-        q[40 + 2 * l] = 0.5f * b;
+        q[39 + 2 * l] = rtf32(0.5f * a, rtf);
+        q[40 + 2 * l] = rtf32(0.5f * b, rtf);
     }
     q[71] = 0.0f;
 }
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(256) rgb_head_kernel(const float* __restrict__
 
 // dU2[p,j] = (sum_c dO[p,c] R2e[c,j]) * [U2[p,j] > 0]
 __global__ void __launch_bounds__(256) rgb_head_bwd_kernel(const float* __restrict__ dO, const float* __restrict__ R2e,
-                                                           const float* __restrict__ U2, long long N, float* __restrict__ dU2) {
+                                                           const float* __restrict__ U2, long long N, float* __restrict__ dU2, int rtf) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over N*64 float4
     if (t >= N * 64) return;
     const long long p = t >> 6;
@@ -214,10 +215,10 @@ __global__ void __launch_bounds__(256) rgb_head_bwd_kernel(const float* __restri
     const float4 w1 = reinterpret_cast<const float4*>(R2e + 256)[j];
     const float4 w2 = reinterpret_cast<const float4*>(R2e + 512)[j];
     float4 r;
-    r.x = u.x > 0.f ? g.x * w0.x + g.y * w1.x + g.z * w2.x : 0.f;
-    r.y = u.y > 0.f ? g.x * w0.y + g.y * w1.y + g.z * w2.y : 0.f;
-    r.z = u.z > 0.f ? g.x * w0.z + g.y * w1.z + g.z * w2.z : 0.f;
-    r.w = u.w > 0.f ? g.x * w0.w + g.y * w1.w + g.z * w2.w : 0.f;
+    r.x = u.x > 0.f ? rtf32(g.x * w0.x + g.y * w1.x + g.z * w2.x, rtf) : 0.f;
+    r.y = u.y > 0.f ? rtf32(g.x * w0.y + g.y * w1.y + g.z * w2.y, rtf) : 0.f;
+    r.z = u.z > 0.f ? rtf32(g.x * w0.z + g.y * w1.z + g.z * w2.z, rtf) : 0.f;
+    r.w = u.w > 0.f ? rtf32(g.x * w0.w + g.y * w1.w + g.z * w2.w, rtf) : 0.f;
     reinterpret_cast<float4*>(dU2 + p * 256)[j] = r;
 }
 
@@ -252,16 +253,16 @@ __global__ void __launch_bounds__(256) add_min_grad_kernel(const float* __restri
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------
-int launch_ray_points(const float* o, const float* d, const float* z, int R, int S, float* X, float* H0, float* RIN,
+int launch_ray_points(const float* o, const float* d, const float* z, int R, int S, float* X, float* H0, float* RIN, int rtf,
                       cudaStream_t st) {
     long long P = (long long)R * S;
     if (P == 0) return HSB_OK;
-    ray_points_kernel<<<cdiv(P, 256), 256, 0, st>>>(o, d, z, R, S, X, H0, RIN);
+    ray_points_kernel<<<cdiv(P, 256), 256, 0, st>>>(o, d, z, R, S, X, H0, RIN, rtf);
     return check_launch("ray_points");
 }
-int launch_points_pe(const float* X, long long N, float* H0, cudaStream_t st) {
+int launch_points_pe(const float* X, long long N, float* H0, int rtf, cudaStream_t st) {
     if (N == 0) return HSB_OK;
-    points_pe_kernel<<<cdiv(N, 256), 256, 0, st>>>(X, N, H0);
+    points_pe_kernel<<<cdiv(N, 256), 256, 0, st>>>(X, N, H0, rtf);
     return check_launch("points_pe");
 }
 int launch_sdf_min(const float* SR, long long N, int K, int Kp, int channel, float* sdf, int* kstar, cudaStream_t st) {
@@ -269,23 +270,23 @@ int launch_sdf_min(const float* SR, long long N, int K, int Kp, int channel, flo
     sdf_min_kernel<<<cdiv(N, 256), 256, 0, st>>>(SR, N, K, Kp, channel, sdf, kstar);
     return check_launch("sdf_min");
 }
-int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long long N, int K, int nseed, float* P2,
+int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long long N, int K, int nseed, float* P2, int rtf,
                       cudaStream_t st) {
     if (N == 0) return HSB_OK;
     dim3 grid(cdiv(N * 64, 256), nseed);
-    chain_seed_kernel<<<grid, 256, 0, st>>>(W2e, H2, kstar, N, K, nseed, P2);
+    chain_seed_kernel<<<grid, 256, 0, st>>>(W2e, H2, kstar, N, K, nseed, P2, rtf);
     return check_launch("chain_seed");
 }
-int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN,
+int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN, int rtf,
                      cudaStream_t st) {
     if (N == 0) return HSB_OK;
-    chain_end_kernel<<<cdiv(N * nseed, 256), 256, 0, st>>>(Q0, H0, DY, N, nseed, G, RIN);
+    chain_end_kernel<<<cdiv(N * nseed, 256), 256, 0, st>>>(Q0, H0, DY, N, nseed, G, RIN, rtf);
     return check_launch("chain_end");
 }
 int launch_chain_end_bwd(float* dG, const float* dRIN, const float* RIN, const float* H0, const float* DY, long long N,
-                         int nseed, float* dQ0, cudaStream_t st) {
+                         int nseed, float* dQ0, int rtf, cudaStream_t st) {
     if (N == 0) return HSB_OK;
-    chain_end_bwd_kernel<<<cdiv(N * nseed, 256), 256, 0, st>>>(dG, dRIN, RIN, H0, DY, N, nseed, dQ0);
+    chain_end_bwd_kernel<<<cdiv(N * nseed, 256), 256, 0, st>>>(dG, dRIN, RIN, H0, DY, N, nseed, dQ0, rtf);
     return check_launch("chain_end_bwd");
 }
 int launch_rgb_head(const float* U2, const float* R2e, const float* bias, long long N, float* RGB, cudaStream_t st) {
@@ -293,9 +294,9 @@ int launch_rgb_head(const float* U2, const float* R2e, const float* bias, long l
     rgb_head_kernel<<<cdiv(N * 32, 256), 256, 0, st>>>(U2, R2e, bias, N, RGB);
     return check_launch("rgb_head");
 }
-int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, cudaStream_t st) {
+int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, int rtf, cudaStream_t st) {
     if (N == 0) return HSB_OK;
-    rgb_head_bwd_kernel<<<cdiv(N * 64, 256), 256, 0, st>>>(dO, R2e, U2, N, dU2);
+    rgb_head_bwd_kernel<<<cdiv(N * 64, 256), 256, 0, st>>>(dO, R2e, U2, N, dU2, rtf);
     return check_launch("rgb_head_bwd");
 }
 int launch_scatter_rows(const float* dQ2, const int* kstar, long long N, int K, int Kp, int nseed, float* dW2e,

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeArgs a, Com
                     float dsg, dbt;
                     laplace_grads(sk, beta, dsg, dbt);
                     const float common = b * T * delta * ek;     // dL/d sigma_k
-                    ds[k] = (common != 0.0f) ? common * dsg : 0.0f;
+                    ds[k] = (common != 0.0f) ? rtf32(common * dsg, g.rtf) : 0.0f;
                     dbeta += (common != 0.0f) ? common * dbt : 0.0f;
                 }
             } else {
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeArgs a, Com
             const float dsdf = (dsig != 0.0f) ? dsig * dsg : 0.0f;
             dbeta += (dsig != 0.0f) ? dsig * dbt : 0.0f;
             const int kk = (a.mode == 1) ? 0 : a.KS[p0 + i];
-            g.dS[(p0 + i) * Kp + kk] += dsdf;
+            g.dS[(p0 + i) * Kp + kk] = rtf32(g.dS[(p0 + i) * Kp + kk] + dsdf, g.rtf);
         }
     }
     dbeta = warp_sum(dbeta);

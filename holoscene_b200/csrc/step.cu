@@ -71,7 +71,8 @@ struct Ctx {
     char* ws; size_t ws_bytes; size_t ws_used;
     std::vector<NamedBuf> names;
     // derived weights
-    float *W0e, *W0eT, *W1e, *W1eT, *W2e, *W2eT, *C0T, *C1T, *R0e, *R0eT, *R1e, *R1eT, *R2e;
+    float *W0e, *W0eT, *W1e, *W1eT, *W2e, *W2eT, *C0e, *C0T, *C1e, *C1T, *R0e, *R0eT, *R1e, *R1eT, *R2e;
+    int rtf() const { return cfg.precise ? 0 : 1; }   // TF32 storage discipline of the tcgen05 fast mode
     // effective-weight gradient accumulators (zeroed by hsb_prepare)
     float *dW0e, *dW1e, *dW2e, *dB2e, *dR0e, *dR1e, *dR2e, *dRB2e;
     char* dwe_begin; size_t dwe_bytes;
@@ -134,6 +135,7 @@ static void carve_all(Ctx* c, bool dry) {
     c->W1e = carve(c, "W1e", 256, 256, dry);     c->W1eT = carve(c, "W1eT", 256, 256, dry);
     c->W2e = carve(c, "W2e", Kp, 256, dry);      c->W2eT = carve(c, "W2eT", 256, Kp, dry);
     c->C0T = carve(c, "C0T", 32, 256, dry);      c->C1T = carve(c, "C1T", 256, 256, dry);
+    c->C0e = carve(c, "C0e", 256, 32, dry);      c->C1e = carve(c, "C1e", 256, 256, dry);
     c->R0e = carve(c, "R0e", 256, LD_RIN, dry);  c->R0eT = carve(c, "R0eT", LD_RIN, 256, dry);
     c->R1e = carve(c, "R1e", 256, 256, dry);     c->R1eT = carve(c, "R1eT", 256, 256, dry);
     c->R2e = carve(c, "R2e", 4, 256, dry);
@@ -152,16 +154,19 @@ static void carve_all(Ctx* c, bool dry) {
 
 #define TRY(x) do { int _e = (x); if (_e != HSB_OK) return _e; } while (0)
 
-static Epi epi(int kind, float* out, long long ldo) { Epi e{}; e.kind = kind; e.out = out; e.ldo = ldo; return e; }
+static Epi epi(int kind, float* out, long long ldo, int round_out = 0) {
+    Epi e{}; e.kind = kind; e.out = out; e.ldo = ldo; e.round_out = round_out; return e;
+}
 
 // ---- SDF net forward: hash features -> H0[:,39:71] (+dy_dx), H1, H2, SR (PE part of H0 must be filled) ----
 static int sdf_forward(Ctx* c, Slot& s, long long N, bool need_dy, cudaStream_t st) {
     const hsb_step_cfg& f = c->cfg;
     const int P = f.precise;
-    TRY(hsb_hash_forward(s.X, c->P(SEG_EMB), c->hoffs, s.H0 + 39, 2, LD_H0, need_dy ? s.DY : nullptr, 96, (uint32_t)N, f.L, f.S, f.H, 1, st));
-    Epi e = epi(EPI_BIAS_SOFTPLUS, s.H1, 256); e.bias = c->P(SEG_L0B);
+    const int rt = c->rtf();
+    TRY(hash_forward_ex(s.X, c->P(SEG_EMB), c->hoffs, s.H0 + 39, 2, LD_H0, need_dy ? s.DY : nullptr, 96, (uint32_t)N, f.L, f.S, f.H, 1, rt, st));
+    Epi e = epi(EPI_BIAS_SOFTPLUS, s.H1, 256, rt); e.bias = c->P(SEG_L0B);
     TRY(gemm_tn(s.H0, LD_H0, c->W0e, LD_H0, N, 256, LD_H0, e, P, st));
-    e = epi(EPI_BIAS_SOFTPLUS, s.H2, 256); e.bias = c->P(SEG_L1B);
+    e = epi(EPI_BIAS_SOFTPLUS, s.H2, 256, rt); e.bias = c->P(SEG_L1B);
     TRY(gemm_tn(s.H1, 256, c->W1e, 256, N, 256, 256, e, P, st));
     e = epi(EPI_BIAS, s.SR, c->Kp); e.bias = c->P(SEG_L2B);
     TRY(gemm_tn(s.H2, 256, c->W2e, 256, N, c->K, 256, e, P, st));
@@ -172,12 +177,13 @@ static int sdf_forward(Ctx* c, Slot& s, long long N, bool need_dy, cudaStream_t 
 static int chain_forward(Ctx* c, Slot& s, long long N, int nseed, cudaStream_t st) {
     const int P = c->cfg.precise;
     const long long E = N * nseed;
-    TRY(launch_chain_seed(c->W2e, s.H2, s.KS, N, c->K, nseed, s.P2, st));
-    Epi e = epi(EPI_MUL_SIGMA, s.P1, 256); e.aux = s.H1; e.lda = 256; e.aux_rows = N;
+    const int rt = c->rtf();
+    TRY(launch_chain_seed(c->W2e, s.H2, s.KS, N, c->K, nseed, s.P2, rt, st));
+    Epi e = epi(EPI_MUL_SIGMA, s.P1, 256, rt); e.aux = s.H1; e.lda = 256; e.aux_rows = N;
     TRY(gemm_tn(s.P2, 256, c->W1eT, 256, E, 256, 256, e, P, st));        // q1 = p2 W1 ; p1 = q1*sg1
     e = epi(EPI_NONE, s.Q0, LD_H0);
     TRY(gemm_tn(s.P1, 256, c->W0eT, 256, E, LD_H0, 256, e, P, st));      // q0 = p1 W0
-    TRY(launch_chain_end(s.Q0, s.H0, s.DY, N, nseed, s.G, s.with_color ? s.RIN : nullptr, st));
+    TRY(launch_chain_end(s.Q0, s.H0, s.DY, N, nseed, s.G, s.with_color ? s.RIN : nullptr, rt, st));
     return HSB_OK;
 }
 
@@ -186,17 +192,18 @@ static int chain_backward(Ctx* c, Slot& s, long long N, int nseed, bool with_rin
     const hsb_step_cfg& f = c->cfg;
     const int P = f.precise;
     const long long E = N * nseed;
-    TRY(launch_chain_end_bwd(s.dG, with_rin ? s.dRIN : nullptr, with_rin ? s.RIN : nullptr, s.H0, s.DY, N, nseed, s.dQ0, st));
+    const int rt = c->rtf();
+    TRY(launch_chain_end_bwd(s.dG, with_rin ? s.dRIN : nullptr, with_rin ? s.RIN : nullptr, s.H0, s.DY, N, nseed, s.dQ0, rt, st));
     const int atomic = nseed > 1;
     if (atomic) {
         cudaMemsetAsync(s.dA1x, 0, (size_t)N * 256 * sizeof(float), st);
         cudaMemsetAsync(s.dA2x, 0, (size_t)N * 256 * sizeof(float), st);
     }
-    Epi e = epi(EPI_BWD_CHAIN, s.dQ1, 256);
+    Epi e = epi(EPI_BWD_CHAIN, s.dQ1, 256, rt);
     e.aux = s.H1; e.lda = 256; e.aux_rows = N; e.aux2 = s.P1; e.lda2 = 256; e.out2 = s.dA1x; e.ldo2 = 256; e.atomic2 = atomic;
     TRY(gemm_tn(s.dQ0, LD_H0, c->W0e, LD_H0, E, 256, LD_H0, e, P, st));  // dp1 = dq0 W0^T
     TRY(gemm_wgrad(s.P1, 256, 256, s.dQ0, LD_H0, LD_H0, E, c->dW0e, LD_H0, nullptr, P, st));
-    e = epi(EPI_BWD_CHAIN, s.dQ2, 256);
+    e = epi(EPI_BWD_CHAIN, s.dQ2, 256, rt);
     e.aux = s.H2; e.lda = 256; e.aux_rows = N; e.aux2 = s.P2; e.lda2 = 256; e.out2 = s.dA2x; e.ldo2 = 256; e.atomic2 = atomic;
     TRY(gemm_tn(s.dQ1, 256, c->W1e, 256, E, 256, 256, e, P, st));        // dp2 = dq1 W1^T
     TRY(gemm_wgrad(s.P2, 256, 256, s.dQ1, 256, 256, E, c->dW1e, 256, nullptr, P, st));
@@ -208,10 +215,11 @@ static int chain_backward(Ctx* c, Slot& s, long long N, int nseed, bool with_rin
 static int sdf_backward(Ctx* c, Slot& s, long long N, int nseed, bool have_chain, cudaStream_t st) {
     const hsb_step_cfg& f = c->cfg;
     const int P = f.precise;
-    Epi e = epi(EPI_BWD_SP, s.dA2, 256); e.aux = s.H2; e.lda = 256; e.aux2 = have_chain ? s.dA2x : nullptr; e.lda2 = 256;
+    const int rt = c->rtf();
+    Epi e = epi(EPI_BWD_SP, s.dA2, 256, rt); e.aux = s.H2; e.lda = 256; e.aux2 = have_chain ? s.dA2x : nullptr; e.lda2 = 256;
     TRY(gemm_tn(s.dS, c->Kp, c->W2eT, c->Kp, N, 256, c->Kp, e, P, st));  // dh2 = ds W2
     TRY(gemm_wgrad(s.dS, c->Kp, c->Kp, s.H2, 256, 256, N, c->dW2e, 256, c->dB2e, P, st));
-    e = epi(EPI_BWD_SP, s.dA1, 256); e.aux = s.H1; e.lda = 256; e.aux2 = have_chain ? s.dA1x : nullptr; e.lda2 = 256;
+    e = epi(EPI_BWD_SP, s.dA1, 256, rt); e.aux = s.H1; e.lda = 256; e.aux2 = have_chain ? s.dA1x : nullptr; e.lda2 = 256;
     TRY(gemm_tn(s.dA2, 256, c->W1eT, 256, N, 256, 256, e, P, st));       // dh1 = da2 W1
     TRY(gemm_wgrad(s.dA2, 256, 256, s.H1, 256, 256, N, c->dW1e, 256, c->Gp(SEG_L1B), P, st));
     e = epi(EPI_NONE, s.dH0E, 32);
@@ -298,20 +306,21 @@ extern "C" int hsb_ctx_buffer(hsb_ctx* h, const char* name, int64_t* offset_byte
 // derived weights for this step + zero the effective-weight gradient accumulators
 extern "C" int hsb_prepare(hsb_ctx* h, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    const int rt = c->rtf();
     cudaMemsetAsync(c->dwe_begin, 0, c->dwe_bytes, st);
     cudaMemsetAsync(c->W0eT, 0, (size_t)LD_H0 * 256 * sizeof(float), st);
     cudaMemsetAsync(c->R0eT, 0, (size_t)LD_RIN * 256 * sizeof(float), st);
     cudaMemsetAsync(c->W2e, 0, (size_t)c->Kp * 256 * sizeof(float), st);
     cudaMemsetAsync(c->W2eT, 0, (size_t)c->Kp * 256 * sizeof(float), st);
     cudaMemsetAsync(c->R2e, 0, (size_t)4 * 256 * sizeof(float), st);
-    TRY(launch_wn_forward(c->P(SEG_L0V), c->P(SEG_L0G), 256, 71, c->W0e, LD_H0, c->W0eT, 256, st));
-    TRY(launch_wn_forward(c->P(SEG_L1V), c->P(SEG_L1G), 256, 256, c->W1e, 256, c->W1eT, 256, st));
-    TRY(launch_wn_forward(c->P(SEG_L2V), c->P(SEG_L2G), c->K, 256, c->W2e, 256, c->W2eT, c->Kp, st));
-    TRY(launch_wn_forward(c->P(SEG_R0V), c->P(SEG_R0G), 256, 337, c->R0e, LD_RIN, c->R0eT, 256, st));
-    TRY(launch_wn_forward(c->P(SEG_R1V), c->P(SEG_R1G), 256, 256, c->R1e, 256, c->R1eT, 256, st));
-    TRY(launch_wn_forward(c->P(SEG_R2V), c->P(SEG_R2G), 3, 256, c->R2e, 256, nullptr, 0, st));
-    TRY(launch_transpose(c->P(SEG_C0W), 256, 32, c->C0T, 256, st));
-    TRY(launch_transpose(c->P(SEG_C1W), 256, 256, c->C1T, 256, st));
+    TRY(launch_wn_forward(c->P(SEG_L0V), c->P(SEG_L0G), 256, 71, c->W0e, LD_H0, c->W0eT, 256, rt, st));
+    TRY(launch_wn_forward(c->P(SEG_L1V), c->P(SEG_L1G), 256, 256, c->W1e, 256, c->W1eT, 256, rt, st));
+    TRY(launch_wn_forward(c->P(SEG_L2V), c->P(SEG_L2G), c->K, 256, c->W2e, 256, c->W2eT, c->Kp, rt, st));
+    TRY(launch_wn_forward(c->P(SEG_R0V), c->P(SEG_R0G), 256, 337, c->R0e, LD_RIN, c->R0eT, 256, rt, st));
+    TRY(launch_wn_forward(c->P(SEG_R1V), c->P(SEG_R1G), 256, 256, c->R1e, 256, c->R1eT, 256, rt, st));
+    TRY(launch_wn_forward(c->P(SEG_R2V), c->P(SEG_R2G), 3, 256, c->R2e, 256, nullptr, 0, 0, st));
+    TRY(launch_transpose(c->P(SEG_C0W), 256, 32, c->C0T, 256, c->C0e, rt, st));
+    TRY(launch_transpose(c->P(SEG_C1W), 256, 256, c->C1T, 256, c->C1e, rt, st));
     return HSB_OK;
 }
 
@@ -339,7 +348,7 @@ extern "C" int hsb_sdf_values(hsb_ctx* h, const float* o, const float* d, const 
     Slot& s = c->scratch;
     const long long N = (long long)R * S;
     if (N > s.cap_points || channel >= c->K) { set_error("hsb_sdf_values: batch exceeds max_points / bad channel"); return HSB_ERR_ARG; }
-    TRY(launch_ray_points(o, d, z, R, S, s.X, s.H0, nullptr, st));
+    TRY(launch_ray_points(o, d, z, R, S, s.X, s.H0, nullptr, c->rtf(), st));
     TRY(sdf_forward(c, s, N, false, st));
     TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, channel, sdf_out, nullptr, st));
     return HSB_OK;
@@ -360,19 +369,20 @@ extern "C" int hsb_render_forward(hsb_ctx* h, int32_t slot_id, const float* o, c
     cudaMemcpyAsync(s.ZV, z, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(s.DSCALE, depth_scale, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(s.ROT, rot, 9 * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    TRY(launch_ray_points(o, d, z, R, S, s.X, s.H0, scene ? s.RIN : nullptr, st));
+    const int rt = c->rtf();
+    TRY(launch_ray_points(o, d, z, R, S, s.X, s.H0, scene ? s.RIN : nullptr, rt, st));
     TRY(sdf_forward(c, s, N, true, st));
     TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, -1, s.SDF, s.KS, st));
     TRY(chain_forward(c, s, N, 1, st));
     if (scene) {
-        TRY(hsb_hash_forward(s.X, c->P(SEG_CEMB), c->hoffs, s.EC, 2, 32, nullptr, 0, (uint32_t)N, f.L, f.S, f.H, 1, st));
-        Epi e = epi(EPI_BIAS_RELU, s.C1, 256); e.bias = c->P(SEG_C0B);
-        TRY(gemm_tn(s.EC, 32, c->P(SEG_C0W), 32, N, 256, 32, e, P, st));
-        e = epi(EPI_BIAS, s.RIN + 81, LD_RIN); e.bias = c->P(SEG_C1B);
-        TRY(gemm_tn(s.C1, 256, c->P(SEG_C1W), 256, N, 256, 256, e, P, st));
-        e = epi(EPI_BIAS_RELU, s.U1, 256); e.bias = c->P(SEG_R0B);
+        TRY(hash_forward_ex(s.X, c->P(SEG_CEMB), c->hoffs, s.EC, 2, 32, nullptr, 0, (uint32_t)N, f.L, f.S, f.H, 1, rt, st));
+        Epi e = epi(EPI_BIAS_RELU, s.C1, 256, rt); e.bias = c->P(SEG_C0B);
+        TRY(gemm_tn(s.EC, 32, c->C0e, 32, N, 256, 32, e, P, st));
+        e = epi(EPI_BIAS, s.RIN + 81, LD_RIN, rt); e.bias = c->P(SEG_C1B);
+        TRY(gemm_tn(s.C1, 256, c->C1e, 256, N, 256, 256, e, P, st));
+        e = epi(EPI_BIAS_RELU, s.U1, 256, rt); e.bias = c->P(SEG_R0B);
         TRY(gemm_tn(s.RIN, LD_RIN, c->R0e, LD_RIN, N, 256, LD_RIN, e, P, st));
-        e = epi(EPI_BIAS_RELU, s.U2, 256); e.bias = c->P(SEG_R1B);
+        e = epi(EPI_BIAS_RELU, s.U2, 256, rt); e.bias = c->P(SEG_R1B);
         TRY(gemm_tn(s.U1, 256, c->R1e, 256, N, 256, 256, e, P, st));
         TRY(launch_rgb_head(s.U2, c->R2e, c->P(SEG_R2B), N, s.RGB, st));
     }
@@ -396,23 +406,24 @@ extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_r
     CompositeArgs a = composite_args(c, s, s.mode);
     CompositeGrads g{};
     g.d_rgb_values = d_rgb_values; g.d_depth_values = d_depth_values; g.d_normal_map = d_normal_map; g.d_opacity = d_opacity;
-    g.dO = s.dO; g.dS = s.dS; g.dGn = s.dG; g.d_beta = c->Gp(SEG_BETA);
+    const int rt = c->rtf();
+    g.dO = s.dO; g.dS = s.dS; g.dGn = s.dG; g.d_beta = c->Gp(SEG_BETA); g.rtf = rt;
     TRY(launch_composite_bwd(a, g, st));
     if (scene) {
         // render net
-        TRY(launch_rgb_head_bwd(s.dO, c->R2e, s.U2, N, s.dU2, st));
+        TRY(launch_rgb_head_bwd(s.dO, c->R2e, s.U2, N, s.dU2, rt, st));
         TRY(gemm_wgrad(s.dO, 4, 4, s.U2, 256, 256, N, c->dR2e, 256, c->dRB2e, P, st));
-        Epi e = epi(EPI_BWD_RELU, s.dU1, 256); e.aux = s.U1; e.lda = 256;
+        Epi e = epi(EPI_BWD_RELU, s.dU1, 256, rt); e.aux = s.U1; e.lda = 256;
         TRY(gemm_tn(s.dU2, 256, c->R1eT, 256, N, 256, 256, e, P, st));
         TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, c->Gp(SEG_R1B), P, st));
         e = epi(EPI_NONE, s.dRIN + 54, LD_RIN);
         TRY(gemm_tn(s.dU1, 256, c->R0eT + 54 * 256, 256, N, 27, 256, e, P, st));     // d PE4(grad)
-        e = epi(EPI_NONE, s.dFEAT, 256);
+        e = epi(EPI_NONE, s.dFEAT, 256, rt);
         TRY(gemm_tn(s.dU1, 256, c->R0eT + 81 * 256, 256, N, 256, 256, e, P, st));    // d feature
         TRY(gemm_wgrad(s.dU1, 256, 256, s.RIN, LD_RIN, LD_RIN, N, c->dR0e, LD_RIN, c->Gp(SEG_R0B), P, st));
         // colour-feature MLP + colour hash grid
         TRY(gemm_wgrad(s.dFEAT, 256, 256, s.C1, 256, 256, N, c->Gp(SEG_C1W), 256, c->Gp(SEG_C1B), P, st));
-        e = epi(EPI_BWD_RELU, s.dC1, 256); e.aux = s.C1; e.lda = 256;
+        e = epi(EPI_BWD_RELU, s.dC1, 256, rt); e.aux = s.C1; e.lda = 256;
         TRY(gemm_tn(s.dFEAT, 256, c->C1T, 256, N, 256, 256, e, P, st));
         TRY(gemm_wgrad(s.dC1, 256, 256, s.EC, 32, 32, N, c->Gp(SEG_C0W), 32, c->Gp(SEG_C0B), P, st));
         e = epi(EPI_NONE, s.dEC, 32);
@@ -434,7 +445,7 @@ extern "C" int hsb_eikonal_forward(hsb_ctx* h, const float* x, int64_t Ne, float
     const int ns = c->K + 1;
     s.N = Ne; s.nseed = ns;
     cudaMemcpyAsync(s.X, x, (size_t)Ne * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    TRY(launch_points_pe(s.X, Ne, s.H0, st));
+    TRY(launch_points_pe(s.X, Ne, s.H0, c->rtf(), st));
     TRY(sdf_forward(c, s, Ne, true, st));
     TRY(launch_sdf_min(s.SR, Ne, c->K, c->Kp, -1, s.SDF, s.KS, st));
     TRY(chain_forward(c, s, Ne, ns, st));

@@ -30,26 +30,29 @@ struct CompositeArgs {
 struct CompositeGrads {
     const float* d_rgb_values; const float* d_depth_values; const float* d_normal_map; const float* d_opacity;
     float* dO; float* dS; float* dGn; float* d_beta;
+    int rtf;   // store dS rounded to TF32
 };
 
-int launch_ray_points(const float* o, const float* d, const float* z, int R, int S, float* X, float* H0, float* RIN, cudaStream_t st);
-int launch_points_pe(const float* X, long long N, float* H0, cudaStream_t st);
+int launch_ray_points(const float* o, const float* d, const float* z, int R, int S, float* X, float* H0, float* RIN, int rtf, cudaStream_t st);
+int launch_points_pe(const float* X, long long N, float* H0, int rtf, cudaStream_t st);
 int launch_sdf_min(const float* SR, long long N, int K, int Kp, int channel, float* sdf, int* kstar, cudaStream_t st);
-int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long long N, int K, int nseed, float* P2, cudaStream_t st);
-int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN, cudaStream_t st);
-int launch_chain_end_bwd(float* dG, const float* dRIN, const float* RIN, const float* H0, const float* DY, long long N, int nseed, float* dQ0, cudaStream_t st);
+int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long long N, int K, int nseed, float* P2, int rtf, cudaStream_t st);
+int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN, int rtf, cudaStream_t st);
+int launch_chain_end_bwd(float* dG, const float* dRIN, const float* RIN, const float* H0, const float* DY, long long N, int nseed, float* dQ0, int rtf, cudaStream_t st);
 int launch_rgb_head(const float* U2, const float* R2e, const float* bias, long long N, float* RGB, cudaStream_t st);
-int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, cudaStream_t st);
+int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, int rtf, cudaStream_t st);
 int launch_scatter_rows(const float* dQ2, const int* kstar, long long N, int K, int Kp, int nseed, float* dW2e, cudaStream_t st);
 int launch_add_min_grad(const float* dsdf, const int* kstar, long long N, int Kp, float* dS, cudaStream_t st);
 int launch_composite_fwd(const CompositeArgs& a, cudaStream_t st);
 int launch_composite_bwd(const CompositeArgs& a, const CompositeGrads& g, cudaStream_t st);
 
 // optim.cu
-int launch_wn_forward(const float* v, const float* g, int rows, int cols, float* We, int ldw, float* WeT, int ldt, cudaStream_t st);
+int launch_wn_forward(const float* v, const float* g, int rows, int cols, float* We, int ldw, float* WeT, int ldt, int rtf, cudaStream_t st);
 int launch_wn_backward(const float* dWe, int ldw, const float* v, const float* g, int rows, int cols, float* dv, float* dg, cudaStream_t st);
 int launch_add_into(const float* src, float* dst, int n, cudaStream_t st);
-int launch_transpose(const float* W, int rows, int cols, float* WT, int ldt, cudaStream_t st);
+int launch_transpose(const float* W, int rows, int cols, float* WT, int ldt, float* Wcopy, int rtf, cudaStream_t st);
+int hash_forward_ex(const float* x, const float* emb, const int32_t* offs, float* out, long long ls, long long ps, float* dy, long long dps,
+                    uint32_t B, uint32_t L, float S, uint32_t H, int map01, int rtf, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float* gnorm2, cudaStream_t st);
 
 }  // namespace hsb

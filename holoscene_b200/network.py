@@ -200,6 +200,7 @@ class HoloSceneNetwork(nn.Module):
         self._flat_grad = None
         self.draws = None
         self._last_ne = 0
+        self.phase_ms = None      # dict -> per-phase timing (debug)
 
     # ---- flat parameter storage -----------------------------------------------------------------------
     def _named_segments(self):
@@ -289,8 +290,13 @@ class HoloSceneNetwork(nn.Module):
         ray_dirs = ray_dirs.reshape(-1, 3).contiguous()
         R = ray_dirs.shape[0]
 
+        if self.phase_ms is not None:
+            import time
+            torch.cuda.synchronize(); _t0 = time.perf_counter()
         z_vals, z_samples_eik = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self)
         z_vals = z_vals.contiguous()
+        if self.phase_ms is not None:
+            torch.cuda.synchronize(); self.phase_ms["sampler"] = self.phase_ms.get("sampler", 0.0) + (time.perf_counter() - _t0) * 1e3
         S = z_vals.shape[1]
         rot = pose[0, :3, :3].permute(1, 0).contiguous()
         rgbv, depth, nmap, opac, sem = eng.render_forward(_engine.SLOT_MAIN, cam_loc, ray_dirs, z_vals, depth_scale, rot)
