@@ -256,6 +256,18 @@ __global__ void __launch_bounds__(256) gemm_wgrad_kernel(const float* __restrict
     if (do_bias && a0 + tid < N1) atomicAdd(bias + a0 + tid, colsum);
 }
 
+// bias[n] += sum_m A[m, n]   (column sums; used when the tcgen05 wgrad path handles the contraction)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, long long lda, int N1, long long M,
+                                                     long long rows_per_cta, float* __restrict__ bias) {
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = min(M, r0 + rows_per_cta);
+    for (int n = threadIdx.x; n < N1; n += 256) {
+        float acc = 0.0f;
+        for (long long r = r0; r < r1; ++r) acc += A[r * lda + n];
+        atomicAdd(bias + n, acc);
+    }
+}
+
 static int g_num_sms = 0;
 int num_sms() {
     if (g_num_sms == 0) {
@@ -294,6 +306,16 @@ int gemm_tn(const float* A, long long lda, const float* B, long long ldb, long l
 int gemm_wgrad(const float* A, long long lda, int N1, const float* B, long long ldb, int N2, long long M, float* C,
                long long ldc, float* bias, int precise, cudaStream_t stream) {
     if (M <= 0 || N1 <= 0 || N2 <= 0) return HSB_OK;
+    if (precise == 0 && gemm_wgrad_tc_eligible(A, lda, N1, B, ldb, N2, M)) {
+        if (bias) {
+            long long ctas = 8LL * num_sms();
+            long long rpc = (M + ctas - 1) / ctas;
+            if (rpc < 32) rpc = 32;
+            colsum_kernel<<<(unsigned)((M + rpc - 1) / rpc), 256, 0, stream>>>(A, lda, N1, M, rpc, bias);
+            count_launch(1);
+        }
+        return gemm_wgrad_tc(A, lda, N1, B, ldb, N2, M, C, ldc, stream);
+    }
     if ((N1 & 3) || (N2 & 3) || (lda & 3) || (ldb & 3) || (((uintptr_t)A | (uintptr_t)B) & 15)) {
         set_error("gemm_wgrad: N1, N2, lda, ldb must be multiples of 4 floats and A, B 16-byte aligned");
         return HSB_ERR_ARG;

@@ -79,58 +79,93 @@ __device__ __forceinline__ void epilogue_store(const Epi& e, long long m, int n,
 }
 
 // `rows` consecutive rows m_first.. of ONE column n (the tcgen05 epilogue: a warp holds a 32x32 tile transposed in
-// smem, lane = column).  vals[r * vstride] is the accumulator of row m_first + r.  Pointers advance incrementally;
-// the aux row index wraps modulo aux_rows without a per-element 64-bit division.
-template <bool FAST>
-__device__ __forceinline__ void epilogue_rows(const Epi& e, long long m_first, int rows, int n, const float* vals, int vstride) {
+// smem, lane = column).  vals[r * vstride] is the accumulator of row m_first + r.  Specialised per epilogue kind at
+// compile time.  Rows are processed 8 at a time: all global loads of a group (aux / aux2) are issued into registers
+// BEFORE the group's stores, otherwise every store orders the following load behind it (possible aliasing) and the
+// loop runs at one L2 round trip per row.  The aux row index wraps modulo aux_rows without per-element division.
+template <bool FAST, int KIND>
+__device__ __forceinline__ void epilogue_rows_k(const Epi& e, long long m_first, int rows, int n, const float* vals, int vstride) {
+    constexpr bool AUX = (KIND == EPI_MUL_SIGMA || KIND == EPI_BWD_CHAIN || KIND == EPI_BWD_SP || KIND == EPI_BWD_RELU);
+    constexpr bool AUX2 = (KIND == EPI_BWD_CHAIN || KIND == EPI_BWD_SP);
+    constexpr bool BIAS = (KIND == EPI_BIAS || KIND == EPI_BIAS_SOFTPLUS || KIND == EPI_BIAS_RELU || KIND == EPI_BIAS_SIGMOID);
+    const float b = BIAS ? e.bias[n] : 0.0f;
+    const int ro = e.round_out;
     float* out = e.out + m_first * e.ldo + n;
     long long ma = 0;
-    if (e.aux) ma = e.aux_rows > 0 ? (m_first % e.aux_rows) : m_first;
+    const float* ap = nullptr;
     const long long wrap = e.aux_rows > 0 ? e.aux_rows : (1LL << 62);
-    const float* aux = e.aux ? e.aux + ma * e.lda + n : nullptr;
-    const float b = e.bias ? e.bias[n] : 0.0f;
-    const int ro = e.round_out;
-#define HSB_ROWS(BODY)                                                           \
-    _Pragma("unroll 4") for (int r = 0; r < rows; ++r) {                        \
-        const float acc = vals[r * vstride];                                     \
-        BODY;                                                                    \
-        out += e.ldo;                                                            \
+    if (AUX) {
+        ma = e.aux_rows > 0 ? (m_first % e.aux_rows) : m_first;
+        ap = e.aux + ma * e.lda + n;
     }
-#define HSB_AUX_NEXT                                                             \
-    { ++ma; if (ma == wrap) { ma = 0; aux = e.aux + n; } else aux += e.lda; }
+    const bool has2 = AUX2 && (e.aux2 != nullptr);
+    const float* a2p = has2 ? e.aux2 + m_first * e.lda2 + n : nullptr;
+    float* o2 = nullptr;
+    if (KIND == EPI_BWD_CHAIN) o2 = e.out2 + (e.atomic2 ? ma : m_first) * e.ldo2 + n;
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+        float ax[8], a2[8];
+        float* o2p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            ax[i] = 0.0f; a2[i] = 0.0f; o2p[i] = o2;
+            if (r0 + i < rows) {
+                if (AUX) ax[i] = *ap;
+                if (has2) { a2[i] = *a2p; a2p += e.lda2; }
+                if (AUX) {
+                    ++ma;
+                    if (ma == wrap) { ma = 0; ap = e.aux + n; if (KIND == EPI_BWD_CHAIN) o2 = e.atomic2 ? e.out2 + n : o2 + e.ldo2; }
+                    else { ap += e.lda; if (KIND == EPI_BWD_CHAIN) o2 += e.ldo2; }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (r0 + i < rows) {
+                const float acc = vals[(r0 + i) * vstride];
+                float o;
+                if (KIND == EPI_NONE) o = acc;
+                else if (KIND == EPI_BIAS) o = acc + b;
+                else if (KIND == EPI_BIAS_SOFTPLUS) o = epi_softplus<FAST>(acc + b);
+                else if (KIND == EPI_BIAS_RELU) o = fmaxf(acc + b, 0.0f);
+                else if (KIND == EPI_BIAS_SIGMOID) o = epi_sigmoid<FAST>(acc + b);
+                else if (KIND == EPI_MUL_SIGMA) o = acc * epi_sigma<FAST>(ax[i]);
+                else if (KIND == EPI_BWD_CHAIN) {
+                    const float sg = epi_sigma<FAST>(ax[i]);
+                    o = acc * sg;
+                    const float v = acc * a2[i] * 100.0f * (1.0f - sg);
+                    if (e.atomic2) atomicAdd(o2p[i], v);
+                    else *o2p[i] = v;
+                } else if (KIND == EPI_BWD_SP) o = acc * epi_sigma<FAST>(ax[i]) + a2[i];
+                else o = ax[i] > 0.0f ? acc : 0.0f;      // EPI_BWD_RELU
+                out[(long long)i * e.ldo] = rtf32(o, ro);
+            }
+        }
+        out += 8 * e.ldo;
+    }
+}
+
+template <bool FAST>
+__device__ __forceinline__ void epilogue_rows(const Epi& e, long long m_first, int rows, int n, const float* vals, int vstride) {
     switch (e.kind) {
-        case EPI_NONE: HSB_ROWS(*out = rtf32(acc, ro)) break;
-        case EPI_BIAS: HSB_ROWS(*out = rtf32(acc + b, ro)) break;
-        case EPI_BIAS_SOFTPLUS: HSB_ROWS(*out = rtf32(epi_softplus<FAST>(acc + b), ro)) break;
-        case EPI_BIAS_RELU: HSB_ROWS(*out = rtf32(fmaxf(acc + b, 0.0f), ro)) break;
-        case EPI_BIAS_SIGMOID: HSB_ROWS(*out = epi_sigmoid<FAST>(acc + b)) break;
-        case EPI_MUL_SIGMA: HSB_ROWS(*out = rtf32(acc * epi_sigma<FAST>(*aux), ro); HSB_AUX_NEXT) break;
-        case EPI_BWD_CHAIN: {
-            const float* a2 = e.aux2 + m_first * e.lda2 + n;
-            float* o2 = e.out2 + (e.atomic2 ? ma : m_first) * e.ldo2 + n;
-            HSB_ROWS(const float sg = epi_sigma<FAST>(*aux); *out = rtf32(acc * sg, ro);
-                     const float v = acc * (*a2) * 100.0f * (1.0f - sg);
-                     if (e.atomic2) atomicAdd(o2, v); else *o2 = v;
-                     a2 += e.lda2;
-                     { ++ma; if (ma == wrap) { ma = 0; aux = e.aux + n; if (e.atomic2) o2 = e.out2 + n; else o2 += e.ldo2; }
-                       else { aux += e.lda; o2 += e.ldo2; } })
-            break;
-        }
-        case EPI_BWD_SP: {
-            const float* a2 = e.aux2 ? e.aux2 + m_first * e.lda2 + n : nullptr;
-            HSB_ROWS(float x = acc * epi_sigma<FAST>(*aux); if (a2) { x += *a2; a2 += e.lda2; } *out = rtf32(x, ro); HSB_AUX_NEXT)
-            break;
-        }
-        case EPI_BWD_RELU: HSB_ROWS(*out = (*aux > 0.0f) ? rtf32(acc, ro) : 0.0f; HSB_AUX_NEXT) break;
+        case EPI_NONE: epilogue_rows_k<FAST, EPI_NONE>(e, m_first, rows, n, vals, vstride); break;
+        case EPI_BIAS: epilogue_rows_k<FAST, EPI_BIAS>(e, m_first, rows, n, vals, vstride); break;
+        case EPI_BIAS_SOFTPLUS: epilogue_rows_k<FAST, EPI_BIAS_SOFTPLUS>(e, m_first, rows, n, vals, vstride); break;
+        case EPI_BIAS_RELU: epilogue_rows_k<FAST, EPI_BIAS_RELU>(e, m_first, rows, n, vals, vstride); break;
+        case EPI_BIAS_SIGMOID: epilogue_rows_k<FAST, EPI_BIAS_SIGMOID>(e, m_first, rows, n, vals, vstride); break;
+        case EPI_MUL_SIGMA: epilogue_rows_k<FAST, EPI_MUL_SIGMA>(e, m_first, rows, n, vals, vstride); break;
+        case EPI_BWD_CHAIN: epilogue_rows_k<FAST, EPI_BWD_CHAIN>(e, m_first, rows, n, vals, vstride); break;
+        case EPI_BWD_SP: epilogue_rows_k<FAST, EPI_BWD_SP>(e, m_first, rows, n, vals, vstride); break;
+        default: epilogue_rows_k<FAST, EPI_BWD_RELU>(e, m_first, rows, n, vals, vstride); break;
     }
-#undef HSB_ROWS
-#undef HSB_AUX_NEXT
 }
 
 int num_sms();
 bool gemm_tn_tc_eligible(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K);
 int gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K, const Epi& epi,
                cudaStream_t stream);
+bool gemm_wgrad_tc_eligible(const float* A, long long lda, int N1, const float* B, long long ldb, int N2, long long M);
+int gemm_wgrad_tc(const float* A, long long lda, int N1, const float* B, long long ldb, int N2, long long M, float* C,
+                  long long ldc, cudaStream_t stream);
 int gemm_tn(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K, const Epi& epi,
             int precise, cudaStream_t stream);
 int gemm_wgrad(const float* A, long long lda, int N1, const float* B, long long ldb, int N2, long long M, float* C,

@@ -187,6 +187,132 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
 }
 
+// =================================================================================================
+// wgrad on tcgen05:   C[N1,N2] += A[M,N1]^T . B[M,N2]      (reduction over the point dimension M)
+//
+// Both operands are "MN-major" for the tensor core: the contraction index (the row m) is the slow
+// dimension of the row-major activation matrices.  A stage holds 32 rows: the N1-tile (128 columns
+// of A) as 4 TMA boxes of [32 rows x 32 columns = 128 B], the N2-tile (<= 256 columns of B) as up to 8
+// boxes.  For 32-bit MN-major operands the tensor core accepts only the "128B swizzle with 32B atomicity"
+// layout (UMMA LayoutType 1 = SWIZZLE_128B_BASE32B; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of
+// 4 rows x 128 B in which the 32-byte chunk index is XORed with (row % 4).  Next 32 columns = next box
+// (LBO = 4096 B); next 4 rows = next atom (SBO = 512 B).  One tcgen05.mma (K = 8 tf32) consumes two atoms
+// (8 rows) of every box; 4 MMAs per stage.  The [128 x N2] fp32
+// accumulator stays in TMEM over the CTA's whole row range (blockIdx.z = split); the epilogue adds it to
+// C with coalesced fp32 reductions.
+// =================================================================================================
+constexpr int WG_ROWS = 32;                                   // rows (k) per stage
+constexpr int WG_BOX_BYTES = WG_ROWS * 128;                   // 4 KB: [32 rows x 32 floats]
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;         // leading byte offset: next 32 MN elements = next box
+    d |= (uint64_t)(512 >> 4) << 32;                  // stride byte offset: next 4-row atom along k
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                           // SWIZZLE_128B_BASE32B
+    return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, long long M, int N1,
+                     int N2, int n2_tile, int n_mma, uint32_t idesc, long long rows_per_split, float* __restrict__ C,
+                     long long ldc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty = full + TC_STAGES;
+    uint64_t* tfull = empty + TC_STAGES;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tfull + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a0 = blockIdx.y * 128;                 // first column of A (row of C) of this CTA
+    const int b0 = blockIdx.x * n2_tile;             // first column of B (column of C)
+    const int nb = min(n2_tile, N2 - b0);            // valid C columns in this tile
+    const long long r_begin = (long long)blockIdx.z * rows_per_split;
+    const long long r_end = min(M, r_begin + rows_per_split);
+    const int nkb = r_begin < r_end ? (int)((r_end - r_begin + WG_ROWS - 1) / WG_ROWS) : 0;
+    const int a_boxes = 4, b_boxes = n_mma / 32 + ((n_mma & 31) ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_holder;
+
+    if (nkb > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)(a_boxes + b_boxes) * WG_BOX_BYTES;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int s = kb % TC_STAGES;
+                    const uint32_t ph = (kb / TC_STAGES) & 1;
+                    mbar_wait(empty + s, ph ^ 1);
+                    mbar_expect_tx(full + s, bytes);
+                    uint8_t* st = smem + s * TC_STAGE_BYTES;
+                    const int row = (int)(r_begin + (long long)kb * WG_ROWS);
+                    // rows_per_split is a multiple of 32, so a stage never straddles two splits; rows >= M are zero-filled
+                    for (int j = 0; j < a_boxes; ++j) tma_load_2d(&mapA, full + s, st + j * WG_BOX_BYTES, a0 + 32 * j, row);
+                    for (int j = 0; j < b_boxes; ++j) tma_load_2d(&mapB, full + s, st + TC_A_BYTES + j * WG_BOX_BYTES, b0 + 32 * j, row);
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int s = kb % TC_STAGES;
+                    const uint32_t ph = (kb / TC_STAGES) & 1;
+                    mbar_wait(full + s, ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * TC_STAGE_BYTES);
+                    const uint64_t ad = smem_desc_mn_sw128(sa), bd = smem_desc_mn_sw128(sa + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < WG_ROWS / 8; ++k)      // next 8 rows = +1024 B = +64 in the (addr >> 4) field
+                        umma_tf32(tmem, ad + 64 * k, bd + 64 * k, idesc, (uint32_t)((kb | k) != 0));
+                    umma_commit(empty + s);
+                }
+                umma_commit(tfull);
+            }
+        } else {
+            const int ew = warp - 2;
+            const int q = warp & 3;
+            const int half = ew >> 2;
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+            float* buf = reinterpret_cast<float*>(smem) + ew * (32 * 33);
+            const int nchunk = (nb + 31) / 32;
+            for (int c = half; c < nchunk; c += 2) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = v[j];
+                __syncwarp();
+                const int n2 = c * 32 + lane;
+                if (n2 < nb) {
+                    for (int r = 0; r < 32; ++r) {
+                        const int n1 = a0 + q * 32 + r;
+                        if (n1 < N1) atomicAdd(C + (long long)n1 * ldc + b0 + n2, buf[r * 33 + lane]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side: tensor maps through the driver entry point (no link-time dependency on libcuda) ----------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -212,7 +338,8 @@ static bool tc_init() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     if (major != 10) return false;
-    if (cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
@@ -220,13 +347,14 @@ static bool tc_init() {
     return true;
 }
 
-static bool make_map(CUtensorMap* map, const float* base, long long rows, int cols, long long ld, int box_rows) {
+static bool make_map(CUtensorMap* map, const float* base, long long rows, int cols, long long ld, int box_rows,
+                     CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -251,6 +379,43 @@ int gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, lon
     const unsigned grid = (unsigned)((M + TC_BM - 1) / TC_BM);
     gemm_tn_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mapA, mapB, M, N, K, n_mma, idesc, epi);
     return check_launch("gemm_tn_tc");
+}
+
+bool gemm_wgrad_tc_eligible(const float* A, long long lda, int N1, const float* B, long long ldb, int N2, long long M) {
+    if (N1 < 1 || N2 < 1 || (N1 & 3) || (N2 & 3) || (lda & 3) || (ldb & 3)) return false;
+    if ((((uintptr_t)A) | ((uintptr_t)B)) & 15) return false;
+    if (M > 0x7fffffffLL || M < 1) return false;
+    return tc_init();
+}
+
+int gemm_wgrad_tc(const float* A, long long lda, int N1, const float* B, long long ldb, int N2, long long M, float* C,
+                  long long ldc, cudaStream_t stream) {
+    // N2 is covered by tiles of <= 256 columns, N1 by tiles of 128; the row range is split over blockIdx.z so that
+    // ~2 CTAs per SM are in flight.  Every split gets its own row extent through the launch (rows_per_split is a
+    // multiple of 32, so a stage never straddles two splits; the tensor map bounds rows at M).
+    const int n2_tile = N2 <= 256 ? N2 : 256;
+    const int n2_tiles = (N2 + n2_tile - 1) / n2_tile;
+    const int n1_tiles = (N1 + 127) / 128;
+    const int tiles = n1_tiles * n2_tiles;
+    long long splits = (2LL * num_sms() + tiles - 1) / tiles;
+    const long long max_splits = (M + 8 * WG_ROWS - 1) / (8 * WG_ROWS);          // at least 256 rows per split
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    long long rps = ((M + splits - 1) / splits + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
+    splits = (M + rps - 1) / rps;
+    const int n_mma = ((n2_tile + 15) / 16) * 16;
+    CUtensorMap mapA, mapB;
+    if (!make_map(&mapA, A, M, N1, lda, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+        !make_map(&mapB, B, M, N2, ldb, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
+        set_error("gemm_wgrad_tc: cuTensorMapEncodeTiled failed");
+        return HSB_ERR_CUDA;
+    }
+    // D = f32, A = B = tf32, BOTH MN-major (bits 15, 16), N>>3 at 17, M>>4 at 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    dim3 grid((unsigned)n2_tiles, (unsigned)n1_tiles, (unsigned)splits);
+    gemm_wgrad_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mapA, mapB, M, N1, N2, n2_tile, n_mma, idesc, rps, C, ldc);
+    return check_launch("gemm_wgrad_tc");
 }
 
 }  // namespace hsb

@@ -12,6 +12,7 @@ import torch
 import torch.distributed as dist
 
 from .optim import StageOneAdam
+from .parallel import allreduce_mean_
 
 
 class TrainStep:
@@ -48,9 +49,7 @@ class TrainStep:
         losses["loss"].backward()
         t = self._mark("backward", t)
         if self.world_size > 1:
-            g = self.model.engine().grads
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)
-            g.mul_(1.0 / self.world_size)
+            allreduce_mean_(self.model.engine().grads, self.world_size)
             t = self._mark("allreduce", t)
         self.opt.step()
         self.opt.scheduler_step()
