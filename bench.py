@@ -268,7 +268,7 @@ def main():
         pass
     peak = peaks.get("bf16_tflops_sustained", 1590.0)
     ach = flops / (k_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_tn_kernel (256x256 fc + softplus epilogue, TF32 mma.sync)", "achieved": ach,
+    roofline = {"bound": "tensor", "kernel": "gemm_tn_tc_kernel (256x256 fc + softplus epilogue; tcgen05.mma kind::tf32, TMA-fed, TMEM accumulator)" if not args.precise else "gemm_tn_kernel<true> (3xTF32 mma.sync parity mode)", "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1590 (of fallback)",
                 "note": "operands are TF32 (nominal dense peak is half the bf16 figure used as denominator); "

@@ -54,6 +54,11 @@ _render_bwd = declare("hsb_render_backward", [_vp, ctypes.c_int32, _vp, _vp, _vp
 _eik_fwd = declare("hsb_eikonal_forward", [_vp, _vp, ctypes.c_int64, _vp, _vp, _vp, c_stream])
 _eik_bwd = declare("hsb_eikonal_backward", [_vp, _vp, _vp, c_stream])
 _adam = declare("hsb_adam_step", [_vp, _vp, _vp, _vp, c_ll, c_f32, c_f32, c_f32, c_f32, c_int, _vp, c_stream])
+i32 = ctypes.c_int32
+sampler_init = declare("hsb_sampler_init", [_vp, _vp, i32, i32, c_f32, c_f32, c_f32, _vp, c_f32, _vp, _vp, c_stream])
+sampler_bound = declare("hsb_sampler_bound", [_vp, _vp, i32, _vp, _vp, i32, _vp, _vp, _vp, _vp, c_f32, c_f32, i32, i32, _vp, c_stream])
+sampler_resample = declare("hsb_sampler_resample", [_vp, _vp, i32, _vp, i32, _vp, i32, c_f32, i32, _vp, c_stream])
+sampler_finalize = declare("hsb_sampler_finalize", [_vp, i32, _vp, i32, _vp, i32, c_f32, c_f32, _vp, i32, _vp, _vp, c_stream])
 gemm_tn = declare("hsb_gemm_tn", [_vp, c_ll, _vp, c_ll, c_ll, c_int, c_int, c_int, _vp, c_ll, _vp, _vp, c_ll, c_ll, _vp, c_ll,
                                   _vp, c_ll, c_int, c_int, c_stream])
 gemm_wgrad = declare("hsb_gemm_wgrad", [_vp, c_ll, c_int, _vp, c_ll, c_int, c_ll, _vp, c_ll, _vp, c_int, c_stream])

@@ -4,8 +4,9 @@ get_z_vals contract as the reference model/ray_sampler.py:16-83,105-287,450-458.
 The SDF queries of every refinement round go through libhsb200 (hsb_sdf_values: hash lookup + SDF
 MLP + min over objects in fused CUDA, SDF-only -- the reference evaluates the colour grid and the
 colour MLP here for nothing, network.py:177-179).  The per-ray bookkeeping between rounds (d* bound,
-beta bisection, CDF inversion, merge) runs as device tensor ops; the only host sync per round is
-the reference's own global convergence test (ray_sampler.py:204).
+beta bisection, CDF inversion, merge) runs in libhsb200's sampler kernels (csrc/sampler.cu, one warp per
+ray); the only host sync per round is the reference's own global convergence test (ray_sampler.py:204).
+`get_z_vals_torch` keeps the same algorithm as device tensor ops (cross-check in the GPU tests).
 """
 from __future__ import annotations
 
@@ -80,6 +81,69 @@ class ErrorBoundSampler:
 
     @torch.no_grad()
     def get_z_vals(self, ray_dirs, cam_loc, model, idx=None):
+        """Same contract as the reference (ray_sampler.py:130-287).  Every refinement round is: fused SDF query of the new
+        samples (hsb_sdf_values) -> hsb_sampler_bound (merge, d*, beta bisection, global flag) -> ONE host read of the flag
+        (the reference's `beta.max() > beta0` sync) -> hsb_sampler_resample.  No other host round trips, no torch ops."""
+        from . import _lib, engine as E
+        dev = ray_dirs.device
+        R = ray_dirs.shape[0]
+        eng = model.engine()
+        channel = -1 if idx is None else int(idx)
+        o = cam_loc.contiguous()
+        d = ray_dirs.contiguous()
+        p, st = _lib.ptr, _lib.stream
+        Ne = self.N_samples_eval
+        t_rand = model.draws.rand("t_rand", (R, Ne)).contiguous() if model.training else None
+        samples = torch.empty(R, Ne, device=dev)
+        beta = torch.empty(R, device=dev)
+        _lib.check(E.sampler_init(p(o), p(d), R, Ne, float(self.near), float(self.far), float(self.scene_bounding_sphere),
+                                  p(t_rand), float(self.eps), p(samples), p(beta), st()))
+        beta_param = model.density.beta
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        z_all = sdf_all = None
+        n_old, total_iters, not_converge = 0, 0, True
+        while not_converge and total_iters < self.max_total_iters:
+            s_new = eng.sdf_values(o, d, samples, channel)
+            n_new = samples.shape[1]
+            n = n_old + n_new
+            z_out = torch.empty(R, n, device=dev)
+            sdf_out = torch.empty(R, n, device=dev)
+            flag.zero_()
+            _lib.check(E.sampler_bound(p(z_all), p(sdf_all), n_old, p(samples), p(s_new), n_new, p(z_out), p(sdf_out), p(beta),
+                                       p(beta_param), float(model.density.beta_min), float(self.eps), int(self.beta_iters), R,
+                                       p(flag), st()))
+            z_all, sdf_all, n_old = z_out, sdf_out, n
+            total_iters += 1
+            not_converge = bool(flag.item())                    # the reference's per-round host sync (:204)
+            more = not_converge and total_iters < self.max_total_iters
+            if more:
+                N, mode, u = Ne, 0, None
+            else:
+                N, mode = self.N_samples, 1
+                u = model.draws.rand("u_final", R, N).contiguous() if model.training else None
+            samples = torch.empty(R, N, device=dev)
+            _lib.check(E.sampler_resample(p(z_all), p(sdf_all), n_old, p(beta), mode, p(u), N, float(self.add_tiny), R,
+                                          p(samples), st()))
+        self.last_rounds = total_iters
+        n = n_old
+        if self.N_samples_extra > 0:
+            if model.training:
+                sampling_idx = model.draws.randperm("extra_perm", n)[: self.N_samples_extra]
+            else:
+                sampling_idx = torch.linspace(0, n - 1, self.N_samples_extra, device=dev).long()
+            extra = sampling_idx.to(dev, torch.int32).contiguous()
+        else:
+            extra = None
+        S = self.N_samples + 2 + self.N_samples_extra
+        eidx = model.draws.randint("eik_idx", S, (R,)).to(dev, torch.int32).contiguous()
+        z_vals = torch.empty(R, S, device=dev)
+        z_eik = torch.empty(R, 1, device=dev)
+        _lib.check(E.sampler_finalize(p(z_all), n, p(samples), self.N_samples, p(extra), self.N_samples_extra, float(self.near),
+                                      float(self.far), p(eidx), R, p(z_vals), p(z_eik), st()))
+        return z_vals, z_eik
+
+    @torch.no_grad()
+    def get_z_vals_torch(self, ray_dirs, cam_loc, model, idx=None):
         dev = ray_dirs.device
         R = ray_dirs.shape[0]
         eng = model.engine()

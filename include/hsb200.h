@@ -144,6 +144,25 @@ int hsb_finish(hsb_ctx* ctx, hsb_stream_t stream);
 int hsb_sdf_values(hsb_ctx* ctx, const float* o, const float* d, const float* z, int32_t R, int32_t S, int32_t channel,
                    float* sdf_out, hsb_stream_t stream);
 
+/* Error-bound sampler bookkeeping (model/ray_sampler.py:63-83,130-287,450-458); one warp per ray.
+ *   init:     z [R,N] uniform in [near, exit of the [-bound,bound]^3 cube (clamped to far_clamp)], stratified with t_rand [R,N]
+ *             (NULL = deterministic); beta [R] = sqrt(sum(dz^2) / (4 log(1+eps))).
+ *   bound:    merges (samples, sdf_new) [R,n_new] into the z-sorted (z_old, sdf_old) [R,n_old] -> (z_out, sdf_out) [R,n_old+n_new];
+ *             d* bound, error bound at beta0 = |*beta_param| + beta_min, `beta_iters` bisection steps; beta [R] updated in place;
+ *             *flag |= 1 if any ray still has beta > beta0 (the reference's global convergence test, :204).
+ *   resample: mode 0 = refinement pdf (opacity error bound + add_tiny), mode 1 = final pdf (weights + 1e-5); inverse CDF at
+ *             u [R,N] (NULL = linspace(0,1,N)) -> samples [R,N].
+ *   finalize: z_final [R, Ns+2+Ne] = sort(cat[samples, near, far, z[:, extra_idx]]);  z_eik[r] = z_final[r, eik_idx[r]]. */
+int hsb_sampler_init(const float* o, const float* d, int32_t R, int32_t N, float near, float far_clamp, float bound,
+                     const float* t_rand, float eps, float* z, float* beta, hsb_stream_t stream);
+int hsb_sampler_bound(const float* z_old, const float* sdf_old, int32_t n_old, const float* samples, const float* sdf_new,
+                      int32_t n_new, float* z_out, float* sdf_out, float* beta, const float* beta_param, float beta_min, float eps,
+                      int32_t beta_iters, int32_t R, int32_t* flag, hsb_stream_t stream);
+int hsb_sampler_resample(const float* z, const float* sdf, int32_t n, const float* beta, int32_t mode, const float* u, int32_t N,
+                         float add_tiny, int32_t R, float* samples, hsb_stream_t stream);
+int hsb_sampler_finalize(const float* z, int32_t n, const float* samples, int32_t Ns, const int32_t* extra_idx, int32_t Ne, float near,
+                         float far, const int32_t* eik_idx, int32_t R, float* z_final, float* z_eik, hsb_stream_t stream);
+
 /* Ray pass forward.  o, d [R,3]; z [R,S] sorted sample depths; depth_scale [R]; rot [9] = pose[:3,:3]^T row-major.
  * Outputs (per ray): rgb_values [R,3], depth_values [R], normal_map [R,3], opacity [R,K], semantic [R,K]
  * (BG slot: rgb_values / opacity unused, may be NULL).  Per-sample state stays in the workspace

@@ -277,3 +277,35 @@ def test_eikonal_pass_backward_matches_oracle():
     report("eikonal pass backward", rows)
     bad = [r for r in rows if not (r[1] <= r[2])]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("training", [False, True])
+def test_sampler_kernels_match_tensor_op_sampler(training):
+    """csrc/sampler.cu (one warp per ray) against the same algorithm written as device tensor ops
+    (ErrorBoundSampler.get_z_vals_torch), on the same rays / weights / random draws, scene SDF and channel 0."""
+    from holoscene_b200 import rend_util
+    from holoscene_b200.rng import ReplayDraws
+    g = common.load_golden("step_train")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    m = build_model(cfg, sd, True)
+    m.train() if training else m.eval()
+    uv, pose, K, gt, draws = common.golden_inputs(g)
+    eng = m.engine()
+    eng.prepare()
+    dirs, cam = rend_util.get_camera_params(uv.clone().cuda(), pose.cuda(), K.cuda())
+    dirs = dirs.reshape(-1, 3).contiguous()
+    cam = cam.unsqueeze(1).repeat(1, dirs.shape[0], 1).reshape(-1, 3).contiguous()
+    # the recorded draws belong to the scene sampler call (extra_perm has the scene's sample count): channel 0 only in eval mode
+    for idx in ((None,) if training else (None, 0)):
+        m.draws = ReplayDraws(draws, "cuda")
+        z_a, e_a = m.ray_sampler.get_z_vals(dirs, cam, m, idx=idx)
+        rounds_a = m.ray_sampler.last_rounds
+        m.draws = ReplayDraws(draws, "cuda")
+        z_b, e_b = m.ray_sampler.get_z_vals_torch(dirs, cam, m, idx=idx)
+        assert rounds_a == m.ray_sampler.last_rounds and rounds_a >= 2
+        assert z_a.shape == z_b.shape
+        assert float((z_a - z_b).abs().max()) < 3e-4, float((z_a - z_b).abs().max())
+        assert float((e_a - e_b).abs().max()) < 3e-4
+        assert bool((z_a[:, 1:] >= z_a[:, :-1]).all())                 # sorted
+        assert float(z_a[:, 0].abs().max()) == 0.0 and float((z_a[:, -1] - 3.5).abs().max()) == 0.0   # near / far appended
