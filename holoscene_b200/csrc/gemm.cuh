@@ -25,6 +25,7 @@ struct Epi {
     float* out2; long long ldo2;
     int atomic2;                                           // out2[m % aux_rows] += (atomic) instead of store
     int round_out;                                         // store `out` rounded to TF32 (it is a later tcgen05 operand)
+    float* colsum;                                         // optional [N]: += column sums of `out` (bias gradient), tcgen05 path only
 };
 
 // ---- epilogue math -----------------------------------------------------------------------------------
@@ -91,6 +92,7 @@ __device__ __forceinline__ void epilogue_rows_k(const Epi& e, long long m_first,
     const float b = BIAS ? e.bias[n] : 0.0f;
     const int ro = e.round_out;
     float* out = e.out + m_first * e.ldo + n;
+    float csum = 0.0f;
     long long ma = 0;
     const float* ap = nullptr;
     const long long wrap = e.aux_rows > 0 ? e.aux_rows : (1LL << 62);
@@ -138,10 +140,12 @@ __device__ __forceinline__ void epilogue_rows_k(const Epi& e, long long m_first,
                 } else if (KIND == EPI_BWD_SP) o = acc * epi_sigma<FAST>(ax[i]) + a2[i];
                 else o = ax[i] > 0.0f ? acc : 0.0f;      // EPI_BWD_RELU
                 out[(long long)i * e.ldo] = rtf32(o, ro);
+                csum += o;
             }
         }
         out += 8 * e.ldo;
     }
+    if (e.colsum) atomicAdd(e.colsum + n, csum);
 }
 
 template <bool FAST>
@@ -159,7 +163,123 @@ __device__ __forceinline__ void epilogue_rows(const Epi& e, long long m_first, i
     }
 }
 
+// ---- 128-bit vectorised tile epilogue (tcgen05 path) ---------------------------------------------------------
+// A warp owns a 32-row x 32-column accumulator tile staged in smem with row stride 36 floats.  Lane l handles the four
+// consecutive columns 4*(l & 7).. of rows (l >> 3) + 4*it, it = 0..7: every global access is a 16-byte vector, a warp
+// instruction covers four full 128-byte row segments.  Requires 16-byte aligned rows for every tensor involved
+// (epi_vec_ok); anything else takes the scalar row walker above.
+__host__ __device__ inline bool epi_vec_ok(const Epi& e, int N) {
+    auto ok = [](const void* p, long long ld) { return p == nullptr || ((((uintptr_t)p) & 15) == 0 && (ld & 3) == 0); };
+    return (N & 3) == 0 && ok(e.out, e.ldo) && ok(e.aux, e.lda) && ok(e.aux2, e.lda2) && ok(e.out2, e.ldo2) &&
+           (e.bias == nullptr || (((uintptr_t)e.bias) & 15) == 0);
+}
+
+template <bool FAST, int KIND>
+__device__ __forceinline__ void epilogue_tile_vec_k(const Epi& e, long long m_first, int rows, int c0, int N, const float* buf, int lane) {
+    constexpr bool AUX = (KIND == EPI_MUL_SIGMA || KIND == EPI_BWD_CHAIN || KIND == EPI_BWD_SP || KIND == EPI_BWD_RELU);
+    constexpr bool AUX2 = (KIND == EPI_BWD_CHAIN || KIND == EPI_BWD_SP);
+    constexpr bool BIAS = (KIND == EPI_BIAS || KIND == EPI_BIAS_SOFTPLUS || KIND == EPI_BIAS_RELU || KIND == EPI_BIAS_SIGMOID);
+    const int n = c0 + 4 * (lane & 7);
+    const int rl = lane >> 3;
+    const bool col_ok = n < N;                         // N % 4 == 0: a float4 is entirely valid or entirely out
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BIAS && col_ok) b = *reinterpret_cast<const float4*>(e.bias + n);
+    const int ro = e.round_out;
+    const bool has2 = AUX2 && (e.aux2 != nullptr);
+    const long long wrap = e.aux_rows > 0 ? e.aux_rows : (1LL << 62);
+    long long ma0 = 0;
+    if (AUX) ma0 = e.aux_rows > 0 ? (m_first % e.aux_rows) : m_first;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float4 ax[4], a2[4];
+        long long mrow[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                  // all loads of the group first
+            const int r = rl + 4 * (half * 4 + i);
+            ax[i] = make_float4(0.f, 0.f, 0.f, 0.f); a2[i] = ax[i]; mrow[i] = 0;
+            if (col_ok && r < rows) {
+                if (AUX) {
+                    long long ma = ma0 + r;
+                    while (ma >= wrap) ma -= wrap;
+                    mrow[i] = ma;
+                    ax[i] = *reinterpret_cast<const float4*>(e.aux + ma * e.lda + n);
+                }
+                if (has2) a2[i] = *reinterpret_cast<const float4*>(e.aux2 + (m_first + r) * e.lda2 + n);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = rl + 4 * (half * 4 + i);
+            if (col_ok && r < rows) {
+                const float4 acc = *reinterpret_cast<const float4*>(buf + r * 36 + 4 * (lane & 7));
+                const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+                const float xv[4] = {ax[i].x, ax[i].y, ax[i].z, ax[i].w};
+                const float yv[4] = {a2[i].x, a2[i].y, a2[i].z, a2[i].w};
+                const float bv[4] = {b.x, b.y, b.z, b.w};
+                float ov[4], o2v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float o;
+                    o2v[k] = 0.0f;
+                    if (KIND == EPI_NONE) o = av[k];
+                    else if (KIND == EPI_BIAS) o = av[k] + bv[k];
+                    else if (KIND == EPI_BIAS_SOFTPLUS) o = epi_softplus<FAST>(av[k] + bv[k]);
+                    else if (KIND == EPI_BIAS_RELU) o = fmaxf(av[k] + bv[k], 0.0f);
+                    else if (KIND == EPI_BIAS_SIGMOID) o = epi_sigmoid<FAST>(av[k] + bv[k]);
+                    else if (KIND == EPI_MUL_SIGMA) o = av[k] * epi_sigma<FAST>(xv[k]);
+                    else if (KIND == EPI_BWD_CHAIN) {
+                        const float sg = epi_sigma<FAST>(xv[k]);
+                        o = av[k] * sg;
+                        o2v[k] = av[k] * yv[k] * 100.0f * (1.0f - sg);
+                    } else if (KIND == EPI_BWD_SP) o = av[k] * epi_sigma<FAST>(xv[k]) + yv[k];
+                    else o = xv[k] > 0.0f ? av[k] : 0.0f;
+                    ov[k] = o;
+                }
+                cs.x += ov[0]; cs.y += ov[1]; cs.z += ov[2]; cs.w += ov[3];
+                *reinterpret_cast<float4*>(e.out + (m_first + r) * e.ldo + n) =
+                    make_float4(rtf32(ov[0], ro), rtf32(ov[1], ro), rtf32(ov[2], ro), rtf32(ov[3], ro));
+                if (KIND == EPI_BWD_CHAIN) {
+                    if (e.atomic2) {
+                        float* o2 = e.out2 + mrow[i] * e.ldo2 + n;
+                        atomicAdd(o2, o2v[0]); atomicAdd(o2 + 1, o2v[1]); atomicAdd(o2 + 2, o2v[2]); atomicAdd(o2 + 3, o2v[3]);
+                    } else {
+                        *reinterpret_cast<float4*>(e.out2 + (m_first + r) * e.ldo2 + n) = make_float4(o2v[0], o2v[1], o2v[2], o2v[3]);
+                    }
+                }
+            }
+        }
+    }
+    if (e.colsum) {                                    // lanes l, l+8, l+16, l+24 share the same four columns
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+        }
+        if (lane < 8 && col_ok) {
+            atomicAdd(e.colsum + n, cs.x); atomicAdd(e.colsum + n + 1, cs.y);
+            atomicAdd(e.colsum + n + 2, cs.z); atomicAdd(e.colsum + n + 3, cs.w);
+        }
+    }
+}
+
+template <bool FAST>
+__device__ __forceinline__ void epilogue_tile_vec(const Epi& e, long long m_first, int rows, int c0, int N, const float* buf, int lane) {
+    switch (e.kind) {
+        case EPI_NONE: epilogue_tile_vec_k<FAST, EPI_NONE>(e, m_first, rows, c0, N, buf, lane); break;
+        case EPI_BIAS: epilogue_tile_vec_k<FAST, EPI_BIAS>(e, m_first, rows, c0, N, buf, lane); break;
+        case EPI_BIAS_SOFTPLUS: epilogue_tile_vec_k<FAST, EPI_BIAS_SOFTPLUS>(e, m_first, rows, c0, N, buf, lane); break;
+        case EPI_BIAS_RELU: epilogue_tile_vec_k<FAST, EPI_BIAS_RELU>(e, m_first, rows, c0, N, buf, lane); break;
+        case EPI_BIAS_SIGMOID: epilogue_tile_vec_k<FAST, EPI_BIAS_SIGMOID>(e, m_first, rows, c0, N, buf, lane); break;
+        case EPI_MUL_SIGMA: epilogue_tile_vec_k<FAST, EPI_MUL_SIGMA>(e, m_first, rows, c0, N, buf, lane); break;
+        case EPI_BWD_CHAIN: epilogue_tile_vec_k<FAST, EPI_BWD_CHAIN>(e, m_first, rows, c0, N, buf, lane); break;
+        case EPI_BWD_SP: epilogue_tile_vec_k<FAST, EPI_BWD_SP>(e, m_first, rows, c0, N, buf, lane); break;
+        default: epilogue_tile_vec_k<FAST, EPI_BWD_RELU>(e, m_first, rows, c0, N, buf, lane); break;
+    }
+}
+
 int num_sms();
+bool gemm_tc_available();   // tcgen05 path usable on this device (and not disabled by HSB_DISABLE_TCGEN05)
 bool gemm_tn_tc_eligible(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K);
 int gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K, const Epi& epi,
                cudaStream_t stream);

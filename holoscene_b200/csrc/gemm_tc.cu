@@ -165,18 +165,28 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int half = ew >> 2;
         mbar_wait(tfull, 0);
         tc_fence_after();
-        float* buf = reinterpret_cast<float*>(smem) + ew * (32 * 33);   // stage ring is idle now
+        float* buf = reinterpret_cast<float*>(smem) + ew * (32 * 36);   // stage ring is idle now
         const int nchunk = (N + 31) / 32;
+        const bool vec = epi_vec_ok(epi, N);
+        const long long m_first = m0 + q * 32;
+        const long long left = M - m_first;
+        const int rows = left < 32 ? (int)left : 32;
         for (int c = half; c < nchunk; c += 2) {
             float v[32];
             tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            if (vec) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = v[j];
-            __syncwarp();
-            const int n = c * 32 + lane;
-            const long long m_first = m0 + q * 32;
-            const long long left = M - m_first;
-            if (n < N && left > 0) epilogue_rows<true>(epi, m_first, left < 32 ? (int)left : 32, n, buf + lane, 33);
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(buf + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                if (rows > 0) epilogue_tile_vec<true>(epi, m_first, rows, c * 32, N, buf, lane);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = v[j];
+                __syncwarp();
+                const int n = c * 32 + lane;
+                if (n < N && rows > 0) epilogue_rows<true>(epi, m_first, rows, n, buf + lane, 33);
+            }
             __syncwarp();
         }
     }
@@ -358,6 +368,8 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, int co
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
+
+bool gemm_tc_available() { return tc_init(); }
 
 bool gemm_tn_tc_eligible(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K) {
     if (N > 256 || N < 1 || K < 4 || (K & 3) || (lda & 3) || (ldb & 3)) return false;

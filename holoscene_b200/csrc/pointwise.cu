@@ -233,10 +233,21 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
     const long long total = N * nseed;
     const long long m0 = (long long)blockIdx.x * rows_per_cta;
     const long long m1 = min(total, m0 + rows_per_cta);
-    for (long long m = m0; m < m1; ++m) {
-        const long long s = m / N, p = m - s * N;
-        const int key = (nseed > 1 && s < K) ? (int)s : kstar[p];
-        tile[key * 256 + j] += dQ2[m * 256 + j];     // column j is private to this thread: no race
+    for (long long mb = m0; mb < m1; mb += 8) {       // 8 independent row loads in flight per thread
+        float v[8];
+        int key[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long m = mb + i;
+            v[i] = 0.0f; key[i] = 0;
+            if (m < m1) {
+                const long long s = m / N, p = m - s * N;
+                key[i] = (nseed > 1 && s < K) ? (int)s : kstar[p];
+                v[i] = dQ2[m * 256 + j];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tile[key[i] * 256 + j] += v[i];     // column j is private to this thread: no race
     }
     for (int k = 0; k < K; ++k) {
         float v = tile[k * 256 + j];

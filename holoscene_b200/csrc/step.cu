@@ -216,15 +216,18 @@ static int sdf_backward(Ctx* c, Slot& s, long long N, int nseed, bool have_chain
     const hsb_step_cfg& f = c->cfg;
     const int P = f.precise;
     const int rt = c->rtf();
+    const bool fold = (P == 0) && gemm_tc_available();   // fast mode: bias gradients = column sums taken in the producing tcgen05 epilogue
     Epi e = epi(EPI_BWD_SP, s.dA2, 256, rt); e.aux = s.H2; e.lda = 256; e.aux2 = have_chain ? s.dA2x : nullptr; e.lda2 = 256;
+    e.colsum = fold ? c->Gp(SEG_L1B) : nullptr;
     TRY(gemm_tn(s.dS, c->Kp, c->W2eT, c->Kp, N, 256, c->Kp, e, P, st));  // dh2 = ds W2
     TRY(gemm_wgrad(s.dS, c->Kp, c->Kp, s.H2, 256, 256, N, c->dW2e, 256, c->dB2e, P, st));
     e = epi(EPI_BWD_SP, s.dA1, 256, rt); e.aux = s.H1; e.lda = 256; e.aux2 = have_chain ? s.dA1x : nullptr; e.lda2 = 256;
+    e.colsum = fold ? c->Gp(SEG_L0B) : nullptr;
     TRY(gemm_tn(s.dA2, 256, c->W1eT, 256, N, 256, 256, e, P, st));       // dh1 = da2 W1
-    TRY(gemm_wgrad(s.dA2, 256, 256, s.H1, 256, 256, N, c->dW1e, 256, c->Gp(SEG_L1B), P, st));
+    TRY(gemm_wgrad(s.dA2, 256, 256, s.H1, 256, 256, N, c->dW1e, 256, fold ? nullptr : c->Gp(SEG_L1B), P, st));
     e = epi(EPI_NONE, s.dH0E, 32);
     TRY(gemm_tn(s.dA1, 256, c->W0eT + 39 * 256, 256, N, 32, 256, e, P, st));   // dE = (da1 W0)[:, 39:71]
-    TRY(gemm_wgrad(s.dA1, 256, 256, s.H0, LD_H0, LD_H0, N, c->dW0e, LD_H0, c->Gp(SEG_L0B), P, st));
+    TRY(gemm_wgrad(s.dA1, 256, 256, s.H0, LD_H0, LD_H0, N, c->dW0e, LD_H0, fold ? nullptr : c->Gp(SEG_L0B), P, st));
     TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dH0E, 32, have_chain ? s.Q0 + 39 : nullptr, LD_H0, have_chain ? s.dG : nullptr,
                                 (uint32_t)nseed, c->Gp(SEG_EMB), (uint32_t)N, f.L, f.S, f.H, st));
     return HSB_OK;
@@ -413,19 +416,20 @@ extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_r
         // render net
         TRY(launch_rgb_head_bwd(s.dO, c->R2e, s.U2, N, s.dU2, rt, st));
         TRY(gemm_wgrad(s.dO, 4, 4, s.U2, 256, 256, N, c->dR2e, 256, c->dRB2e, P, st));
-        Epi e = epi(EPI_BWD_RELU, s.dU1, 256, rt); e.aux = s.U1; e.lda = 256;
+        const bool fold = (P == 0) && gemm_tc_available();
+        Epi e = epi(EPI_BWD_RELU, s.dU1, 256, rt); e.aux = s.U1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_R0B) : nullptr;
         TRY(gemm_tn(s.dU2, 256, c->R1eT, 256, N, 256, 256, e, P, st));
         TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, c->Gp(SEG_R1B), P, st));
         e = epi(EPI_NONE, s.dRIN + 54, LD_RIN);
         TRY(gemm_tn(s.dU1, 256, c->R0eT + 54 * 256, 256, N, 27, 256, e, P, st));     // d PE4(grad)
-        e = epi(EPI_NONE, s.dFEAT, 256, rt);
+        e = epi(EPI_NONE, s.dFEAT, 256, rt); e.colsum = fold ? c->Gp(SEG_C1B) : nullptr;
         TRY(gemm_tn(s.dU1, 256, c->R0eT + 81 * 256, 256, N, 256, 256, e, P, st));    // d feature
-        TRY(gemm_wgrad(s.dU1, 256, 256, s.RIN, LD_RIN, LD_RIN, N, c->dR0e, LD_RIN, c->Gp(SEG_R0B), P, st));
+        TRY(gemm_wgrad(s.dU1, 256, 256, s.RIN, LD_RIN, LD_RIN, N, c->dR0e, LD_RIN, fold ? nullptr : c->Gp(SEG_R0B), P, st));
         // colour-feature MLP + colour hash grid
-        TRY(gemm_wgrad(s.dFEAT, 256, 256, s.C1, 256, 256, N, c->Gp(SEG_C1W), 256, c->Gp(SEG_C1B), P, st));
-        e = epi(EPI_BWD_RELU, s.dC1, 256, rt); e.aux = s.C1; e.lda = 256;
+        TRY(gemm_wgrad(s.dFEAT, 256, 256, s.C1, 256, 256, N, c->Gp(SEG_C1W), 256, fold ? nullptr : c->Gp(SEG_C1B), P, st));
+        e = epi(EPI_BWD_RELU, s.dC1, 256, rt); e.aux = s.C1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_C0B) : nullptr;
         TRY(gemm_tn(s.dFEAT, 256, c->C1T, 256, N, 256, 256, e, P, st));
-        TRY(gemm_wgrad(s.dC1, 256, 256, s.EC, 32, 32, N, c->Gp(SEG_C0W), 32, c->Gp(SEG_C0B), P, st));
+        TRY(gemm_wgrad(s.dC1, 256, 256, s.EC, 32, 32, N, c->Gp(SEG_C0W), 32, fold ? nullptr : c->Gp(SEG_C0B), P, st));
         e = epi(EPI_NONE, s.dEC, 32);
         TRY(gemm_tn(s.dC1, 256, c->C0T, 256, N, 32, 256, e, P, st));
         TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dEC, 32, nullptr, 0, nullptr, 1, c->Gp(SEG_CEMB), (uint32_t)N, f.L, f.S, f.H, st));
