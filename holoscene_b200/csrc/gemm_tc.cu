@@ -8,9 +8,10 @@
 // epilogue warps: tcgen05.ld 32 lanes x 32 columns -> per-warp transpose through the (by then idle)
 // stage buffers -> fused epilogue (bias / softplus / ReLU / sigmoid / chain terms) with fully
 // coalesced 128-byte row segments for every global read and write.
-// Two CTAs are resident per SM (2 x 97 KB smem, 2 x 256 TMEM columns) so one CTA's epilogue overlaps
-// the other's TMA + MMA main loop; warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer,
-// 2..9 = epilogue.
+// The kernel is persistent (one CTA per SM walks its 128-row tiles): the 3-stage TMA ring runs
+// continuously across tiles and the accumulator is double-buffered in TMEM (2 x 256 columns), so the
+// MMA warp computes tile i+1 while sixteen epilogue warps drain tile i.  Warp roles: 0 = TMA producer,
+// 1 = TMEM allocator + MMA issuer, 2..17 = epilogue.
 #include "common.cuh"
 #include "gemm.cuh"
 
@@ -22,13 +23,21 @@ namespace hsb {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                                  // floats = 128 bytes = one swizzle row
-constexpr int TC_STAGES = 2;
+constexpr int TC_STAGES = 3;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;              // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BK * 4;                // 32 KB (max N)
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;    // 48 KB
-constexpr int TC_THREADS = 320;
-constexpr int TC_TMEM_COLS = 256;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 256 + 1024;   // ring + barriers + alignment slack
+constexpr int TC_EPI_GROUPS = 4;                           // epilogue warps per TMEM lane quarter
+constexpr int TC_EPI_WARPS = 4 * TC_EPI_GROUPS;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;         // TMA warp + MMA warp + 16 epilogue warps
+constexpr int TC_TMEM_COLS = 512;                          // two 256-column fp32 accumulators
+constexpr int TC_PAD_BYTES = TC_EPI_WARPS * 32 * 36 * 4;   // per-warp transpose pads (72 KB)
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_PAD_BYTES + 256 + 1024;   // ring + pads + barriers + alignment slack
+// wgrad kernel (non-persistent, 2 CTAs / SM)
+constexpr int WG_STAGES = 2;
+constexpr int WG_THREADS = 320;
+constexpr int WG_TMEM_COLS = 256;
+constexpr int WG_SMEM_BYTES = WG_STAGES * TC_STAGE_BYTES + 256 + 1024;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -39,9 +48,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // bounded spin: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 28); ++it) {
         uint32_t done;
         asm volatile(
@@ -98,24 +111,243 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- persistent epilogue role ----------------------------------------------------------------------------
+// Sixteen epilogue warps; warp -> (TMEM lane quarter q = warp % 4, column group g): it drains the 32-column chunks
+// c = g, g + 4 of rows [32q, 32q + 32) of every tile of this CTA.  Per chunk: (1) the aux rows the epilogue needs
+// are requested from HBM FIRST (they do not depend on the accumulator), (2) tcgen05.ld of the 32x32 block, (3) transpose
+// through the warp's private smem pad (explicit ld/st.shared: the pad pointer is derived by integer arithmetic, so
+// the compiler would otherwise emit generic-space accesses), (4) 128-bit coalesced math + stores.  Full chunks
+// (32 valid rows, 32 valid columns -- everything but the last tile) take a branch-free path so the eight rows of a
+// lane are independent instruction streams.  After its last tcgen05.ld of a tile the warp releases the accumulator
+// buffer (tempty) so the MMA warp can start the tile after next.  Bias-gradient column sums are kept in registers
+// across all tiles of the CTA and flushed with one atomic per column per warp at the end (a per-chunk atomicAdd on
+// 256 addresses serialised in L2 and cost more than the whole contraction).
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+template <int KIND>
+__device__ __forceinline__ float4 epi_math4(const float4 acc, const float4 x4, const float4 y4, const float4 b4, float4& o2) {
+    const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+    const float xv[4] = {x4.x, x4.y, x4.z, x4.w};
+    const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
+    const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+    float ov[4], o2v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float o;
+        o2v[k] = 0.0f;
+        if (KIND == EPI_NONE) o = av[k];
+        else if (KIND == EPI_BIAS) o = av[k] + bv[k];
+        else if (KIND == EPI_BIAS_SOFTPLUS) o = epi_softplus<true>(av[k] + bv[k]);
+        else if (KIND == EPI_BIAS_RELU) o = fmaxf(av[k] + bv[k], 0.0f);
+        else if (KIND == EPI_BIAS_SIGMOID) o = epi_sigmoid<true>(av[k] + bv[k]);
+        else if (KIND == EPI_MUL_SIGMA) o = av[k] * epi_sigma<true>(xv[k]);
+        else if (KIND == EPI_BWD_CHAIN) {
+            const float sg = epi_sigma<true>(xv[k]);
+            o = av[k] * sg;
+            o2v[k] = av[k] * yv[k] * 100.0f * (1.0f - sg);
+        } else if (KIND == EPI_BWD_SP) o = av[k] * epi_sigma<true>(xv[k]) + yv[k];
+        else o = av[k] * (xv[k] > 0.0f ? 1.0f : 0.0f);          // EPI_BWD_RELU, select-free
+        ov[k] = o;
+    }
+    o2 = make_float4(o2v[0], o2v[1], o2v[2], o2v[3]);
+    return make_float4(ov[0], ov[1], ov[2], ov[3]);
+}
+
+template <int KIND, bool FULL>
+__device__ __forceinline__ void tc_epilogue_chunk(const Epi& e, uint32_t taddr, uint32_t pad, long long m_first, int rows, int c, int N,
+                                                  long long ma0, long long wrap, bool has2, bool release, uint64_t* tfull_b,
+                                                  uint32_t tfull_parity, bool& waited, uint64_t* tempty_b, int lane, float4& cs) {
+    constexpr bool AUX = (KIND == EPI_MUL_SIGMA || KIND == EPI_BWD_CHAIN || KIND == EPI_BWD_SP || KIND == EPI_BWD_RELU);
+    constexpr bool BIAS = (KIND == EPI_BIAS || KIND == EPI_BIAS_SOFTPLUS || KIND == EPI_BIAS_RELU || KIND == EPI_BIAS_SIGMOID);
+    const int rl = lane >> 3;                              // lane -> rows rl + 4 i (i = 0..7), columns n .. n + 3
+    const int cl = 4 * (lane & 7);
+    const int n = c * 32 + cl;
+    const bool col_ok = FULL || n < N;
+    const int ro = e.round_out;
+    // BWD_CHAIN carries two aux streams and two outputs: prefetching all eight aux rows as well spills; it fetches
+    // aux together with aux2, four rows at a time.
+    constexpr bool PRE = AUX && (KIND != EPI_BWD_CHAIN);
+    float4 ax[PRE ? 8 : 4];
+    if (PRE) {                                             // (1) aux prefetch, all eight rows of this lane
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = rl + 4 * i;
+            ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (FULL || (col_ok && r < rows)) {
+                long long ma = ma0 + r;
+                while (ma >= wrap) ma -= wrap;
+                ax[i] = __ldg(reinterpret_cast<const float4*>(e.aux + ma * e.lda + n));
+            }
+        }
+    }
+    if (!waited) { mbar_wait(tfull_b, tfull_parity); tc_fence_after(); waited = true; }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                          // (2) + (3): two 16-column halves keep the register peak low
+        float v[16];
+        tmem_ld16(taddr + 16 * h, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts128(pad + (uint32_t)(lane * 36 + 16 * h + 4 * j) * 4u, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    if (release) {                                         // last read of this accumulator by this warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_b);
+    }
+    __syncwarp();
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BIAS && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {                 // (4)
+        float4 a2[4];
+        int mrow[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = rl + 4 * (half * 4 + i);
+            a2[i] = make_float4(0.f, 0.f, 0.f, 0.f); mrow[i] = 0;
+            if (FULL || (col_ok && r < rows)) {
+                if (has2) a2[i] = __ldg(reinterpret_cast<const float4*>(e.aux2 + (m_first + r) * e.lda2 + n));
+                if (AUX && !PRE) {
+                    long long ma = ma0 + r;
+                    while (ma >= wrap) ma -= wrap;
+                    mrow[i] = (int)ma;
+                    ax[i] = __ldg(reinterpret_cast<const float4*>(e.aux + ma * e.lda + n));
+                }
+            } else if (AUX && !PRE) ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = rl + 4 * (half * 4 + i);
+            if (FULL || (col_ok && r < rows)) {
+                const float4 acc = lds128(pad + (uint32_t)(r * 36 + cl) * 4u);
+                float4 o2;
+                const float4 o = epi_math4<KIND>(acc, AUX ? ax[PRE ? half * 4 + i : i] : make_float4(0.f, 0.f, 0.f, 0.f), a2[i], bias4, o2);
+                cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+                *reinterpret_cast<float4*>(e.out + (m_first + r) * e.ldo + n) = make_float4(rtf32(o.x, ro), rtf32(o.y, ro), rtf32(o.z, ro), rtf32(o.w, ro));
+                if (KIND == EPI_BWD_CHAIN) {
+                    if (e.atomic2) atomicAdd(reinterpret_cast<float4*>(e.out2 + (long long)mrow[i] * e.ldo2 + n), o2);
+                    else *reinterpret_cast<float4*>(e.out2 + (m_first + r) * e.ldo2 + n) = o2;
+                }
+            }
+        }
+    }
+    __syncwarp();                                          // the pad is reused by the next chunk
+}
+
+template <int KIND>
+__device__ __forceinline__ void tc_epilogue_role(const Epi& e, long long M, int N, uint32_t tmem, uint64_t* tfull, uint64_t* tempty,
+                                                 float* buf, int q, int g, int lane, int num_tiles) {
+    constexpr bool AUX = (KIND == EPI_MUL_SIGMA || KIND == EPI_BWD_CHAIN || KIND == EPI_BWD_SP || KIND == EPI_BWD_RELU);
+    constexpr bool AUX2 = (KIND == EPI_BWD_CHAIN || KIND == EPI_BWD_SP);
+    const int nchunk = (N + 31) / 32;
+    if (g >= nchunk) return;                               // not part of tempty's arrival count (see kernel)
+    const bool vec = epi_vec_ok(e, N);
+    const bool has2 = AUX2 && (e.aux2 != nullptr);
+    const long long wrap = e.aux_rows > 0 ? e.aux_rows : (1LL << 62);
+    const uint32_t pad = smem_u32(buf);
+    float4 cs[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};     // column sums of chunks g, g + 4
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const int b = t & 1;
+        const uint32_t use = (uint32_t)t >> 1;
+        const long long m_first = (long long)tile * TC_BM + q * 32;
+        const long long left = M - m_first;
+        const int rows = left < 32 ? (left > 0 ? (int)left : 0) : 32;
+        long long ma0 = 0;
+        if (AUX) ma0 = e.aux_rows > 0 ? (m_first % e.aux_rows) : m_first;
+        bool waited = false;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = g + TC_EPI_GROUPS * j;
+            if (c >= nchunk) break;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 32);
+            const bool release = c + TC_EPI_GROUPS >= nchunk;
+            if (vec) {
+                if (rows == 32 && c * 32 + 32 <= N)
+                    tc_epilogue_chunk<KIND, true>(e, taddr, pad, m_first, rows, c, N, ma0, wrap, has2, release, tfull + b, use & 1, waited, tempty + b, lane, cs[j]);
+                else
+                    tc_epilogue_chunk<KIND, false>(e, taddr, pad, m_first, rows, c, N, ma0, wrap, has2, release, tfull + b, use & 1, waited, tempty + b, lane, cs[j]);
+            } else {                                       // misaligned / N % 4 != 0 operands: scalar column walker
+                if (!waited) { mbar_wait(tfull + b, use & 1); tc_fence_after(); waited = true; }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[16];
+                    tmem_ld16(taddr + 16 * h, v);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) buf[lane * 33 + 16 * h + k] = v[k];
+                }
+                if (release) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty + b);
+                }
+                __syncwarp();
+                const int nn = c * 32 + lane;
+                if (nn < N && rows > 0) epilogue_rows_k<true, KIND>(e, m_first, rows, nn, buf + lane, 33);
+                __syncwarp();
+            }
+        }
+    }
+    if (e.colsum && vec) {                                 // lanes l, l+8, l+16, l+24 hold the same four columns
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int n = (g + TC_EPI_GROUPS * j) * 32 + 4 * (lane & 7);
+            float v[4] = {cs[j].x, cs[j].y, cs[j].z, cs[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);
+                v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+            }
+            if (lane < 8 && n < N) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) atomicAdd(e.colsum + n + k, v[k]);
+            }
+        }
+    }
+}
+
+// Persistent: grid = min(#tiles, #SMs) CTAs, each walks the 128-row tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// The smem ring and its phases run continuously across tiles; the fp32 accumulator is double-buffered in TMEM
+// (2 x 256 columns) so the MMA warp computes tile i+1 while the epilogue warps drain tile i.
+template <int KIND>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, long long M, int N,
-                  int K, int n_mma, uint32_t idesc, Epi epi) {
+                  int K, int n_mma, uint32_t idesc, Epi epi, int num_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    float* pads = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_PAD_BYTES);
     uint64_t* empty = full + TC_STAGES;
     uint64_t* tfull = empty + TC_STAGES;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tfull + 1);
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long m0 = (long long)blockIdx.x * TC_BM;
     const int nkb = (K + TC_BK - 1) / TC_BK;
+    const int nchunk = (N + 31) / 32;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(tfull, 1);
+        const uint32_t active = 4u * (uint32_t)(nchunk < TC_EPI_GROUPS ? nchunk : TC_EPI_GROUPS);   // epilogue warps that own chunks
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, active); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -131,64 +363,53 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         // ===== TMA producer =====
         if (lane == 0) {
             const uint32_t bytes = TC_A_BYTES + (uint32_t)n_mma * TC_BK * 4;
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TC_STAGES;
-                const uint32_t ph = (kb / TC_STAGES) & 1;
-                mbar_wait(empty + s, ph ^ 1);
-                mbar_expect_tx(full + s, bytes);
-                uint8_t* st = smem + s * TC_STAGE_BYTES;
-                tma_load_2d(&mapA, full + s, st, kb * TC_BK, (int)m0);
-                tma_load_2d(&mapB, full + s, st + TC_A_BYTES, kb * TC_BK, 0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = tile * TC_BM;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    mbar_wait(empty + s, ph ^ 1);
+                    mbar_expect_tx(full + s, bytes);
+                    uint8_t* st = smem + s * TC_STAGE_BYTES;
+                    tma_load_2d(&mapA, full + s, st, kb * TC_BK, m0);
+                    tma_load_2d(&mapB, full + s, st + TC_A_BYTES, kb * TC_BK, 0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TC_STAGES;
-                const uint32_t ph = (kb / TC_STAGES) & 1;
-                mbar_wait(full + s, ph);
+            uint32_t it = 0;
+            int t = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+                const int b = t & 1;
+                const uint32_t use = (uint32_t)t >> 1;
+                mbar_wait(tempty + b, (use & 1) ^ 1);          // epilogue has drained this accumulator (free on first use)
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(smem + s * TC_STAGE_BYTES);
-                const uint64_t ad = smem_desc_k_sw128(a0), bd = smem_desc_k_sw128(a0 + TC_A_BYTES);
+                const uint32_t acc = tmem + (uint32_t)(b * 256);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % TC_STAGES;
+                    const uint32_t ph = (it / TC_STAGES) & 1;
+                    mbar_wait(full + s, ph);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(smem + s * TC_STAGE_BYTES);
+                    const uint64_t ad = smem_desc_k_sw128(a0), bd = smem_desc_k_sw128(a0 + TC_A_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k)          // 8 tf32 = 32 bytes = +2 in the (addr >> 4) field
-                    umma_tf32(tmem, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-                umma_commit(empty + s);                       // smem slot free once these MMAs retire
+                    for (int k = 0; k < TC_BK / 8; ++k)          // 8 tf32 = 32 bytes = +2 in the (addr >> 4) field
+                        umma_tf32(acc, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                    umma_commit(empty + s);                       // smem slot free once these MMAs retire
+                }
+                umma_commit(tfull + b);                           // accumulator complete
             }
-            umma_commit(tfull);                               // accumulator complete
         }
     } else {
-        // ===== epilogue: 8 warps, TMEM lane quarter = warp % 4, column chunks interleaved between the two warps of a quarter =====
+        // ===== epilogue: 16 warps =====
         const int ew = warp - 2;
-        const int q = warp & 3;
-        const int half = ew >> 2;
-        mbar_wait(tfull, 0);
-        tc_fence_after();
-        float* buf = reinterpret_cast<float*>(smem) + ew * (32 * 36);   // stage ring is idle now
-        const int nchunk = (N + 31) / 32;
-        const bool vec = epi_vec_ok(epi, N);
-        const long long m_first = m0 + q * 32;
-        const long long left = M - m_first;
-        const int rows = left < 32 ? (int)left : 32;
-        for (int c = half; c < nchunk; c += 2) {
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            if (vec) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(buf + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                __syncwarp();
-                if (rows > 0) epilogue_tile_vec<true>(epi, m_first, rows, c * 32, N, buf, lane);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) buf[lane * 33 + j] = v[j];
-                __syncwarp();
-                const int n = c * 32 + lane;
-                if (n < N && rows > 0) epilogue_rows<true>(epi, m_first, rows, n, buf + lane, 33);
-            }
-            __syncwarp();
-        }
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int g = ew >> 2;
+        float* buf = pads + ew * (32 * 36);
+        tc_epilogue_role<KIND>(epi, M, N, tmem, tfull, tempty, buf, q, g, lane, num_tiles);
     }
     tc_fence_before();
     __syncthreads();
@@ -224,15 +445,15 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
     return d;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(WG_THREADS, 2)
 gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, long long M, int N1,
                      int N2, int n2_tile, int n_mma, uint32_t idesc, long long rows_per_split, float* __restrict__ C,
                      long long ldc) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* empty = full + TC_STAGES;
-    uint64_t* tfull = empty + TC_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_STAGES * TC_STAGE_BYTES);
+    uint64_t* empty = full + WG_STAGES;
+    uint64_t* tfull = empty + WG_STAGES;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tfull + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int a0 = blockIdx.y * 128;                 // first column of A (row of C) of this CTA
@@ -246,12 +467,12 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(WG_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -264,8 +485,8 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             if (lane == 0) {
                 const uint32_t bytes = (uint32_t)(a_boxes + b_boxes) * WG_BOX_BYTES;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    const int s = kb % TC_STAGES;
-                    const uint32_t ph = (kb / TC_STAGES) & 1;
+                    const int s = kb % WG_STAGES;
+                    const uint32_t ph = (kb / WG_STAGES) & 1;
                     mbar_wait(empty + s, ph ^ 1);
                     mbar_expect_tx(full + s, bytes);
                     uint8_t* st = smem + s * TC_STAGE_BYTES;
@@ -278,8 +499,8 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         } else if (warp == 1) {
             if (lane == 0) {
                 for (int kb = 0; kb < nkb; ++kb) {
-                    const int s = kb % TC_STAGES;
-                    const uint32_t ph = (kb / TC_STAGES) & 1;
+                    const int s = kb % WG_STAGES;
+                    const uint32_t ph = (kb / WG_STAGES) & 1;
                     mbar_wait(full + s, ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * TC_STAGE_BYTES);
@@ -319,7 +540,7 @@ gemm_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(WG_TMEM_COLS) : "memory");
     }
 }
 
@@ -330,6 +551,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static bool g_tc_checked = false, g_tc_ok = false;
 static std::mutex g_tc_mu;
+
+template <int KIND> static bool tn_set_smem() {
+    return cudaFuncSetAttribute(gemm_tn_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) == cudaSuccess;
+}
+template <int KIND>
+static void tn_launch(unsigned grid, cudaStream_t stream, const CUtensorMap& mapA, const CUtensorMap& mapB, long long M, int N, int K,
+                      int n_mma, uint32_t idesc, const Epi& epi, int num_tiles) {
+    gemm_tn_tc_kernel<KIND><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles);
+}
 
 static bool tc_init() {
     std::lock_guard<std::mutex> lk(g_tc_mu);
@@ -348,8 +578,10 @@ static bool tc_init() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     if (major != 10) return false;
-    if (cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess) {
+    if (!tn_set_smem<EPI_NONE>() || !tn_set_smem<EPI_BIAS>() || !tn_set_smem<EPI_BIAS_SOFTPLUS>() || !tn_set_smem<EPI_BIAS_RELU>() ||
+        !tn_set_smem<EPI_BIAS_SIGMOID>() || !tn_set_smem<EPI_MUL_SIGMA>() || !tn_set_smem<EPI_BWD_CHAIN>() || !tn_set_smem<EPI_BWD_SP>() ||
+        !tn_set_smem<EPI_BWD_RELU>() ||
+        cudaFuncSetAttribute(gemm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
@@ -388,8 +620,20 @@ int gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, lon
     }
     // instruction descriptor: D = f32 (bits 4-5 = 1), A = B = tf32 (bits 7-9, 10-12 = 2), K-major both, N>>3 at 17, M>>4 at 24
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    const unsigned grid = (unsigned)((M + TC_BM - 1) / TC_BM);
-    gemm_tn_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mapA, mapB, M, N, K, n_mma, idesc, epi);
+    const int num_tiles = (int)((M + TC_BM - 1) / TC_BM);
+    const unsigned grid = (unsigned)(num_tiles < num_sms() ? num_tiles : num_sms());
+    switch (epi.kind) {
+        case EPI_NONE: tn_launch<EPI_NONE>(grid, stream, mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles); break;
+        case EPI_BIAS: tn_launch<EPI_BIAS>(grid, stream, mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles); break;
+        case EPI_BIAS_SOFTPLUS: tn_launch<EPI_BIAS_SOFTPLUS>(grid, stream, mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles); break;
+        case EPI_BIAS_RELU: tn_launch<EPI_BIAS_RELU>(grid, stream, mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles); break;
+        case EPI_BIAS_SIGMOID: tn_launch<EPI_BIAS_SIGMOID>(grid, stream, mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles); break;
+        case EPI_MUL_SIGMA: tn_launch<EPI_MUL_SIGMA>(grid, stream, mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles); break;
+        case EPI_BWD_CHAIN: tn_launch<EPI_BWD_CHAIN>(grid, stream, mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles); break;
+        case EPI_BWD_SP: tn_launch<EPI_BWD_SP>(grid, stream, mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles); break;
+        case EPI_BWD_RELU: tn_launch<EPI_BWD_RELU>(grid, stream, mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles); break;
+        default: set_error("gemm_tn_tc: unknown epilogue kind"); return HSB_ERR_ARG;
+    }
     return check_launch("gemm_tn_tc");
 }
 
@@ -426,7 +670,7 @@ int gemm_wgrad_tc(const float* A, long long lda, int N1, const float* B, long lo
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n_mma >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
     dim3 grid((unsigned)n2_tiles, (unsigned)n1_tiles, (unsigned)splits);
-    gemm_wgrad_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mapA, mapB, M, N1, N2, n2_tile, n_mma, idesc, rps, C, ldc);
+    gemm_wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, stream>>>(mapA, mapB, M, N1, N2, n2_tile, n_mma, idesc, rps, C, ldc);
     return check_launch("gemm_wgrad_tc");
 }
 

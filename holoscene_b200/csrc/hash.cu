@@ -135,6 +135,83 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const float* __restrict__
     }
 }
 
+// Row-major variant used inside the train step: all 16 levels of a point are contiguous in the destination row (MLP input
+// row H0[:, 39:71] or the colour row EC[:, 0:32]).  A CTA owns 64 points; warp w evaluates levels 2w and 2w+1 for them (lanes =
+// consecutive samples of a ray: same locality of the gathers as the level-major kernel) into shared tiles, then the CTA writes
+// the 64 x 32 features and the 64 x 96 dy_dx block with fully coalesced rows.  The level-major kernel writes 8 bytes into 32
+// different rows per store instruction (4 sectors touched per 32 bytes kept).
+constexpr int HR_PTS = 64;
+__global__ void __launch_bounds__(256) hash_fwd_rows_kernel(const float* __restrict__ x, const float2* __restrict__ table,
+                                                            const int* __restrict__ offsets, float* __restrict__ out,
+                                                            long long out_ps, float* __restrict__ dy_dx, long long dy_ps,
+                                                            uint32_t B, float S, uint32_t H, int map01, int rtf) {
+    __shared__ float F[HR_PTS][33];
+    __shared__ float D[HR_PTS][97];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t p0 = blockIdx.x * HR_PTS;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int lp = (it & 1) * 32 + lane;
+        const uint32_t level = (uint32_t)(warp * 2 + (it >> 1));
+        const uint32_t p = p0 + lp;
+        float2 r = make_float2(0.f, 0.f);
+        float2 a[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        if (p < B) {
+            float xa, xb, xc;
+            load_xyz(x, p, map01, xa, xb, xc);
+            Cell c;
+            locate(xa, xb, xc, offsets, level, S, H, c);
+            if (!c.oob) {
+                const float2* tab = table + (uint32_t)offsets[level];
+                float2 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __ldg(tab + c.row[i]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float w = corner_w(c, i);
+                    r.x += w * v[i].x;
+                    r.y += w * v[i].y;
+                }
+                if (dy_dx) {
+#pragma unroll
+                    for (int gd = 0; gd < 3; ++gd) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int d0 = (gd == 0) ? 1 : 0, d1 = (gd == 2) ? 1 : 2;
+                            const int b0 = j & 1, b1 = (j >> 1) & 1;
+                            float w = c.scale;
+                            w *= b0 ? c.w[d0] : 1.0f - c.w[d0];
+                            w *= b1 ? c.w[d1] : 1.0f - c.w[d1];
+                            const int left = (b0 << d0) | (b1 << d1), right = left | (1 << gd);
+                            a[gd].x += w * (v[right].x - v[left].x) * c.dw[gd];
+                            a[gd].y += w * (v[right].y - v[left].y) * c.dw[gd];
+                        }
+                    }
+                }
+            }
+        }
+        F[lp][2 * level] = rtf32(r.x, rtf);
+        F[lp][2 * level + 1] = rtf32(r.y, rtf);
+        if (dy_dx) {
+#pragma unroll
+            for (int gd = 0; gd < 3; ++gd) { D[lp][level * 6 + 2 * gd] = a[gd].x; D[lp][level * 6 + 2 * gd + 1] = a[gd].y; }
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < HR_PTS * 32; idx += 256) {
+        const int row = idx >> 5, col = idx & 31;
+        if (p0 + row < B) out[(long long)(p0 + row) * out_ps + col] = F[row][col];
+    }
+    if (dy_dx) {
+        for (int idx = threadIdx.x; idx < HR_PTS * 24; idx += 256) {
+            const int row = idx / 24, c4 = idx - row * 24;
+            if (p0 + row < B)
+                *reinterpret_cast<float4*>(dy_dx + (long long)(p0 + row) * dy_ps + 4 * c4) =
+                    make_float4(D[row][4 * c4], D[row][4 * c4 + 1], D[row][4 * c4 + 2], D[row][4 * c4 + 3]);
+        }
+    }
+}
+
 // Scatter of one corner contribution per lane with warp-level pre-reduction.  Consecutive lanes are consecutive
 // samples of a ray, and the error-bound sampler packs most samples of a ray into a thin shell around the surface,
 // so at every level long runs of lanes hit the SAME table row; same-address atomics serialise in the L2 slice and
@@ -314,6 +391,13 @@ int hsb::hash_forward_ex(const float* inputs, const float* embeddings, const int
                          uint32_t B, uint32_t L, float S, uint32_t H, int map01, int rtf, cudaStream_t stream) {
     if (B == 0) return HSB_OK;
     if (!inputs || !embeddings || !offsets || !outputs || L == 0 || L > 32) { set_error("hsb_hash_forward: bad argument"); return HSB_ERR_ARG; }
+    const bool rows_ok = L == 16 && out_level_stride == 2 &&
+                         (!dy_dx || ((dy_point_stride & 3) == 0 && (((uintptr_t)dy_dx) & 15) == 0 && dy_point_stride >= 96));
+    if (rows_ok) {
+        hash_fwd_rows_kernel<<<cdiv(B, HR_PTS), 256, 0, stream>>>(inputs, reinterpret_cast<const float2*>(embeddings), offsets, outputs,
+                                                                  out_point_stride, dy_dx, dy_point_stride, B, S, H, map01, rtf);
+        return check_launch("hsb_hash_forward");
+    }
     dim3 grid(cdiv(B, 256), L);
     hash_fwd_kernel<<<grid, 256, 0, stream>>>(inputs, reinterpret_cast<const float2*>(embeddings), offsets, outputs,
                                               out_level_stride, out_point_stride, dy_dx, dy_point_stride, B, L, S, H, map01, rtf);

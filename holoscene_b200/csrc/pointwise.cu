@@ -22,28 +22,58 @@ __device__ __forceinline__ void pe_write(float* __restrict__ dst, float x, float
     }
 }
 
+// One PE element: column j of [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...] (three coordinates per group).
+__device__ __forceinline__ float pe_elem(int j, float x, float y, float z, int ncol) {
+    if (j >= ncol) return 0.0f;
+    if (j < 3) return j == 0 ? x : (j == 1 ? y : z);
+    const int i = (j - 3) / 6, w = (j - 3) - 6 * i;
+    const int d = w >= 3 ? w - 3 : w;
+    const float v = (d == 0 ? x : (d == 1 ? y : z)) * (float)(1 << i);
+    return w >= 3 ? cosf(v) : sinf(v);
+}
+
 // points of a ray batch: x = o + z d;  H0[:, 0:39] = PE6(x), H0[:,71] = 0;
 // RIN[:, 0:27] = PE4(x), RIN[:, 27:54] = PE4(d), RIN[:, 337:344] = 0   (RIN may be null: SDF-only use)
+// One thread per (point, 16-byte output slot): consecutive threads write consecutive float4s of a row, so every store
+// instruction covers whole sectors (the per-point scalar walk wrote 4 bytes into 32 different rows per instruction and
+// ran at 0.35 TB/s).  Slots: 0..9 = H0 columns 0..39, 10 = H0 columns 68..71, 11..24 = RIN columns 0..55, 25..26 = RIN columns
+// 336..343, 27 = X.  Columns this kernel zero-fills inside those slots but does not own (H0 39, 68..70: hash features; RIN 54, 55:
+// PE4(g); RIN 336: feature) are written by later kernels of the same pass.
 __global__ void __launch_bounds__(256) ray_points_kernel(const float* __restrict__ o, const float* __restrict__ d,
                                                          const float* __restrict__ z, int R, int S, float* __restrict__ X,
                                                          float* __restrict__ H0, float* __restrict__ RIN, int rtf) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nslot = RIN ? 28 : 12;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p = t / nslot;
     if (p >= (long long)R * S) return;
+    int slot = (int)(t - p * nslot);
+    if (!RIN && slot == 11) slot = 27;
     const int r = (int)(p / S);
     const float zz = z[p];
     const float dx = d[r * 3 + 0], dy = d[r * 3 + 1], dz = d[r * 3 + 2];
     const float x = o[r * 3 + 0] + zz * dx, y = o[r * 3 + 1] + zz * dy, w = o[r * 3 + 2] + zz * dz;
-    X[p * 3 + 0] = x; X[p * 3 + 1] = y; X[p * 3 + 2] = w;
-    float* h = H0 + p * LD_H0;
-    pe_write(h, x, y, w, 6, rtf);
-    h[71] = 0.0f;
-    if (RIN) {
-        float* q = RIN + p * LD_RIN;
-        pe_write(q, x, y, w, 4, rtf);
-        pe_write(q + 27, dx, dy, dz, 4, rtf);
+    if (slot == 27) { X[p * 3 + 0] = x; X[p * 3 + 1] = y; X[p * 3 + 2] = w; return; }
+    float4 v;
+    float* dst;
+    if (slot < 10) {
+        const int j = 4 * slot;
+        v = make_float4(pe_elem(j, x, y, w, 39), pe_elem(j + 1, x, y, w, 39), pe_elem(j + 2, x, y, w, 39), pe_elem(j + 3, x, y, w, 39));
+        dst = H0 + p * LD_H0 + j;
+    } else if (slot == 10) {
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        dst = H0 + p * LD_H0 + 68;
+    } else if (slot < 25) {
+        const int j = 4 * (slot - 11);
+        float e[4];
 #pragma unroll
-        for (int i = 337; i < LD_RIN; ++i) q[i] = 0.0f;
+        for (int k = 0; k < 4; ++k) e[k] = (j + k < 27) ? pe_elem(j + k, x, y, w, 27) : pe_elem(j + k - 27, dx, dy, dz, 27);
+        v = make_float4(e[0], e[1], e[2], e[3]);
+        dst = RIN + p * LD_RIN + j;
+    } else {
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        dst = RIN + p * LD_RIN + 336 + 4 * (slot - 25);
     }
+    *reinterpret_cast<float4*>(dst) = make_float4(rtf32(v.x, rtf), rtf32(v.y, rtf), rtf32(v.z, rtf), rtf32(v.w, rtf));
 }
 
 // explicit points (eikonal samples): H0[:, 0:39] = PE6(x), H0[:, 71] = 0
@@ -55,19 +85,24 @@ __global__ void __launch_bounds__(256) points_pe_kernel(const float* __restrict_
     h[71] = 0.0f;
 }
 
-// min over the K object channels, first index on ties (== -maxpool1d(-s)); channel >= 0 selects one channel
+// min over the K object channels, first index on ties (== -maxpool1d(-s)); channel >= 0 selects one channel.
+// Rows are Kp = 8 n floats, 16-byte aligned: read as float4.
 __global__ void __launch_bounds__(256) sdf_min_kernel(const float* __restrict__ SR, long long N, int K, int Kp, int channel,
                                                       float* __restrict__ sdf, int* __restrict__ kstar) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     const float* s = SR + p * Kp;
     int best = 0;
-    float v = s[0];
+    float v;
     if (channel >= 0) { best = channel; v = s[channel]; }
     else {
-        for (int k = 1; k < K; ++k) {
-            float t = s[k];
-            if (t < v) { v = t; best = k; }
+        v = 3.0e38f;
+        for (int k4 = 0; k4 < Kp; k4 += 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(s + k4));
+            const float e[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (k4 + u < K && (e[u] < v || (k4 + u) == 0)) { v = e[u]; best = k4 + u; }
         }
     }
     sdf[p] = v;
@@ -93,32 +128,56 @@ __global__ void __launch_bounds__(256) chain_seed_kernel(const float* __restrict
     reinterpret_cast<float4*>(P2 + ((long long)s * N + p) * 256)[j] = r;
 }
 
+// One thread per row; rows are 16-byte aligned (LD_H0 = 72, DY rows = 96 floats), so a row is moved as float4s: 4x fewer
+// load/store instructions than the scalar walk (these kernels are LSU-issue bound, not HBM bound).
+__device__ __forceinline__ void load_row72(const float* __restrict__ src, float (&r)[72]) {
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+    }
+}
+
 // end of the chain: g = (dh0/dx)^T q0.  rows m = s*N + p.  Optionally writes PE4(g) into RIN[:, 54:81].
-__global__ void __launch_bounds__(256) chain_end_kernel(const float* __restrict__ Q0, const float* __restrict__ H0,
+__global__ void __launch_bounds__(128) chain_end_kernel(const float* __restrict__ Q0, const float* __restrict__ H0,
                                                         const float* __restrict__ DY, long long N, int nseed,
                                                         float* __restrict__ G, float* __restrict__ RIN, int rtf) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= N * nseed) return;
     const long long p = m % N;
-    const float* q = Q0 + m * LD_H0;
-    const float* h = H0 + p * LD_H0;
-    const float* dy = DY + p * 96;
+    float q[72];
+    load_row72(Q0 + m * LD_H0, q);
     float g[3] = {q[0], q[1], q[2]};
-    float f = 1.0f;
+    {
+        float h[40];                                       // PE part of the H0 row: columns 0..39
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            float sn = h[3 + 6 * i + d], cs = h[3 + 6 * i + 3 + d];
-            g[d] += f * (cs * q[3 + 6 * i + d] - sn * q[3 + 6 * i + 3 + d]);
+        for (int i = 0; i < 10; ++i) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(H0 + p * LD_H0) + i);
+            h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
         }
-        f *= 2.0f;
+        float f = 1.0f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float sn = h[3 + 6 * i + d], cs = h[3 + 6 * i + 3 + d];
+                g[d] += f * (cs * q[3 + 6 * i + d] - sn * q[3 + 6 * i + 3 + d]);
+            }
+            f *= 2.0f;
+        }
     }
     float e[3] = {0.f, 0.f, 0.f};
-    for (int l = 0; l < 16; ++l) {
-        const float q0 = q[39 + 2 * l], q1 = q[40 + 2 * l];
+    const float4* dy4 = reinterpret_cast<const float4*>(DY + p * 96);
 #pragma unroll
-        for (int d = 0; d < 3; ++d) e[d] += dy[l * 6 + d * 2] * q0 + dy[l * 6 + d * 2 + 1] * q1;
+    for (int l2 = 0; l2 < 8; ++l2) {                       // two levels = 12 floats = three float4
+        const float4 a = __ldg(dy4 + 3 * l2), b = __ldg(dy4 + 3 * l2 + 1), c = __ldg(dy4 + 3 * l2 + 2);
+        const float dy[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const float q0 = q[39 + 2 * (2 * l2 + u)], q1 = q[40 + 2 * (2 * l2 + u)];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) e[d] += dy[u * 6 + d * 2] * q0 + dy[u * 6 + d * 2 + 1] * q1;
+        }
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d) g[d] += 0.5f * e[d];
@@ -129,7 +188,7 @@ __global__ void __launch_bounds__(256) chain_end_kernel(const float* __restrict_
 // backward of chain_end: dQ0 = (dh0/dx) dG, where for the main pass
 //   dG = dGn (normal-map term) + PE4(g)^T dRIN[:, 54:81]        (RIN holds sin/cos of g)
 // The total dG is written back to dGn (it feeds the second-order hash scatter).
-__global__ void __launch_bounds__(256) chain_end_bwd_kernel(float* __restrict__ dG, const float* __restrict__ dRIN,
+__global__ void __launch_bounds__(128) chain_end_bwd_kernel(float* __restrict__ dG, const float* __restrict__ dRIN,
                                                             const float* __restrict__ RIN, const float* __restrict__ H0,
                                                             const float* __restrict__ DY, long long N, int nseed,
                                                             float* __restrict__ dQ0, int rtf) {
@@ -138,7 +197,7 @@ __global__ void __launch_bounds__(256) chain_end_bwd_kernel(float* __restrict__ 
     const long long p = m % N;
     float dg[3] = {dG[m * 3 + 0], dG[m * 3 + 1], dG[m * 3 + 2]};
     if (dRIN) {
-        const float* dr = dRIN + p * LD_RIN + 54;
+        const float* dr = dRIN + p * LD_RIN + 54;          // 216 B into the row: only 8-byte aligned
         const float* r = RIN + p * LD_RIN + 54;
         float f = 1.0f;
 #pragma unroll
@@ -154,29 +213,46 @@ __global__ void __launch_bounds__(256) chain_end_bwd_kernel(float* __restrict__ 
         }
         dG[m * 3 + 0] = dg[0]; dG[m * 3 + 1] = dg[1]; dG[m * 3 + 2] = dg[2];
     }
-    const float* h = H0 + p * LD_H0;
-    const float* dy = DY + p * 96;
-    float* q = dQ0 + m * LD_H0;
-    q[0] = rtf32(dg[0], rtf); q[1] = rtf32(dg[1], rtf); q[2] = rtf32(dg[2], rtf);
-    float f = 1.0f;
+    float q[72];
+    q[0] = dg[0]; q[1] = dg[1]; q[2] = dg[2];
+    {
+        float h[40];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            float sn = h[3 + 6 * i + d], cs = h[3 + 6 * i + 3 + d];
-            q[3 + 6 * i + d] = rtf32(f * cs * dg[d], rtf);
-            q[3 + 6 * i + 3 + d] = rtf32(-f * sn * dg[d], rtf);
+        for (int i = 0; i < 10; ++i) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(H0 + p * LD_H0) + i);
+            h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
         }
-        f *= 2.0f;
-    }
-    for (int l = 0; l < 16; ++l) {
-        float a = 0.f, b = 0.f;
+        float f = 1.0f;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) { a += dy[l * 6 + d * 2] * dg[d]; b += dy[l * 6 + d * 2 + 1] * dg[d]; }
-        q[39 + 2 * l] = rtf32(0.5f * a, rtf);
-        q[40 + 2 * l] = rtf32(0.5f * b, rtf);
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float sn = h[3 + 6 * i + d], cs = h[3 + 6 * i + 3 + d];
+                q[3 + 6 * i + d] = f * cs * dg[d];
+                q[3 + 6 * i + 3 + d] = -f * sn * dg[d];
+            }
+            f *= 2.0f;
+        }
+    }
+    const float4* dy4 = reinterpret_cast<const float4*>(DY + p * 96);
+#pragma unroll
+    for (int l2 = 0; l2 < 8; ++l2) {
+        const float4 a4 = __ldg(dy4 + 3 * l2), b4 = __ldg(dy4 + 3 * l2 + 1), c4 = __ldg(dy4 + 3 * l2 + 2);
+        const float dy[12] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w, c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { a += dy[u * 6 + d * 2] * dg[d]; b += dy[u * 6 + d * 2 + 1] * dg[d]; }
+            q[39 + 2 * (2 * l2 + u)] = 0.5f * a;
+            q[40 + 2 * (2 * l2 + u)] = 0.5f * b;
+        }
     }
     q[71] = 0.0f;
+    float4* out = reinterpret_cast<float4*>(dQ0 + m * LD_H0);
+#pragma unroll
+    for (int i = 0; i < 18; ++i)
+        out[i] = make_float4(rtf32(q[4 * i], rtf), rtf32(q[4 * i + 1], rtf), rtf32(q[4 * i + 2], rtf), rtf32(q[4 * i + 3], rtf));
 }
 
 // colour head: RGB[p, 0:3] = sigmoid(U2[p,:] . R2e[c,:] + b[c]),  RGB[p,3] = 0.   One warp per point.
@@ -268,7 +344,7 @@ int launch_ray_points(const float* o, const float* d, const float* z, int R, int
                       cudaStream_t st) {
     long long P = (long long)R * S;
     if (P == 0) return HSB_OK;
-    ray_points_kernel<<<cdiv(P, 256), 256, 0, st>>>(o, d, z, R, S, X, H0, RIN, rtf);
+    ray_points_kernel<<<cdiv(P * (RIN ? 28 : 12), 256), 256, 0, st>>>(o, d, z, R, S, X, H0, RIN, rtf);
     return check_launch("ray_points");
 }
 int launch_points_pe(const float* X, long long N, float* H0, int rtf, cudaStream_t st) {
@@ -291,13 +367,13 @@ int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long 
 int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN, int rtf,
                      cudaStream_t st) {
     if (N == 0) return HSB_OK;
-    chain_end_kernel<<<cdiv(N * nseed, 256), 256, 0, st>>>(Q0, H0, DY, N, nseed, G, RIN, rtf);
+    chain_end_kernel<<<cdiv(N * nseed, 128), 128, 0, st>>>(Q0, H0, DY, N, nseed, G, RIN, rtf);
     return check_launch("chain_end");
 }
 int launch_chain_end_bwd(float* dG, const float* dRIN, const float* RIN, const float* H0, const float* DY, long long N,
                          int nseed, float* dQ0, int rtf, cudaStream_t st) {
     if (N == 0) return HSB_OK;
-    chain_end_bwd_kernel<<<cdiv(N * nseed, 256), 256, 0, st>>>(dG, dRIN, RIN, H0, DY, N, nseed, dQ0, rtf);
+    chain_end_bwd_kernel<<<cdiv(N * nseed, 128), 128, 0, st>>>(dG, dRIN, RIN, H0, DY, N, nseed, dQ0, rtf);
     return check_launch("chain_end_bwd");
 }
 int launch_rgb_head(const float* U2, const float* R2e, const float* bias, long long N, float* RGB, cudaStream_t st) {
