@@ -22,58 +22,66 @@ __device__ __forceinline__ void pe_write(float* __restrict__ dst, float x, float
     }
 }
 
-// One PE element: column j of [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...] (three coordinates per group).
-__device__ __forceinline__ float pe_elem(int j, float x, float y, float z, int ncol) {
-    if (j >= ncol) return 0.0f;
-    if (j < 3) return j == 0 ? x : (j == 1 ? y : z);
-    const int i = (j - 3) / 6, w = (j - 3) - 6 * i;
-    const int d = w >= 3 ? w - 3 : w;
-    const float v = (d == 0 ? x : (d == 1 ? y : z)) * (float)(1 << i);
-    return w >= 3 ? cosf(v) : sinf(v);
-}
-
 // points of a ray batch: x = o + z d;  H0[:, 0:39] = PE6(x), H0[:,71] = 0;
 // RIN[:, 0:27] = PE4(x), RIN[:, 27:54] = PE4(d), RIN[:, 337:344] = 0   (RIN may be null: SDF-only use)
-// One thread per (point, 16-byte output slot): consecutive threads write consecutive float4s of a row, so every store
-// instruction covers whole sectors (the per-point scalar walk wrote 4 bytes into 32 different rows per instruction and
-// ran at 0.35 TB/s).  Slots: 0..9 = H0 columns 0..39, 10 = H0 columns 68..71, 11..24 = RIN columns 0..55, 25..26 = RIN columns
-// 336..343, 27 = X.  Columns this kernel zero-fills inside those slots but does not own (H0 39, 68..70: hash features; RIN 54, 55:
-// PE4(g); RIN 336: feature) are written by later kernels of the same pass.
-__global__ void __launch_bounds__(256) ray_points_kernel(const float* __restrict__ o, const float* __restrict__ d,
-                                                         const float* __restrict__ z, int R, int S, float* __restrict__ X,
-                                                         float* __restrict__ H0, float* __restrict__ RIN, int rtf) {
-    const int nslot = RIN ? 28 : 12;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long p = t / nslot;
-    if (p >= (long long)R * S) return;
-    int slot = (int)(t - p * nslot);
-    if (!RIN && slot == 11) slot = 27;
-    const int r = (int)(p / S);
-    const float zz = z[p];
-    const float dx = d[r * 3 + 0], dy = d[r * 3 + 1], dz = d[r * 3 + 2];
-    const float x = o[r * 3 + 0] + zz * dx, y = o[r * 3 + 1] + zz * dy, w = o[r * 3 + 2] + zz * dz;
-    if (slot == 27) { X[p * 3 + 0] = x; X[p * 3 + 1] = y; X[p * 3 + 2] = w; return; }
-    float4 v;
-    float* dst;
-    if (slot < 10) {
-        const int j = 4 * slot;
-        v = make_float4(pe_elem(j, x, y, w, 39), pe_elem(j + 1, x, y, w, 39), pe_elem(j + 2, x, y, w, 39), pe_elem(j + 3, x, y, w, 39));
-        dst = H0 + p * LD_H0 + j;
-    } else if (slot == 10) {
-        v = make_float4(0.f, 0.f, 0.f, 0.f);
-        dst = H0 + p * LD_H0 + 68;
-    } else if (slot < 25) {
-        const int j = 4 * (slot - 11);
-        float e[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) e[k] = (j + k < 27) ? pe_elem(j + k, x, y, w, 27) : pe_elem(j + k - 27, dx, dy, dz, 27);
-        v = make_float4(e[0], e[1], e[2], e[3]);
-        dst = RIN + p * LD_RIN + j;
-    } else {
-        v = make_float4(0.f, 0.f, 0.f, 0.f);
-        dst = RIN + p * LD_RIN + 336 + 4 * (slot - 25);
+// A CTA owns 128 points.  Phase 1: thread = point, 18 (+12) sincosf into a shared tile (PE4(x) is the first 27 columns of
+// PE6(x)).  Phase 2: thread = (point, 16-byte slot); consecutive threads write consecutive float4s of a row, so every store
+// instruction covers whole sectors (a per-point scalar walk writes 4 bytes into 32 different rows per instruction).
+// Slots: 0..9 = H0 columns 0..39, 10 = H0 columns 68..71, 11..24 = RIN columns 0..55, 25..26 = RIN columns 336..343.  Columns
+// zero-filled inside those slots but not owned here (H0 39, 68..70: hash features; RIN 54, 55: PE4(g); RIN 336: feature) are
+// written by later kernels of the same pass.
+constexpr int RP_PTS = 128;
+__global__ void __launch_bounds__(RP_PTS) ray_points_kernel(const float* __restrict__ o, const float* __restrict__ d,
+                                                            const float* __restrict__ z, int R, int S, float* __restrict__ X,
+                                                            float* __restrict__ H0, float* __restrict__ RIN, int rtf) {
+    __shared__ __align__(16) float sx[RP_PTS][40];      // PE6(x), column 39 = 0
+    __shared__ __align__(16) float sd[RP_PTS][28];      // PE4(d), column 27 = 0
+    const int P = R * S;
+    const int p0 = blockIdx.x * RP_PTS;
+    {
+        const int p = p0 + threadIdx.x;
+        if (p < P) {
+            const int r = p / S;
+            const float zz = z[p];
+            const float dx = d[r * 3 + 0], dy = d[r * 3 + 1], dz = d[r * 3 + 2];
+            const float x = o[r * 3 + 0] + zz * dx, y = o[r * 3 + 1] + zz * dy, w = o[r * 3 + 2] + zz * dz;
+            X[p * 3 + 0] = x; X[p * 3 + 1] = y; X[p * 3 + 2] = w;
+            pe_write(sx[threadIdx.x], x, y, w, 6, rtf);
+            sx[threadIdx.x][39] = 0.0f;
+            if (RIN) {
+                pe_write(sd[threadIdx.x], dx, dy, dz, 4, rtf);
+                sd[threadIdx.x][27] = 0.0f;
+            }
+        }
     }
-    *reinterpret_cast<float4*>(dst) = make_float4(rtf32(v.x, rtf), rtf32(v.y, rtf), rtf32(v.z, rtf), rtf32(v.w, rtf));
+    __syncthreads();
+    const int nslot = RIN ? 27 : 11;
+    const int npts = min(RP_PTS, P - p0);
+    for (int idx = threadIdx.x; idx < npts * nslot; idx += RP_PTS) {
+        const int lp = idx / nslot, slot = idx - lp * nslot;
+        const long long p = p0 + lp;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* dst;
+        if (slot < 10) {
+            v = *reinterpret_cast<const float4*>(&sx[lp][4 * slot]);
+            dst = H0 + p * LD_H0 + 4 * slot;
+        } else if (slot == 10) {
+            dst = H0 + p * LD_H0 + 68;
+        } else if (slot < 25) {
+            const int j = 4 * (slot - 11);
+            float e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = j + k;
+                e[k] = c < 27 ? sx[lp][c] : (c < 54 ? sd[lp][c - 27] : 0.0f);
+            }
+            v = make_float4(e[0], e[1], e[2], e[3]);
+            dst = RIN + p * LD_RIN + j;
+        } else {
+            dst = RIN + p * LD_RIN + 336 + 4 * (slot - 25);
+        }
+        *reinterpret_cast<float4*>(dst) = v;
+    }
 }
 
 // explicit points (eikonal samples): H0[:, 0:39] = PE6(x), H0[:, 71] = 0
@@ -142,12 +150,15 @@ __device__ __forceinline__ void load_row72(const float* __restrict__ src, float 
 __global__ void __launch_bounds__(128) chain_end_kernel(const float* __restrict__ Q0, const float* __restrict__ H0,
                                                         const float* __restrict__ DY, long long N, int nseed,
                                                         float* __restrict__ G, float* __restrict__ RIN, int rtf) {
+    __shared__ float sg[128][28];                          // PE4(g) of the CTA's rows (main pass only)
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= N * nseed) return;
-    const long long p = m % N;
+    const bool live = m < N * nseed;
+    const long long p = live ? m % N : 0;
+    float g[3] = {0.f, 0.f, 0.f};
+    if (live) {
     float q[72];
     load_row72(Q0 + m * LD_H0, q);
-    float g[3] = {q[0], q[1], q[2]};
+    g[0] = q[0]; g[1] = q[1]; g[2] = q[2];
     {
         float h[40];                                       // PE part of the H0 row: columns 0..39
 #pragma unroll
@@ -182,7 +193,17 @@ __global__ void __launch_bounds__(128) chain_end_kernel(const float* __restrict_
 #pragma unroll
     for (int d = 0; d < 3; ++d) g[d] += 0.5f * e[d];
     G[m * 3 + 0] = g[0]; G[m * 3 + 1] = g[1]; G[m * 3 + 2] = g[2];
-    if (RIN) pe_write(RIN + p * LD_RIN + 54, g[0], g[1], g[2], 4, rtf);
+    }
+    if (!RIN) return;
+    // main pass (nseed == 1, m == p): PE4(g) -> RIN[:, 54:81], staged so that a row's 27 floats leave as one contiguous run
+    if (live) pe_write(sg[threadIdx.x], g[0], g[1], g[2], 4, rtf);
+    __syncthreads();
+    const long long m0 = (long long)blockIdx.x * blockDim.x;
+    const int nrows = (int)min((long long)blockDim.x, N * nseed - m0);
+    for (int idx = threadIdx.x; idx < nrows * 27; idx += blockDim.x) {
+        const int lr = idx / 27, c = idx - lr * 27;
+        RIN[((m0 + lr) % N) * LD_RIN + 54 + c] = sg[lr][c];
+    }
 }
 
 // backward of chain_end: dQ0 = (dh0/dx) dG, where for the main pass
@@ -299,35 +320,58 @@ __global__ void __launch_bounds__(256) rgb_head_bwd_kernel(const float* __restri
 }
 
 // dW2e[key(m), :] += dQ2[m, :]   with key = seed s (< K) or kstar[p]; rows m = s*N + p.
-// One CTA reduces a slab of rows into a [Kp,256] shared tile, then adds it to global.
+// A CTA reduces a slab of rows into a [Kp,256] shared tile, then adds it to global.  64 threads cover a row with float4
+// loads, four rows per pass, eight passes in flight (32 KB of loads per CTA); a thread keeps a running sum while consecutive
+// rows of its lane share the key (always, within a seed block of the eikonal pass) and flushes it with shared-memory atomics
+// when the key changes.
 __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restrict__ dQ2, const int* __restrict__ kstar,
                                                            long long N, int K, int Kp, int nseed, long long rows_per_cta,
                                                            float* __restrict__ dW2e) {
     extern __shared__ float tile[];   // [Kp][256]
-    const int j = threadIdx.x;
-    for (int k = 0; k < Kp; ++k) tile[k * 256 + j] = 0.0f;
+    for (int i = threadIdx.x; i < Kp * 256; i += 256) tile[i] = 0.0f;
+    __syncthreads();
+    const int c4 = (threadIdx.x & 63) * 4, rg = threadIdx.x >> 6;
     const long long total = N * nseed;
     const long long m0 = (long long)blockIdx.x * rows_per_cta;
     const long long m1 = min(total, m0 + rows_per_cta);
-    for (long long mb = m0; mb < m1; mb += 8) {       // 8 independent row loads in flight per thread
-        float v[8];
+    int cur = -1;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long mb = m0 + rg; mb < m1; mb += 32) {
+        float4 v[8];
         int key[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const long long m = mb + i;
-            v[i] = 0.0f; key[i] = 0;
+            const long long m = mb + 4 * i;
+            key[i] = -1;
             if (m < m1) {
-                const long long s = m / N, p = m - s * N;
-                key[i] = (nseed > 1 && s < K) ? (int)s : kstar[p];
-                v[i] = dQ2[m * 256 + j];
+                const long long sd = m / N, p = m - sd * N;
+                key[i] = (nseed > 1 && sd < K) ? (int)sd : kstar[p];
+                v[i] = __ldg(reinterpret_cast<const float4*>(dQ2 + m * 256 + c4));
             }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tile[key[i] * 256 + j] += v[i];     // column j is private to this thread: no race
+        for (int i = 0; i < 8; ++i) {
+            if (key[i] < 0) continue;
+            if (key[i] != cur) {
+                if (cur >= 0) {
+                    float* t = tile + cur * 256 + c4;
+                    atomicAdd(t, acc.x); atomicAdd(t + 1, acc.y); atomicAdd(t + 2, acc.z); atomicAdd(t + 3, acc.w);
+                }
+                cur = key[i];
+                acc = v[i];
+            } else {
+                acc.x += v[i].x; acc.y += v[i].y; acc.z += v[i].z; acc.w += v[i].w;
+            }
+        }
     }
-    for (int k = 0; k < K; ++k) {
-        float v = tile[k * 256 + j];
-        if (v != 0.0f) atomicAdd(dW2e + (long long)k * 256 + j, v);
+    if (cur >= 0) {
+        float* t = tile + cur * 256 + c4;
+        atomicAdd(t, acc.x); atomicAdd(t + 1, acc.y); atomicAdd(t + 2, acc.z); atomicAdd(t + 3, acc.w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * 256; i += 256) {
+        const float v = tile[i];
+        if (v != 0.0f) atomicAdd(dW2e + i, v);
     }
 }
 
@@ -344,7 +388,8 @@ int launch_ray_points(const float* o, const float* d, const float* z, int R, int
                       cudaStream_t st) {
     long long P = (long long)R * S;
     if (P == 0) return HSB_OK;
-    ray_points_kernel<<<cdiv(P * (RIN ? 28 : 12), 256), 256, 0, st>>>(o, d, z, R, S, X, H0, RIN, rtf);
+    if (P > 0x7fffffffLL / 32) { set_error("ray_points: batch too large"); return HSB_ERR_ARG; }
+    ray_points_kernel<<<cdiv(P, RP_PTS), RP_PTS, 0, st>>>(o, d, z, R, S, X, H0, RIN, rtf);
     return check_launch("ray_points");
 }
 int launch_points_pe(const float* X, long long N, float* H0, int rtf, cudaStream_t st) {
@@ -390,8 +435,8 @@ int launch_scatter_rows(const float* dQ2, const int* kstar, long long N, int K, 
                         cudaStream_t st) {
     long long total = N * nseed;
     if (total == 0) return HSB_OK;
-    long long ctas = 4LL * 148;
-    long long rpc = (total + ctas - 1) / ctas;
+    long long ctas = 3LL * num_sms();
+    long long rpc = ((total + ctas - 1) / ctas + 31) / 32 * 32;
     if (rpc < 64) rpc = 64;
     // a CTA's slab may straddle seed blocks; keys are evaluated per row so that is fine
     size_t smem = (size_t)Kp * 256 * sizeof(float);

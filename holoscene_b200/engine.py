@@ -64,6 +64,35 @@ gemm_tn = declare("hsb_gemm_tn", [_vp, c_ll, _vp, c_ll, c_ll, c_int, c_int, c_in
 gemm_wgrad = declare("hsb_gemm_wgrad", [_vp, c_ll, c_int, _vp, c_ll, c_int, c_ll, _vp, c_ll, _vp, c_int, c_stream])
 
 
+
+
+class LossCfg(ctypes.Structure):
+    _fields_ = [("R", ctypes.c_int32), ("S", ctypes.c_int32), ("K", ctypes.c_int32), ("n_grad_rows", ctypes.c_int64),
+                ("w_rgb", c_f32), ("w_eik", c_f32), ("w_smooth", c_f32), ("w_depth", c_f32), ("w_nl1", c_f32), ("w_ncos", c_f32),
+                ("w_sem", c_f32)]
+
+
+LOSS_SCRATCH_DOUBLES = 16
+_loss = declare("hsb_loss", [ctypes.POINTER(LossCfg)] + [_vp] * 18 + [c_stream])
+
+
+def fused_loss(cfg: LossCfg, rgb_values, depth_values, normal_map, opacity, sdf, grad_all, rgb_gt, depth_gt, normal_gt, mask_gt,
+               segs):
+    """hsb_loss: returns (losses[8], d_rgb, d_depth, d_normal, d_opacity, d_grad_all) -- see include/hsb200.h."""
+    dev = rgb_values.device
+    d_rgb = torch.empty_like(rgb_values)
+    d_depth = torch.empty_like(depth_values)
+    d_normal = torch.empty_like(normal_map)
+    d_opacity = torch.empty_like(opacity)
+    d_grad = torch.empty_like(grad_all) if grad_all is not None else None
+    scratch = torch.empty(LOSS_SCRATCH_DOUBLES, dtype=torch.float64, device=dev)
+    losses = torch.empty(8, device=dev)
+    check(_loss(ctypes.byref(cfg), ptr(rgb_values), ptr(depth_values), ptr(normal_map), ptr(opacity), ptr(sdf), ptr(grad_all),
+                ptr(rgb_gt), ptr(depth_gt), ptr(normal_gt), ptr(mask_gt), ptr(segs), ptr(d_rgb), ptr(d_depth), ptr(d_normal),
+                ptr(d_opacity), ptr(d_grad), ptr(scratch), ptr(losses), stream()))
+    return losses, d_rgb, d_depth, d_normal, d_opacity, d_grad
+
+
 def param_layout(K: int, table_rows: int) -> list[int]:
     arr = (ctypes.c_int64 * (NUM_SEGMENTS + 1))()
     check(_param_layout(K, table_rows, arr))

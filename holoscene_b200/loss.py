@@ -100,6 +100,30 @@ class MonoSDFLoss(nn.Module):
                 "depth_loss": depth_loss, "normal_l1": normal_l1, "normal_cos": normal_cos}
 
 
+class _FusedLossFn(torch.autograd.Function):
+    """One autograd node for the always-on Stage-1 terms: forward = hsb_loss (values AND weighted gradients in three
+    launches), backward hands the stored gradients to the model's fused backward.  Only the total is differentiable;
+    the per-term values are returned detached."""
+
+    @staticmethod
+    def forward(ctx, cfg, sdf, gts, rgb_values, depth_values, normal_map, opacity, grad_all):
+        from . import engine as _engine
+        losses, d_rgb, d_depth, d_normal, d_opacity, d_grad = _engine.fused_loss(
+            cfg, rgb_values.contiguous(), depth_values.contiguous(), normal_map.contiguous(), opacity.contiguous(), sdf,
+            None if grad_all is None else grad_all.contiguous(), *gts)
+        ctx.grads = (d_rgb, d_depth, d_normal, d_opacity, d_grad)
+        ctx.mark_non_differentiable(losses)
+        return losses[0].clone(), losses
+
+    @staticmethod
+    def backward(ctx, g_total, _g_terms):
+        d_rgb, d_depth, d_normal, d_opacity, d_grad = ctx.grads
+        ctx.grads = None
+        # g_total is 1 for loss.backward(); kept general (one tiny launch per tensor only when it is not the constant one)
+        sc = (lambda t: t) if g_total is None else (lambda t: None if t is None else t * g_total)
+        return None, None, None, sc(d_rgb), sc(d_depth), sc(d_normal), sc(d_opacity), sc(d_grad)
+
+
 class HoloSceneLoss(MonoSDFLoss):
     def __init__(self, rgb_loss, eikonal_weight, semantic_weight=0.04, smooth_weight=0.005, semantic_loss=None,
                  depth_weight=0.1, normal_l1_weight=0.05, normal_cos_weight=0.05, reg_vio_weight=0.1,
@@ -113,6 +137,9 @@ class HoloSceneLoss(MonoSDFLoss):
         self.use_obj_opacity = use_obj_opacity
         if not use_obj_opacity:
             raise NotImplementedError("Stage-1 confs use use_obj_opacity = True (ObjectSDF++ opacity loss)")
+        # fused=True: the always-on terms and their gradients come from hsb_loss (three launches); False keeps the
+        # tensor-op formulation above (same arithmetic, differentiated by autograd) -- the parity tests run both.
+        self.fused = True
 
     def object_distinct_loss(self, sdf_value, min_sdf):
         _, min_indice = torch.min(sdf_value, dim=1, keepdim=True)
@@ -150,7 +177,48 @@ class HoloSceneLoss(MonoSDFLoss):
         mask = mask.reshape(1, 32, 32)
         return self.compute_grad_error(bg_depth, mask) + self.compute_grad_error(bg_normal, mask.repeat(3, 1, 1))
 
+    def _fused_ok(self, mo):
+        return (self.fused and isinstance(self.rgb_loss, nn.L1Loss) and self.rgb_loss.reduction == "mean"
+                and mo["rgb_values"].is_cuda and "object_opacity" in mo and "sdf" in mo
+                and (("grad_theta" in mo) == ("_hsb_grad_theta_all" in mo)))
+
+    def _forward_fused(self, mo, gt, call_reg):
+        """Always-on terms through hsb_loss (csrc/loss.cu); collision / background-patch regularisers as tensor code."""
+        from . import engine as _engine
+        dev = mo["rgb_values"].device
+        R, K = mo["object_opacity"].shape
+        sdf = mo["sdf"].contiguous()
+        grad_all = mo.get("_hsb_grad_theta_all")
+        decay = math.exp(-self.step / self.end_step * 10.0) if self.end_step > 0 else 1.0
+        self.step += 1
+        cfg = _engine.LossCfg()
+        cfg.R, cfg.S, cfg.K = R, sdf.shape[1], K
+        cfg.n_grad_rows = 0 if grad_all is None else grad_all.shape[0]
+        cfg.w_rgb, cfg.w_eik, cfg.w_smooth = 1.0, self.eikonal_weight, self.smooth_weight
+        cfg.w_depth = decay * self.depth_weight if self.depth_weight > 0 else 0.0
+        cfg.w_nl1, cfg.w_ncos, cfg.w_sem = decay * self.normal_l1_weight, decay * self.normal_cos_weight, self.semantic_weight
+        f32 = lambda t, n: t.to(dev, torch.float32, non_blocking=True).reshape(R, n).contiguous()
+        gts = (f32(gt["rgb"], 3), f32(gt["depth"], 1), f32(gt["normal"], 3), f32(gt["mask"], 1),
+               gt["segs"].to(dev, non_blocking=True).long().reshape(R).contiguous())
+        total, terms = _FusedLossFn.apply(cfg, sdf, gts, mo["rgb_values"], mo["depth_values"], mo["normal_map"],
+                                          mo["object_opacity"], grad_all)
+        zero = torch.zeros((), device=dev)
+        out = {"rgb_loss": terms[1], "eikonal_loss": terms[2], "smooth_loss": terms[3], "depth_loss": terms[4],
+               "normal_l1": terms[5], "normal_cos": terms[6], "semantic_loss": terms[7]}
+        reg = zero
+        if "sample_sdf" in mo and call_reg:
+            reg = self.object_distinct_loss(mo["sample_sdf"], mo["sample_minsdf"])
+            total = total + self.reg_vio_weight * reg
+        bgl = zero
+        if "bg_depth_values" in mo:
+            bgl = self.get_bg_render_loss(mo["bg_depth_values"], mo["bg_normal_map"], (mo["bg_mask"] != 0).int())
+            total = total + self.bg_reg_weight * bgl
+        out["collision_reg_loss"], out["background_reg_loss"], out["loss"] = reg, bgl, total
+        return out
+
     def forward(self, model_outputs, ground_truth, call_reg=False, call_bg_reg=False):
+        if self._fused_ok(model_outputs):
+            return self._forward_fused(model_outputs, ground_truth, call_reg)
         output = super().forward(model_outputs, ground_truth)
         dev = model_outputs["rgb_values"].device
         zero = torch.zeros((), device=dev)

@@ -357,6 +357,7 @@ class HoloSceneNetwork(nn.Module):
             output["sample_sdf"] = ssdf
             output["grad_theta"] = gt[: gt.shape[0] // 2]
             output["grad_theta_nei"] = gt[gt.shape[0] // 2:]
+            output["_hsb_grad_theta_all"] = gt      # the fused loss reads / differentiates the stacked tensor in one piece
         if bg is not None:
             output["bg_depth_values"], output["bg_normal_map"] = bg
         return output

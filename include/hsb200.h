@@ -181,6 +181,25 @@ int hsb_eikonal_forward(hsb_ctx* ctx, const float* x, int64_t Ne, float* grad_th
 int hsb_eikonal_backward(hsb_ctx* ctx, const float* d_grad_theta, const float* d_sample_sdf /* may be NULL */,
                          hsb_stream_t stream);
 
+/* Stage-1 loss terms and d(total)/d(output) in three launches (model/loss.py:181-193,227-346,487-492; see csrc/loss.cu).
+ * Inputs: per-ray outputs of hsb_render_forward(MAIN) (rgb_values [R,3], depth_values [R], normal_map [R,3], opacity [R,K]), the
+ * scene SDF samples sdf [R,S] (buffer "main.SDF"), the stacked eikonal gradients grad_theta_all [n_grad_rows,3] (first half =
+ * grad_theta, second half = grad_theta_nei as the reference slices them; n_grad_rows = 0: no eikonal terms) and the ground truth
+ * rgb_gt [R,3], depth_gt [R], normal_gt [R,3], mask_gt [R], segs [R] (int64 class ids).  Weights are the conf's loss weights with
+ * the depth/normal decay already applied.  Outputs: d_* = weight * d(term)/d(output), ready for hsb_render_backward /
+ * hsb_eikonal_backward; losses[8] = {weighted total of these terms, rgb, eikonal, smooth, depth, normal_l1, normal_cos, semantic}.
+ * scratch: HSB_LOSS_SCRATCH_DOUBLES device doubles. */
+#define HSB_LOSS_SCRATCH_DOUBLES 16
+typedef struct hsb_loss_cfg {
+    int32_t R, S, K;
+    int64_t n_grad_rows;
+    float w_rgb, w_eik, w_smooth, w_depth, w_nl1, w_ncos, w_sem;
+} hsb_loss_cfg;
+int hsb_loss(const hsb_loss_cfg* cfg, const float* rgb_values, const float* depth_values, const float* normal_map,
+             const float* opacity, const float* sdf, const float* grad_theta_all, const float* rgb_gt, const float* depth_gt,
+             const float* normal_gt, const float* mask_gt, const int64_t* segs, float* d_rgb, float* d_depth, float* d_normal,
+             float* d_opacity, float* d_grad_theta_all, double* scratch, float* losses, hsb_stream_t stream);
+
 /* torch.optim.Adam semantics over one flat segment (holoscene_train.py:156-164); grad_norm_sq (may be NULL)
  * accumulates sum(g^2) in the same pass (the trainer's total_norm statistic, :367-372). */
 int hsb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
