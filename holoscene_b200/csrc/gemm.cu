@@ -257,14 +257,44 @@ __global__ void __launch_bounds__(256) gemm_wgrad_kernel(const float* __restrict
 }
 
 // bias[n] += sum_m A[m, n]   (column sums; used when the tcgen05 wgrad path handles the contraction)
+// Thread = (row lane, float4 column group): the 256 threads of a CTA cover 256 / (N1/4) rows per pass with 16-byte loads, so
+// narrow matrices (dO [P,4], dS [P,Kp]) keep every lane busy -- one-thread-per-column left 4 of 256 threads working on dO.
+// N1 % 4 == 0, lda % 4 == 0 and 16-byte alignment are guaranteed by gemm_wgrad_tc_eligible.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ A, long long lda, int N1, long long M,
                                                      long long rows_per_cta, float* __restrict__ bias) {
+    __shared__ float4 red[256];
+    const int cols4 = N1 >> 2;
+    const int lanes = 256 / cols4;                                  // row lanes (>= 4 for N1 <= 256)
+    const int tid = threadIdx.x;
+    const int c4 = tid % cols4, ry = tid / cols4;
     const long long r0 = (long long)blockIdx.x * rows_per_cta;
     const long long r1 = min(M, r0 + rows_per_cta);
-    for (int n = threadIdx.x; n < N1; n += 256) {
-        float acc = 0.0f;
-        for (long long r = r0; r < r1; ++r) acc += A[r * lda + n];
-        atomicAdd(bias + n, acc);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ry < lanes) {
+        long long r = r0 + ry;
+        for (; r + 3LL * lanes < r1; r += 4LL * lanes) {            // four independent loads in flight
+            const float4 a = __ldg(reinterpret_cast<const float4*>(A + r * lda) + c4);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(A + (r + lanes) * lda) + c4);
+            const float4 c = __ldg(reinterpret_cast<const float4*>(A + (r + 2LL * lanes) * lda) + c4);
+            const float4 d = __ldg(reinterpret_cast<const float4*>(A + (r + 3LL * lanes) * lda) + c4);
+            acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+            acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+        }
+        for (; r < r1; r += lanes) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(A + r * lda) + c4);
+            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+    }
+    red[tid] = acc;
+    __syncthreads();
+    if (tid < cols4) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < lanes; ++l) {
+            const float4 v = red[l * cols4 + tid];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        atomicAdd(bias + 4 * tid, t.x); atomicAdd(bias + 4 * tid + 1, t.y);
+        atomicAdd(bias + 4 * tid + 2, t.z); atomicAdd(bias + 4 * tid + 3, t.w);
     }
 }
 
@@ -308,9 +338,10 @@ int gemm_wgrad(const float* A, long long lda, int N1, const float* B, long long 
     if (M <= 0 || N1 <= 0 || N2 <= 0) return HSB_OK;
     if (precise == 0 && gemm_wgrad_tc_eligible(A, lda, N1, B, ldb, N2, M)) {
         if (bias) {
+            if (N1 > 256) { set_error("gemm_wgrad: bias column sums support N1 <= 256"); return HSB_ERR_ARG; }
             long long ctas = 8LL * num_sms();
             long long rpc = (M + ctas - 1) / ctas;
-            if (rpc < 32) rpc = 32;
+            if (rpc < 256) rpc = 256;
             colsum_kernel<<<(unsigned)((M + rpc - 1) / rpc), 256, 0, stream>>>(A, lda, N1, M, rpc, bias);
             count_launch(1);
         }

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) hash_bwd2_kernel(const float* __restrict_
 // (hashgrid.py:158).  dE may be null (eikonal-only), q0E/dg may be null (first order only).
 //   dE   [B, *] row stride e_ps, level l at columns 2l..2l+1
 //   q0E  [nseed*B, *] row stride q_ps  (seed s, point p -> row s*B+p)
-//   dg   [nseed*B, 3]
+//   dg   [nseed*B, 3]; NULL with nseed == 3: q0E rows are forward-mode tangent cotangents (seed s = unit vector e_s)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hash_bwd_fused_kernel(const float* __restrict__ x, const int* __restrict__ offsets,
                                                              const float* __restrict__ dE, long long e_ps,
@@ -372,7 +372,11 @@ __global__ void __launch_bounds__(256) hash_bwd_fused_kernel(const float* __rest
                 const long long r = (long long)s * B + p;
                 float2 q = ld2(q0E + r * q_ps + level * 2);
                 q.x *= 0.5f; q.y *= 0.5f;
-                const float gx[3] = {dg[r * 3 + 0], dg[r * 3 + 1], dg[r * 3 + 2]};
+                // dg == nullptr (nseed == 3): tangent rows of the forward-mode eikonal pass -- row s carries d(loss)/d(d h0 / d x_s),
+                // i.e. the coefficient of dy_dx[:, s, :] directly (unit seed e_s)
+                float gx[3];
+                if (dg) { gx[0] = dg[r * 3 + 0]; gx[1] = dg[r * 3 + 1]; gx[2] = dg[r * 3 + 2]; }
+                else { gx[0] = s == 0 ? 1.0f : 0.0f; gx[1] = s == 1 ? 1.0f : 0.0f; gx[2] = s == 2 ? 1.0f : 0.0f; }
                 second_order_cache(c, q, gx, cache);
             }
         }
@@ -451,7 +455,7 @@ extern "C" int hsb_hash_backward_fused(const float* x_world, const int32_t* offs
                                        float* grad_embeddings, uint32_t B, uint32_t L, float S, uint32_t H,
                                        cudaStream_t stream) {
     if (B == 0) return HSB_OK;
-    if (!x_world || !offsets || !grad_embeddings || L == 0 || L > 32 || (q0E && !dg)) { set_error("hsb_hash_backward_fused: bad argument"); return HSB_ERR_ARG; }
+    if (!x_world || !offsets || !grad_embeddings || L == 0 || L > 32 || (q0E && !dg && nseed != 3)) { set_error("hsb_hash_backward_fused: bad argument"); return HSB_ERR_ARG; }
     dim3 grid(cdiv(B, 256), L);
     hash_bwd_fused_kernel<<<grid, 256, 0, stream>>>(x_world, offsets, dE, e_point_stride, q0E, q_point_stride, dg, nseed,
                                                     reinterpret_cast<float2*>(grad_embeddings), B, L, S, H);

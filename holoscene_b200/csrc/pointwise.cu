@@ -276,6 +276,79 @@ __global__ void __launch_bounds__(128) chain_end_bwd_kernel(float* __restrict__ 
         out[i] = make_float4(rtf32(q[4 * i], rtf), rtf32(q[4 * i + 1], rtf), rtf32(q[4 * i + 2], rtf), rtf32(q[4 * i + 3], rtf));
 }
 
+// ---- eikonal pass in forward mode ---------------------------------------------------------------------------------
+// The reference stacks K+1 reverse-mode gradients per eikonal point (network.py:212-254): the K rows of the Jacobian
+// J = d sdf_raw / d x  [K,3] plus the arg-min row.  J has only three COLUMNS, so it is evaluated in forward mode: three
+// tangent rows per point (rows m = d*N + p) instead of K+1 cotangent rows -- 11x fewer rows at K = 32, and the row count no
+// longer grows with the object count.
+//
+// tangent seeds:  U0[d*N + p, :] = d h0[p, :] / d x_d,   h0 = [x | sin(2^i x) | cos(2^i x) | hash(x)]
+//   column d: 1;  d sin(f x_d)/d x_d = f cos(f x_d) (stored in H0);  d cos = -f sin;  hash: 0.5 * dy_dx[l, d, :]
+//   (0.5 = chain factor of the [-1,1] -> [0,1] map, hashgrid.py:158).
+__global__ void __launch_bounds__(128) tangent_seed_kernel(const float* __restrict__ H0, const float* __restrict__ DY, long long N,
+                                                           float* __restrict__ U0, int rtf) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= 3 * N) return;
+    const int d = (int)(m / N);
+    const long long p = m - (long long)d * N;
+    float q[72];
+#pragma unroll
+    for (int i = 0; i < 72; ++i) q[i] = 0.0f;
+    const float* h = H0 + p * LD_H0;
+    const float* dy = DY + p * 96 + d * 2;                 // (l, d, c) at l*6 + d*2 + c: 8-byte aligned
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {                       // compile-time indices into q (keeps the row in registers)
+        if (dd != d) continue;
+        q[dd] = 1.0f;
+        float f = 1.0f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            q[3 + 6 * i + dd] = f * __ldg(h + 3 + 6 * i + 3 + dd);
+            q[3 + 6 * i + 3 + dd] = -f * __ldg(h + 3 + 6 * i + dd);
+            f *= 2.0f;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(dy + l * 6));
+        q[39 + 2 * l] = 0.5f * v.x;
+        q[40 + 2 * l] = 0.5f * v.y;
+    }
+    float4* out = reinterpret_cast<float4*>(U0 + m * LD_H0);
+#pragma unroll
+    for (int i = 0; i < 18; ++i)
+        out[i] = make_float4(rtf32(q[4 * i], rtf), rtf32(q[4 * i + 1], rtf), rtf32(q[4 * i + 2], rtf), rtf32(q[4 * i + 3], rtf));
+}
+
+// grad_theta[(s*N + p), d] = J[d*N + p, key],  key = s < K ? s : kstar[p]   (reference stacking: K channels, then the min-SDF)
+__global__ void __launch_bounds__(256) jac_to_grad_kernel(const float* __restrict__ J, const int* __restrict__ kstar, long long N,
+                                                          int K, int Kp, float* __restrict__ G) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)(K + 1) * N) return;
+    const int s = (int)(t / N);
+    const long long p = t - (long long)s * N;
+    const int key = s < K ? s : kstar[p];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) G[t * 3 + d] = J[((long long)d * N + p) * Kp + key];
+}
+
+// transpose of the above: dJ[d*N + p, k] = dG[(k*N + p), d] + [k == kstar[p]] dG[(K*N + p), d];  pad columns K..Kp-1 = 0
+__global__ void __launch_bounds__(256) grad_to_jac_kernel(const float* __restrict__ dG, const int* __restrict__ kstar, long long N,
+                                                          int K, int Kp, float* __restrict__ dJ, int rtf) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * N * Kp) return;
+    const int k = (int)(t % Kp);
+    const long long m = t / Kp;
+    const int d = (int)(m / N);
+    const long long p = m - (long long)d * N;
+    float v = 0.0f;
+    if (k < K) {
+        v = dG[((long long)k * N + p) * 3 + d];
+        if (k == kstar[p]) v += dG[((long long)K * N + p) * 3 + d];
+    }
+    dJ[t] = rtf32(v, rtf);
+}
+
 // colour head: RGB[p, 0:3] = sigmoid(U2[p,:] . R2e[c,:] + b[c]),  RGB[p,3] = 0.   One warp per point.
 __global__ void __launch_bounds__(256) rgb_head_kernel(const float* __restrict__ U2, const float* __restrict__ R2e,
                                                        const float* __restrict__ bias, long long N, float* __restrict__ RGB) {
@@ -299,24 +372,55 @@ __global__ void __launch_bounds__(256) rgb_head_kernel(const float* __restrict__
     }
 }
 
-// dU2[p,j] = (sum_c dO[p,c] R2e[c,j]) * [U2[p,j] > 0]
+// dU2[p,j] = (sum_c dO[p,c] R2e[c,j]) * [U2[p,j] > 0];  optionally colsum[j] += sum_p dU2[p,j] (the lin1 bias gradient of the
+// render net, taken here so that dU2 is not re-read by a separate column-sum pass).  A CTA owns 128 rows: thread = (row lane
+// 0..3, float4 column group 0..63), 32 rows per thread, four rows in flight.
+constexpr int RHB_ROWS = 128;
 __global__ void __launch_bounds__(256) rgb_head_bwd_kernel(const float* __restrict__ dO, const float* __restrict__ R2e,
-                                                           const float* __restrict__ U2, long long N, float* __restrict__ dU2, int rtf) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // over N*64 float4
-    if (t >= N * 64) return;
-    const long long p = t >> 6;
-    const int j = (int)(t & 63);
-    const float4 g = reinterpret_cast<const float4*>(dO)[p];
-    const float4 u = reinterpret_cast<const float4*>(U2 + p * 256)[j];
+                                                           const float* __restrict__ U2, long long N, float* __restrict__ dU2, int rtf,
+                                                           float* __restrict__ colsum) {
+    __shared__ float4 red[256];
+    const int j = threadIdx.x & 63, ry = threadIdx.x >> 6;
     const float4 w0 = reinterpret_cast<const float4*>(R2e)[j];
     const float4 w1 = reinterpret_cast<const float4*>(R2e + 256)[j];
     const float4 w2 = reinterpret_cast<const float4*>(R2e + 512)[j];
-    float4 r;
-    r.x = u.x > 0.f ? rtf32(g.x * w0.x + g.y * w1.x + g.z * w2.x, rtf) : 0.f;
-    r.y = u.y > 0.f ? rtf32(g.x * w0.y + g.y * w1.y + g.z * w2.y, rtf) : 0.f;
-    r.z = u.z > 0.f ? rtf32(g.x * w0.z + g.y * w1.z + g.z * w2.z, rtf) : 0.f;
-    r.w = u.w > 0.f ? rtf32(g.x * w0.w + g.y * w1.w + g.z * w2.w, rtf) : 0.f;
-    reinterpret_cast<float4*>(dU2 + p * 256)[j] = r;
+    const long long p0 = (long long)blockIdx.x * RHB_ROWS;
+    const long long p1 = min(N, p0 + RHB_ROWS);
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long pb = p0 + ry; pb < p1; pb += 16) {
+        float4 g[4], u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long p = pb + 4 * i;
+            if (p < p1) {
+                g[i] = __ldg(reinterpret_cast<const float4*>(dO) + p);
+                u[i] = __ldg(reinterpret_cast<const float4*>(U2 + p * 256) + j);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long p = pb + 4 * i;
+            if (p < p1) {
+                float4 r;
+                r.x = u[i].x > 0.f ? rtf32(g[i].x * w0.x + g[i].y * w1.x + g[i].z * w2.x, rtf) : 0.f;
+                r.y = u[i].y > 0.f ? rtf32(g[i].x * w0.y + g[i].y * w1.y + g[i].z * w2.y, rtf) : 0.f;
+                r.z = u[i].z > 0.f ? rtf32(g[i].x * w0.z + g[i].y * w1.z + g[i].z * w2.z, rtf) : 0.f;
+                r.w = u[i].w > 0.f ? rtf32(g[i].x * w0.w + g[i].y * w1.w + g[i].z * w2.w, rtf) : 0.f;
+                reinterpret_cast<float4*>(dU2 + p * 256)[j] = r;
+                cs.x += r.x; cs.y += r.y; cs.z += r.z; cs.w += r.w;
+            }
+        }
+    }
+    if (!colsum) return;
+    red[threadIdx.x] = cs;
+    __syncthreads();
+    if (ry == 0) {
+        const float4 a = red[j], b = red[64 + j], c = red[128 + j], d = red[192 + j];
+        atomicAdd(colsum + 4 * j, (a.x + b.x) + (c.x + d.x));
+        atomicAdd(colsum + 4 * j + 1, (a.y + b.y) + (c.y + d.y));
+        atomicAdd(colsum + 4 * j + 2, (a.z + b.z) + (c.z + d.z));
+        atomicAdd(colsum + 4 * j + 3, (a.w + b.w) + (c.w + d.w));
+    }
 }
 
 // dW2e[key(m), :] += dQ2[m, :]   with key = seed s (< K) or kstar[p]; rows m = s*N + p.
@@ -383,6 +487,58 @@ __global__ void __launch_bounds__(256) add_min_grad_kernel(const float* __restri
     dS[p * Kp + kstar[p]] += dsdf[p];
 }
 
+// ---- camera rays (utils/rend_util.py:56-98,112-125 called twice from model/network.py:788-792) -------------------------
+// One thread per pixel.  Reproduces the reference's in-place side effect: get_camera_params adds ray_offset to uv, and the
+// model calls it a second time (identity pose, same offset) to obtain depth_scale = z of the unit camera-space direction,
+// so ray_dirs use uv + offset while depth_scale uses uv + 2*offset, and uv leaves shifted by 2*offset.
+__device__ __forceinline__ void lift_pixel(float u, float v, const float* __restrict__ K, float& xl, float& yl) {
+    const float fx = K[0], sk = K[1], cx = K[2], fy = K[5], cy = K[6];
+    xl = (u - cx + cy * sk / fy - sk * v / fy) / fx;
+    yl = (v - cy) / fy;
+}
+__global__ void __launch_bounds__(256) camera_rays_kernel(float* __restrict__ uv, const float* __restrict__ offset,
+                                                          const float* __restrict__ pose, const float* __restrict__ K, int R,
+                                                          float* __restrict__ dirs, float* __restrict__ cam_loc,
+                                                          float* __restrict__ depth_scale) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float u = uv[2 * r], v = uv[2 * r + 1];
+    const float ou = offset ? offset[2 * r] : 0.0f, ov = offset ? offset[2 * r + 1] : 0.0f;
+    u += ou; v += ov;
+    float xl, yl;
+    lift_pixel(u, v, K, xl, yl);
+    float w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = pose[4 * i] * xl + pose[4 * i + 1] * yl + pose[4 * i + 2] + pose[4 * i + 3];
+    const float cx = pose[3], cy = pose[7], cz = pose[11];
+    float dx = w[0] / w[3] - cx, dy = w[1] / w[3] - cy, dz = w[2] / w[3] - cz;
+    float n = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+    dirs[3 * r] = dx / n; dirs[3 * r + 1] = dy / n; dirs[3 * r + 2] = dz / n;
+    cam_loc[3 * r] = cx; cam_loc[3 * r + 1] = cy; cam_loc[3 * r + 2] = cz;
+    u += ou; v += ov;                                       // second call of the reference: the offset is added again
+    lift_pixel(u, v, K, xl, yl);
+    n = fmaxf(sqrtf(xl * xl + yl * yl + 1.0f), 1e-12f);
+    depth_scale[r] = 1.0f / n;
+    uv[2 * r] = u; uv[2 * r + 1] = v;
+}
+
+// eikonal sample points (model/network.py:843-858): [uniform | near-surface o + z_eik d | both + (noise - 0.5) * 0.01]
+__global__ void __launch_bounds__(256) eik_points_kernel(const float* __restrict__ uniform, const float* __restrict__ o,
+                                                         const float* __restrict__ d, const float* __restrict__ z_eik,
+                                                         const float* __restrict__ noise, int n, float* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;    // over 2n * 3
+    if (t >= 6 * n) return;
+    const int row = t / 3, c = t - row * 3;
+    float v;
+    if (row < n) v = uniform[t];
+    else {
+        const int r = row - n;
+        v = o[3 * r + c] + z_eik[r] * d[3 * r + c];
+    }
+    out[t] = v;
+    out[6 * n + t] = v + (noise[t] - 0.5f) * 0.01f;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------------
 int launch_ray_points(const float* o, const float* d, const float* z, int R, int S, float* X, float* H0, float* RIN, int rtf,
                       cudaStream_t st) {
@@ -426,9 +582,10 @@ int launch_rgb_head(const float* U2, const float* R2e, const float* bias, long l
     rgb_head_kernel<<<cdiv(N * 32, 256), 256, 0, st>>>(U2, R2e, bias, N, RGB);
     return check_launch("rgb_head");
 }
-int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, int rtf, cudaStream_t st) {
+int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, int rtf, float* colsum,
+                        cudaStream_t st) {
     if (N == 0) return HSB_OK;
-    rgb_head_bwd_kernel<<<cdiv(N * 64, 256), 256, 0, st>>>(dO, R2e, U2, N, dU2, rtf);
+    rgb_head_bwd_kernel<<<cdiv(N, RHB_ROWS), 256, 0, st>>>(dO, R2e, U2, N, dU2, rtf, colsum);
     return check_launch("rgb_head_bwd");
 }
 int launch_scatter_rows(const float* dQ2, const int* kstar, long long N, int K, int Kp, int nseed, float* dW2e,
@@ -447,6 +604,33 @@ int launch_scatter_rows(const float* dQ2, const int* kstar, long long N, int K, 
     }
     scatter_rows_kernel<<<cdiv(total, rpc), 256, smem, st>>>(dQ2, kstar, N, K, Kp, nseed, rpc, dW2e);
     return check_launch("scatter_rows");
+}
+int launch_tangent_seed(const float* H0, const float* DY, long long N, float* U0, int rtf, cudaStream_t st) {
+    if (N == 0) return HSB_OK;
+    tangent_seed_kernel<<<cdiv(3 * N, 128), 128, 0, st>>>(H0, DY, N, U0, rtf);
+    return check_launch("tangent_seed");
+}
+int launch_jac_to_grad(const float* J, const int* kstar, long long N, int K, int Kp, float* G, cudaStream_t st) {
+    if (N == 0) return HSB_OK;
+    jac_to_grad_kernel<<<cdiv((long long)(K + 1) * N, 256), 256, 0, st>>>(J, kstar, N, K, Kp, G);
+    return check_launch("jac_to_grad");
+}
+int launch_grad_to_jac(const float* dG, const int* kstar, long long N, int K, int Kp, float* dJ, int rtf, cudaStream_t st) {
+    if (N == 0) return HSB_OK;
+    grad_to_jac_kernel<<<cdiv(3 * N * Kp, 256), 256, 0, st>>>(dG, kstar, N, K, Kp, dJ, rtf);
+    return check_launch("grad_to_jac");
+}
+int launch_camera_rays(float* uv, const float* offset, const float* pose, const float* K, int R, float* dirs, float* cam_loc,
+                       float* depth_scale, cudaStream_t st) {
+    if (R == 0) return HSB_OK;
+    camera_rays_kernel<<<cdiv(R, 256), 256, 0, st>>>(uv, offset, pose, K, R, dirs, cam_loc, depth_scale);
+    return check_launch("camera_rays");
+}
+int launch_eik_points(const float* uniform, const float* o, const float* d, const float* z_eik, const float* noise, int n,
+                      float* out, cudaStream_t st) {
+    if (n == 0) return HSB_OK;
+    eik_points_kernel<<<cdiv(6LL * n, 256), 256, 0, st>>>(uniform, o, d, z_eik, noise, n, out);
+    return check_launch("eik_points");
 }
 int launch_add_min_grad(const float* dsdf, const int* kstar, long long N, int Kp, float* dS, cudaStream_t st) {
     if (N == 0) return HSB_OK;

@@ -60,6 +60,9 @@ struct Slot {
     float *EC, *C1, *RIN, *U1, *U2, *RGB, *W, *T, *WSUM, *WZSUM, *ZV, *DSCALE, *ROT;
     // backward temporaries
     float *dO, *dS, *dG, *dQ0, *dQ1, *dA1x, *dQ2, *dA2x, *dA2, *dA1, *dH0E, *dU2, *dU1, *dRIN, *dFEAT, *dC1, *dEC;
+    // forward-mode (tangent) buffers of the eikonal slot, rows m = d*N + p (d = 0..2)
+    bool tangent = false;
+    float *U0, *T1, *T2, *J, *dJ, *R2, *R1, *dU0;
 };
 
 struct Ctx {
@@ -91,20 +94,25 @@ static float* carve(Ctx* c, const char* name, long long rows, long long ld, bool
     return reinterpret_cast<float*>(c->ws + o);
 }
 
-static void carve_slot(Ctx* c, int idx, const char* pre, long long points, int max_seeds, int rays, bool color, bool dry) {
+static void carve_slot(Ctx* c, int idx, const char* pre, long long points, int max_seeds, int rays, bool color, bool tangent, bool dry) {
     Slot& s = c->slot[idx];
-    s.cap_points = points; s.cap_rows = points * max_seeds; s.cap_rays = rays; s.with_color = color;
+    s.cap_points = points; s.cap_rows = points * max_seeds; s.cap_rays = rays; s.with_color = color; s.tangent = tangent;
     const long long N = points, E = s.cap_rows;
     const int Kp = c->Kp;
     auto nm = [&](const char* n) { static char b[64]; snprintf(b, sizeof b, "%s.%s", pre, n); return (const char*)b; };
     s.X = carve(c, nm("X"), N, 3, dry);        s.H0 = carve(c, nm("H0"), N, LD_H0, dry);  s.DY = carve(c, nm("DY"), N, 96, dry);
     s.H1 = carve(c, nm("H1"), N, 256, dry);    s.H2 = carve(c, nm("H2"), N, 256, dry);    s.SR = carve(c, nm("SR"), N, Kp, dry);
     s.SDF = carve(c, nm("SDF"), N, 1, dry);    s.KS = (int*)carve(c, nm("KS"), N, 1, dry);
-    s.P2 = carve(c, nm("P2"), E, 256, dry);    s.P1 = carve(c, nm("P1"), E, 256, dry);    s.Q0 = carve(c, nm("Q0"), E, LD_H0, dry);
-    s.G = carve(c, nm("G"), E, 3, dry);
-    s.dS = carve(c, nm("dS"), N, Kp, dry);     s.dG = carve(c, nm("dG"), E, 3, dry);      s.dQ0 = carve(c, nm("dQ0"), E, LD_H0, dry);
-    s.dQ1 = carve(c, nm("dQ1"), E, 256, dry);  s.dA1x = carve(c, nm("dA1x"), N, 256, dry);
-    s.dQ2 = carve(c, nm("dQ2"), E, 256, dry);  s.dA2x = carve(c, nm("dA2x"), N, 256, dry);
+    s.dS = carve(c, nm("dS"), N, Kp, dry);     s.dA1x = carve(c, nm("dA1x"), N, 256, dry); s.dA2x = carve(c, nm("dA2x"), N, 256, dry);
+    if (!tangent) {                              // reverse-mode chain of the min-SDF gradient (one cotangent row per point)
+        s.P2 = carve(c, nm("P2"), E, 256, dry);    s.P1 = carve(c, nm("P1"), E, 256, dry);    s.Q0 = carve(c, nm("Q0"), E, LD_H0, dry);
+        s.G = carve(c, nm("G"), E, 3, dry);        s.dG = carve(c, nm("dG"), E, 3, dry);      s.dQ0 = carve(c, nm("dQ0"), E, LD_H0, dry);
+        s.dQ1 = carve(c, nm("dQ1"), E, 256, dry);  s.dQ2 = carve(c, nm("dQ2"), E, 256, dry);
+    } else {                                     // forward-mode Jacobian: three tangent rows per point
+        s.U0 = carve(c, nm("U0"), E, LD_H0, dry);  s.T1 = carve(c, nm("T1"), E, 256, dry);    s.T2 = carve(c, nm("T2"), E, 256, dry);
+        s.J = carve(c, nm("J"), E, Kp, dry);       s.dJ = carve(c, nm("dJ"), E, Kp, dry);     s.R2 = carve(c, nm("R2"), E, 256, dry);
+        s.R1 = carve(c, nm("R1"), E, 256, dry);    s.dU0 = carve(c, nm("dU0"), E, LD_H0, dry);
+    }
     s.dA2 = carve(c, nm("dA2"), N, 256, dry);  s.dA1 = carve(c, nm("dA1"), N, 256, dry);  s.dH0E = carve(c, nm("dH0E"), N, 32, dry);
     if (rays > 0) {
         s.W = carve(c, nm("W"), N, 1, dry);    s.T = carve(c, nm("T"), N, 1, dry);        s.ZV = carve(c, nm("ZV"), N, 1, dry);
@@ -146,9 +154,9 @@ static void carve_all(Ctx* c, bool dry) {
     c->dR2e = carve(c, "dR2e", 4, 256, dry);     c->dRB2e = carve(c, "dRB2e", 4, 1, dry);
     c->dwe_bytes = c->ws_used - begin;
     if (!dry) c->dwe_begin = c->ws + begin;
-    carve_slot(c, HSB_SLOT_MAIN, "main", c->cfg.max_points, 1, c->cfg.max_rays, true, dry);
-    carve_slot(c, HSB_SLOT_EIK, "eik", c->cfg.max_eik_points, c->K + 1, 0, false, dry);
-    carve_slot(c, HSB_SLOT_BG, "bg", c->cfg.max_bg_points, 1, c->cfg.max_bg_rays, false, dry);
+    carve_slot(c, HSB_SLOT_MAIN, "main", c->cfg.max_points, 1, c->cfg.max_rays, true, false, dry);
+    carve_slot(c, HSB_SLOT_EIK, "eik", c->cfg.max_eik_points, 3, 0, false, true, dry);
+    carve_slot(c, HSB_SLOT_BG, "bg", c->cfg.max_bg_points, 1, c->cfg.max_bg_rays, false, false, dry);
     carve_scratch(c, c->cfg.max_points, dry);
 }
 
@@ -212,7 +220,7 @@ static int chain_backward(Ctx* c, Slot& s, long long N, int nseed, bool with_rin
 }
 
 // ---- SDF net backward given dS [N,Kp] and the chain's extra terms dA1x / dA2x (may be absent) ----
-static int sdf_backward(Ctx* c, Slot& s, long long N, int nseed, bool have_chain, cudaStream_t st) {
+static int sdf_backward(Ctx* c, Slot& s, long long N, bool have_chain, cudaStream_t st) {
     const hsb_step_cfg& f = c->cfg;
     const int P = f.precise;
     const int rt = c->rtf();
@@ -228,8 +236,52 @@ static int sdf_backward(Ctx* c, Slot& s, long long N, int nseed, bool have_chain
     e = epi(EPI_NONE, s.dH0E, 32);
     TRY(gemm_tn(s.dA1, 256, c->W0eT + 39 * 256, 256, N, 32, 256, e, P, st));   // dE = (da1 W0)[:, 39:71]
     TRY(gemm_wgrad(s.dA1, 256, 256, s.H0, LD_H0, LD_H0, N, c->dW0e, LD_H0, fold ? nullptr : c->Gp(SEG_L0B), P, st));
-    TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dH0E, 32, have_chain ? s.Q0 + 39 : nullptr, LD_H0, have_chain ? s.dG : nullptr,
-                                (uint32_t)nseed, c->Gp(SEG_EMB), (uint32_t)N, f.L, f.S, f.H, st));
+    // second-order table term: reverse-mode slots pass (q0E, dg) of their single cotangent row, the tangent slot passes
+    // d(loss)/d(tangent seed) rows directly (dg = NULL, three rows per point)
+    const float* q0E = !have_chain ? nullptr : (s.tangent ? s.dU0 + 39 : s.Q0 + 39);
+    const float* dg = (have_chain && !s.tangent) ? s.dG : nullptr;
+    TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dH0E, 32, q0E, LD_H0, dg, s.tangent ? 3u : 1u, c->Gp(SEG_EMB), (uint32_t)N, f.L,
+                                f.S, f.H, st));
+    return HSB_OK;
+}
+
+// ---- forward-mode Jacobian of the SDF net at N points (eikonal slot):  J[d*N + p, :] = d sdf_raw[p, :] / d x_d ----
+//   u0_d = d h0/d x_d ; t1_d = (W0 u0_d) * sg1 ; t2_d = (W1 t1_d) * sg2 ; J[:, d] = W2 t2_d
+static int tangent_forward(Ctx* c, Slot& s, long long N, cudaStream_t st) {
+    const int P = c->cfg.precise;
+    const long long E = 3 * N;
+    const int rt = c->rtf();
+    TRY(launch_tangent_seed(s.H0, s.DY, N, s.U0, rt, st));
+    Epi e = epi(EPI_MUL_SIGMA, s.T1, 256, rt); e.aux = s.H1; e.lda = 256; e.aux_rows = N;
+    TRY(gemm_tn(s.U0, LD_H0, c->W0e, LD_H0, E, 256, LD_H0, e, P, st));
+    e = epi(EPI_MUL_SIGMA, s.T2, 256, rt); e.aux = s.H2; e.lda = 256; e.aux_rows = N;
+    TRY(gemm_tn(s.T1, 256, c->W1e, 256, E, 256, 256, e, P, st));
+    e = epi(EPI_NONE, s.J, c->Kp);
+    TRY(gemm_tn(s.T2, 256, c->W2e, 256, E, c->K, 256, e, P, st));
+    return HSB_OK;
+}
+
+// backward of tangent_forward given dJ [3N, Kp]:
+//   dt2 = W2^T dJ ; r2 = dt2*sg2 ; da2 += dt2*t2*100(1-sg2) ; dW2 += dJ t2^T
+//   dt1 = W1^T r2 ; r1 = dt1*sg1 ; da1 += dt1*t1*100(1-sg1) ; dW1 += r2 t1^T
+//   du0 = W0^T r1 ; dW0 += r1 u0^T ; d(table) += second-order scatter(du0_E)       (in sdf_backward)
+static int tangent_backward(Ctx* c, Slot& s, long long N, cudaStream_t st) {
+    const int P = c->cfg.precise;
+    const long long E = 3 * N;
+    const int rt = c->rtf();
+    cudaMemsetAsync(s.dA1x, 0, (size_t)N * 256 * sizeof(float), st);
+    cudaMemsetAsync(s.dA2x, 0, (size_t)N * 256 * sizeof(float), st);
+    Epi e = epi(EPI_BWD_CHAIN, s.R2, 256, rt);
+    e.aux = s.H2; e.lda = 256; e.aux_rows = N; e.aux2 = s.T2; e.lda2 = 256; e.out2 = s.dA2x; e.ldo2 = 256; e.atomic2 = 1;
+    TRY(gemm_tn(s.dJ, c->Kp, c->W2eT, c->Kp, E, 256, c->Kp, e, P, st));
+    TRY(gemm_wgrad(s.dJ, c->Kp, c->Kp, s.T2, 256, 256, E, c->dW2e, 256, nullptr, P, st));
+    e = epi(EPI_BWD_CHAIN, s.R1, 256, rt);
+    e.aux = s.H1; e.lda = 256; e.aux_rows = N; e.aux2 = s.T1; e.lda2 = 256; e.out2 = s.dA1x; e.ldo2 = 256; e.atomic2 = 1;
+    TRY(gemm_tn(s.R2, 256, c->W1eT, 256, E, 256, 256, e, P, st));
+    TRY(gemm_wgrad(s.R2, 256, 256, s.T1, 256, 256, E, c->dW1e, 256, nullptr, P, st));
+    e = epi(EPI_NONE, s.dU0, LD_H0);
+    TRY(gemm_tn(s.R1, 256, c->W0eT, 256, E, LD_H0, 256, e, P, st));
+    TRY(gemm_wgrad(s.R1, 256, 256, s.U0, LD_H0, LD_H0, E, c->dW0e, LD_H0, nullptr, P, st));
     return HSB_OK;
 }
 
@@ -342,6 +394,18 @@ extern "C" int hsb_finish(hsb_ctx* h, cudaStream_t st) {
     return HSB_OK;
 }
 
+// Camera rays of a pixel batch and the eikonal sample points (small per-ray kernels; see csrc/pointwise.cu)
+extern "C" int hsb_camera_rays(float* uv, const float* ray_offset, const float* pose, const float* intrinsics, int32_t R,
+                               float* ray_dirs, float* cam_loc, float* depth_scale, cudaStream_t st) {
+    if (!uv || !pose || !intrinsics || !ray_dirs || !cam_loc || !depth_scale || R < 0) { set_error("hsb_camera_rays: bad argument"); return HSB_ERR_ARG; }
+    return launch_camera_rays(uv, ray_offset, pose, intrinsics, R, ray_dirs, cam_loc, depth_scale, st);
+}
+extern "C" int hsb_eik_points(const float* uniform, const float* o, const float* d, const float* z_eik, const float* noise,
+                              int32_t n, float* out, cudaStream_t st) {
+    if (!uniform || !o || !d || !z_eik || !noise || !out || n < 0) { set_error("hsb_eik_points: bad argument"); return HSB_ERR_ARG; }
+    return launch_eik_points(uniform, o, d, z_eik, noise, n, out, st);
+}
+
 // SDF values (min over K, or one channel) at the points o + z d of a ray batch -- the sampler's no-grad queries
 // (model/ray_sampler.py:150-156).  Runs in its own scratch buffers ("samp.*"): the background-patch sampler is
 // called between the main pass forward and its backward and must not touch the saved activations.
@@ -414,12 +478,12 @@ extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_r
     TRY(launch_composite_bwd(a, g, st));
     if (scene) {
         // render net
-        TRY(launch_rgb_head_bwd(s.dO, c->R2e, s.U2, N, s.dU2, rt, st));
-        TRY(gemm_wgrad(s.dO, 4, 4, s.U2, 256, 256, N, c->dR2e, 256, c->dRB2e, P, st));
         const bool fold = (P == 0) && gemm_tc_available();
+        TRY(launch_rgb_head_bwd(s.dO, c->R2e, s.U2, N, s.dU2, rt, fold ? c->Gp(SEG_R1B) : nullptr, st));
+        TRY(gemm_wgrad(s.dO, 4, 4, s.U2, 256, 256, N, c->dR2e, 256, c->dRB2e, P, st));
         Epi e = epi(EPI_BWD_RELU, s.dU1, 256, rt); e.aux = s.U1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_R0B) : nullptr;
         TRY(gemm_tn(s.dU2, 256, c->R1eT, 256, N, 256, 256, e, P, st));
-        TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, c->Gp(SEG_R1B), P, st));
+        TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, fold ? nullptr : c->Gp(SEG_R1B), P, st));
         e = epi(EPI_NONE, s.dRIN + 54, LD_RIN);
         TRY(gemm_tn(s.dU1, 256, c->R0eT + 54 * 256, 256, N, 27, 256, e, P, st));     // d PE4(grad)
         e = epi(EPI_NONE, s.dFEAT, 256, rt); e.colsum = fold ? c->Gp(SEG_C1B) : nullptr;
@@ -435,7 +499,7 @@ extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_r
         TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dEC, 32, nullptr, 0, nullptr, 1, c->Gp(SEG_CEMB), (uint32_t)N, f.L, f.S, f.H, st));
     }
     TRY(chain_backward(c, s, N, 1, scene, st));
-    TRY(sdf_backward(c, s, N, 1, true, st));
+    TRY(sdf_backward(c, s, N, true, st));
     return HSB_OK;
 }
 
@@ -446,14 +510,13 @@ extern "C" int hsb_eikonal_forward(hsb_ctx* h, const float* x, int64_t Ne, float
     Ctx* c = reinterpret_cast<Ctx*>(h);
     Slot& s = c->slot[HSB_SLOT_EIK];
     if (Ne > s.cap_points || !x || !grad_theta) { set_error("hsb_eikonal_forward: batch exceeds max_eik_points / null pointer"); return HSB_ERR_ARG; }
-    const int ns = c->K + 1;
-    s.N = Ne; s.nseed = ns;
+    s.N = Ne; s.nseed = 3;
     cudaMemcpyAsync(s.X, x, (size_t)Ne * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st);
     TRY(launch_points_pe(s.X, Ne, s.H0, c->rtf(), st));
     TRY(sdf_forward(c, s, Ne, true, st));
     TRY(launch_sdf_min(s.SR, Ne, c->K, c->Kp, -1, s.SDF, s.KS, st));
-    TRY(chain_forward(c, s, Ne, ns, st));
-    cudaMemcpyAsync(grad_theta, s.G, (size_t)Ne * ns * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    TRY(tangent_forward(c, s, Ne, st));
+    TRY(launch_jac_to_grad(s.J, s.KS, Ne, c->K, c->Kp, grad_theta, st));
     if (sample_sdf)
         cudaMemcpy2DAsync(sample_sdf, (size_t)c->K * sizeof(float), s.SR, (size_t)c->Kp * sizeof(float), (size_t)c->K * sizeof(float),
                           (size_t)Ne, cudaMemcpyDeviceToDevice, st);
@@ -466,13 +529,12 @@ extern "C" int hsb_eikonal_backward(hsb_ctx* h, const float* d_grad_theta, const
     Slot& s = c->slot[HSB_SLOT_EIK];
     if (s.N == 0 || !d_grad_theta) { set_error("hsb_eikonal_backward: no forward recorded / null gradient"); return HSB_ERR_ARG; }
     const long long Ne = s.N;
-    const int ns = s.nseed;
-    cudaMemcpyAsync(s.dG, d_grad_theta, (size_t)Ne * ns * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    TRY(launch_grad_to_jac(d_grad_theta, s.KS, Ne, c->K, c->Kp, s.dJ, c->rtf(), st));
     cudaMemsetAsync(s.dS, 0, (size_t)Ne * c->Kp * sizeof(float), st);
     if (d_sample_sdf)
         cudaMemcpy2DAsync(s.dS, (size_t)c->Kp * sizeof(float), d_sample_sdf, (size_t)c->K * sizeof(float), (size_t)c->K * sizeof(float),
                           (size_t)Ne, cudaMemcpyDeviceToDevice, st);
-    TRY(chain_backward(c, s, Ne, ns, false, st));
-    TRY(sdf_backward(c, s, Ne, ns, true, st));
+    TRY(tangent_backward(c, s, Ne, st));
+    TRY(sdf_backward(c, s, Ne, true, st));
     return HSB_OK;
 }

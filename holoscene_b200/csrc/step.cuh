@@ -40,8 +40,15 @@ int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long 
 int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN, int rtf, cudaStream_t st);
 int launch_chain_end_bwd(float* dG, const float* dRIN, const float* RIN, const float* H0, const float* DY, long long N, int nseed, float* dQ0, int rtf, cudaStream_t st);
 int launch_rgb_head(const float* U2, const float* R2e, const float* bias, long long N, float* RGB, cudaStream_t st);
-int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, int rtf, cudaStream_t st);
+int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, int rtf, float* colsum, cudaStream_t st);
 int launch_scatter_rows(const float* dQ2, const int* kstar, long long N, int K, int Kp, int nseed, float* dW2e, cudaStream_t st);
+int launch_tangent_seed(const float* H0, const float* DY, long long N, float* U0, int rtf, cudaStream_t st);
+int launch_jac_to_grad(const float* J, const int* kstar, long long N, int K, int Kp, float* G, cudaStream_t st);
+int launch_grad_to_jac(const float* dG, const int* kstar, long long N, int K, int Kp, float* dJ, int rtf, cudaStream_t st);
+int launch_camera_rays(float* uv, const float* offset, const float* pose, const float* K, int R, float* dirs, float* cam_loc,
+                       float* depth_scale, cudaStream_t st);
+int launch_eik_points(const float* uniform, const float* o, const float* d, const float* z_eik, const float* noise, int n, float* out,
+                      cudaStream_t st);
 int launch_add_min_grad(const float* dsdf, const int* kstar, long long N, int Kp, float* dS, cudaStream_t st);
 int launch_composite_fwd(const CompositeArgs& a, cudaStream_t st);
 int launch_composite_bwd(const CompositeArgs& a, const CompositeGrads& g, cudaStream_t st);

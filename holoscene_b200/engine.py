@@ -59,6 +59,8 @@ sampler_init = declare("hsb_sampler_init", [_vp, _vp, i32, i32, c_f32, c_f32, c_
 sampler_bound = declare("hsb_sampler_bound", [_vp, _vp, i32, _vp, _vp, i32, _vp, _vp, _vp, _vp, c_f32, c_f32, i32, i32, _vp, c_stream])
 sampler_resample = declare("hsb_sampler_resample", [_vp, _vp, i32, _vp, i32, _vp, i32, c_f32, i32, _vp, c_stream])
 sampler_finalize = declare("hsb_sampler_finalize", [_vp, i32, _vp, i32, _vp, i32, c_f32, c_f32, _vp, i32, _vp, _vp, c_stream])
+_camera_rays = declare("hsb_camera_rays", [_vp, _vp, _vp, _vp, i32, _vp, _vp, _vp, c_stream])
+_eik_points = declare("hsb_eik_points", [_vp, _vp, _vp, _vp, _vp, i32, _vp, c_stream])
 gemm_tn = declare("hsb_gemm_tn", [_vp, c_ll, _vp, c_ll, c_ll, c_int, c_int, c_int, _vp, c_ll, _vp, _vp, c_ll, c_ll, _vp, c_ll,
                                   _vp, c_ll, c_int, c_int, c_stream])
 gemm_wgrad = declare("hsb_gemm_wgrad", [_vp, c_ll, c_int, _vp, c_ll, c_int, c_ll, _vp, c_ll, _vp, c_int, c_stream])
@@ -91,6 +93,33 @@ def fused_loss(cfg: LossCfg, rgb_values, depth_values, normal_map, opacity, sdf,
                 ptr(rgb_gt), ptr(depth_gt), ptr(normal_gt), ptr(mask_gt), ptr(segs), ptr(d_rgb), ptr(d_depth), ptr(d_normal),
                 ptr(d_opacity), ptr(d_grad), ptr(scratch), ptr(losses), stream()))
     return losses, d_rgb, d_depth, d_normal, d_opacity, d_grad
+
+
+def camera_rays(uv, pose, intrinsics, ray_offset=None):
+    """hsb_camera_rays: uv [1,R,2] (updated in place, += 2*ray_offset as the reference does) -> ray_dirs [R,3], cam_loc [R,3],
+    depth_scale [R,1]."""
+    if uv.shape[0] != 1 or pose.shape[-2:] != (4, 4):
+        raise _lib.HsbError("hsb_camera_rays: batch size 1 and 4x4 poses only (the Stage-1 trainer's layout)")
+    if not uv.is_contiguous() or uv.dtype != torch.float32:
+        raise _lib.HsbError("hsb_camera_rays: uv must be a contiguous float32 tensor (it is updated in place)")
+    R = uv.shape[1]
+    dev = uv.device
+    dirs = torch.empty(R, 3, device=dev)
+    cam = torch.empty(R, 3, device=dev)
+    ds = torch.empty(R, 1, device=dev)
+    off = None if ray_offset is None else ray_offset.reshape(R, 2).float().contiguous()
+    check(_camera_rays(ptr(uv), ptr(off), ptr(pose.reshape(16).float().contiguous()), ptr(intrinsics.reshape(16).float().contiguous()),
+                       R, ptr(dirs), ptr(cam), ptr(ds), stream()))
+    return dirs, cam, ds
+
+
+def eik_points(uniform, o, d, z_eik, noise):
+    """hsb_eik_points: [uniform | o + z_eik d | both + (noise - 0.5) * 0.01]  -> [4n, 3]."""
+    n = uniform.shape[0]
+    out = torch.empty(4 * n, 3, device=uniform.device)
+    check(_eik_points(ptr(uniform.contiguous()), ptr(o), ptr(d), ptr(z_eik.reshape(n).contiguous()), ptr(noise.contiguous()), n,
+                      ptr(out), stream()))
+    return out
 
 
 def param_layout(K: int, table_rows: int) -> list[int]:

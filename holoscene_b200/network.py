@@ -281,13 +281,10 @@ class HoloSceneNetwork(nn.Module):
             self._attach_grads()
         eng.prepare()
         ray_offset = draws.rand("ray_offset", uv.shape) - 0.5 if training else None
-        ray_dirs, cam_loc = rend_util.get_camera_params(uv, pose, intrinsics, ray_offset=ray_offset)
-        # second call with the identity pose: unnormalised z of the (again jittered) pixel -> depth scale
-        ray_dirs_tmp, _ = rend_util.get_camera_params(uv, torch.eye(4, device=dev)[None], intrinsics, ray_offset=ray_offset)
-        depth_scale = ray_dirs_tmp[0, :, 2:].contiguous()
-        batch_size, num_pixels, _ = ray_dirs.shape
-        cam_loc = cam_loc.unsqueeze(1).repeat(1, num_pixels, 1).reshape(-1, 3).contiguous()
-        ray_dirs = ray_dirs.reshape(-1, 3).contiguous()
+        # one kernel for both get_camera_params calls of the reference (real pose -> ray_dirs; identity pose on the again-
+        # jittered pixel -> depth scale), including the in-place shift of uv (network.py:788-792, rend_util.py:70-75)
+        ray_dirs, cam_loc, depth_scale = _engine.camera_rays(uv, pose, intrinsics, ray_offset)
+        batch_size, num_pixels = uv.shape[0], uv.shape[1]
         R = ray_dirs.shape[0]
 
         if self.phase_ms is not None:
@@ -312,11 +309,9 @@ class HoloSceneNetwork(nn.Module):
         gt = ssdf = smin = None
         if training:
             n_eik = batch_size * num_pixels
-            eik = draws.uniform("eik_uniform", (n_eik, 3), -self.scene_bounding_sphere, self.scene_bounding_sphere)
-            near_pts = (cam_loc.unsqueeze(1) + z_samples_eik.unsqueeze(2) * ray_dirs.unsqueeze(1)).reshape(-1, 3)
-            eik = torch.cat([eik, near_pts], 0)
-            nei = eik + (draws.rand("nei_noise", eik.shape) - 0.5) * 0.01
-            eik = torch.cat([eik, nei], 0).contiguous()
+            uni = draws.uniform("eik_uniform", (n_eik, 3), -self.scene_bounding_sphere, self.scene_bounding_sphere)
+            noise = draws.rand("nei_noise", (2 * n_eik, 3))
+            eik = _engine.eik_points(uni, cam_loc, ray_dirs, z_samples_eik, noise)   # [uniform | near-surface | both + jitter]
             self._last_ne = eik.shape[0]
             gt, ssdf, smin = eng.eikonal_forward(eik)
             output["sample_minsdf"] = smin
@@ -329,11 +324,7 @@ class HoloSceneNetwork(nn.Module):
             y0 = draws.np_randint("patch_y0", int(cy_2) - ps + 1)
             gx, gy = np.meshgrid(np.arange(ps), np.arange(ps), indexing="xy")
             uv0 = torch.from_numpy(np.stack([gx + x0, gy + y0], -1).reshape(1, -1, 2)).float().to(dev)
-            d0, c0 = rend_util.get_camera_params(uv0, pose, intrinsics)
-            d0t, _ = rend_util.get_camera_params(uv0, torch.eye(4, device=dev)[None], intrinsics)
-            ds0 = d0t[0, :, 2:].contiguous()
-            c0 = c0.unsqueeze(1).repeat(1, d0.shape[1], 1).reshape(-1, 3).contiguous()
-            d0 = d0.reshape(-1, 3).contiguous()
+            d0, c0, ds0 = _engine.camera_rays(uv0.contiguous(), pose, intrinsics)
             bz, _ = self.ray_sampler.get_z_vals(d0, c0, self, idx=0)
             bz = bz.contiguous()
             _, bdepth, bnmap, _, bsem = eng.render_forward(_engine.SLOT_BG, c0, d0, bz, ds0, rot)

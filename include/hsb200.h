@@ -74,7 +74,9 @@ int hsb_hash_second_backward(const float* grad, long long g_level_stride, long l
                              uint32_t B, uint32_t L, float S, uint32_t H, int map01, hsb_stream_t stream);
 
 /* Train-step scatter: first-order (dE) and second-order (sum over nseed of q0E (x) dg) table
- * gradients in one pass; x_world in [-1,1].  Either dE or (q0E, dg) may be NULL. */
+ * gradients in one pass; x_world in [-1,1].  Either dE or (q0E, dg) may be NULL.  dg == NULL with
+ * q0E != NULL and nseed == 3 selects the forward-mode form used by the eikonal pass: row d*B+p of q0E
+ * is d(loss)/d(d h0[p] / d x_d), the coefficient of dy_dx[p, :, d, :] itself. */
 int hsb_hash_backward_fused(const float* x_world, const int32_t* offsets, const float* dE, long long e_point_stride,
                             const float* q0E, long long q_point_stride, const float* dg, uint32_t nseed,
                             float* grad_embeddings, uint32_t B, uint32_t L, float S, uint32_t H,
@@ -138,6 +140,16 @@ int hsb_ctx_buffer(hsb_ctx* ctx, const char* name, int64_t* offset_bytes, int64_
 int hsb_prepare(hsb_ctx* ctx, hsb_stream_t stream);
 /* weight_norm backward + bias fix-ups into the flat gradient buffer; call once after all *_backward. */
 int hsb_finish(hsb_ctx* ctx, hsb_stream_t stream);
+
+/* Camera rays of one pixel batch (utils/rend_util.py:56-98,112-125 as called twice by model/network.py:788-792).
+ * uv [R,2] pixel coordinates, UPDATED IN PLACE like the reference does (uv += 2*ray_offset; ray_offset [R,2] may be NULL),
+ * pose [4,4] camera-to-world, intrinsics [4,4], both row-major.  ray_dirs [R,3] unit world directions of uv + ray_offset,
+ * cam_loc [R,3] the camera centre repeated, depth_scale [R] = z of the unit camera-space direction of uv + 2*ray_offset. */
+int hsb_camera_rays(float* uv, const float* ray_offset, const float* pose, const float* intrinsics, int32_t R,
+                    float* ray_dirs, float* cam_loc, float* depth_scale, hsb_stream_t stream);
+/* Eikonal sample points (model/network.py:843-858): out [4n,3] = [uniform [n,3] | o + z_eik d | both + (noise [2n,3] - 0.5)*0.01]. */
+int hsb_eik_points(const float* uniform, const float* o, const float* d, const float* z_eik, const float* noise, int32_t n,
+                   float* out, hsb_stream_t stream);
 
 /* No-grad SDF at the points o[r] + z[r,i] d[r]: min over the K channels (channel < 0) or one channel.
  * Replaces implicit_network.get_sdf_vals / get_object_sdf_vals inside the sampler (ray_sampler.py:150-156). */

@@ -85,7 +85,7 @@ def test_gemm_tn_chain_epilogues(precise):
 
 
 @pytest.mark.parametrize("M,N1,N2", [(5000, 256, 72), (33, 256, 344), (100000, 32, 256), (777, 4, 256), (4096, 256, 32),
-                                     (70001, 256, 256), (1300, 8, 256), (9000, 256, 344)])
+                                     (70001, 256, 256), (1300, 8, 256), (9000, 256, 344), (49152, 24, 256), (3001, 40, 72)])
 @pytest.mark.parametrize("precise", [1, 2, 0])
 def test_gemm_wgrad(M, N1, N2, precise):
     from holoscene_b200 import _lib, engine

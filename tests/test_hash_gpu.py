@@ -122,6 +122,20 @@ def test_fused_layout_and_fused_scatter():
                                         3, _lib.ptr(got), B, L, c["S"], c["H"], _lib.stream()))
     torch.cuda.synchronize()
     assert common.rel_err(got.cpu(), want_t) < 5e-4
+    # forward-mode form (eikonal pass): dg = NULL, nseed = 3 -- row s*B+p of q0E is the cotangent of d h0[p]/d x_s itself,
+    # i.e. a second-order backward with the unit seed ggx = e_s / 2
+    want_u = torch.zeros_like(c["emb"])
+    for s in range(3):
+        gg = torch.zeros(L, B, 2)
+        e_s = torch.zeros(B, 3)
+        e_s[:, s] = 0.5
+        ohg.hash_encode_second_backward(q0[s * B:(s + 1) * B, 39:71].reshape(B, L, 2).permute(1, 0, 2).contiguous(), x01.cpu(),
+                                        c["emb"], c["offsets"], B, 3, 2, L, c["S"], c["H"], True, o["dy_dx"], e_s, gg, want_u)
+    got = torch.zeros_like(emb)
+    _lib.check(_lib.hash_backward_fused(_lib.ptr(xw), _lib.ptr(offs), None, 32, ctypes_off(q0c, 39), 72, None, 3, _lib.ptr(got), B, L,
+                                        c["S"], c["H"], _lib.stream()))
+    torch.cuda.synchronize()
+    assert common.rel_err(got.cpu(), want_u) < 5e-4
 
 
 def ctypes_off(t, col):

@@ -309,3 +309,42 @@ def test_sampler_kernels_match_tensor_op_sampler(training):
         assert float((e_a - e_b).abs().max()) < 3e-4
         assert bool((z_a[:, 1:] >= z_a[:, :-1]).all())                 # sorted
         assert float(z_a[:, 0].abs().max()) == 0.0 and float((z_a[:, -1] - 3.5).abs().max()) == 0.0   # near / far appended
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_camera_rays_kernel_matches_reference_call_sequence(training):
+    """hsb_camera_rays against the reference's two get_camera_params calls (real pose, then identity pose on the again-jittered
+    pixels; rend_util.py:56-98 restated in holoscene_b200/rend_util.py), including the in-place shift of uv."""
+    from holoscene_b200 import engine as E, rend_util, synthetic
+    Kmat, pose = synthetic.camera()
+    gen = torch.Generator().manual_seed(5)
+    rot = torch.linalg.qr(torch.randn(3, 3, generator=gen))[0]
+    pose = pose.clone()
+    pose[0, :3, :3] = rot
+    Kmat = Kmat.clone()
+    Kmat[0, 0, 1] = 0.7                                        # non-zero skew exercises the whole lift formula
+    uv = (torch.rand(1, 777, 2, generator=gen) * 512).cuda()
+    off = (torch.rand(1, 777, 2, generator=gen) - 0.5).cuda() if training else None
+    uv_a, uv_b = uv.clone(), uv.clone()
+    d_ref, c_ref = rend_util.get_camera_params(uv_a, pose.cuda(), Kmat.cuda(), ray_offset=off)
+    d_tmp, _ = rend_util.get_camera_params(uv_a, torch.eye(4, device="cuda")[None], Kmat.cuda(), ray_offset=off)
+    d, c, ds = E.camera_rays(uv_b, pose.cuda(), Kmat.cuda(), off)
+    torch.cuda.synchronize()
+    assert float((d - d_ref[0]).abs().max()) < 5e-6
+    assert float((c - c_ref.expand(777, 3)).abs().max()) == 0.0
+    assert float((ds - d_tmp[0, :, 2:]).abs().max()) < 5e-6
+    assert float((uv_a - uv_b).abs().max()) < 1e-4            # same in-place side effect (uv += 2 * offset)
+
+
+def test_eik_points_kernel():
+    from holoscene_b200 import engine as E
+    gen = torch.Generator().manual_seed(6)
+    n = 333
+    uni, o, d = (torch.rand(n, 3, generator=gen).cuda() * 2 - 1 for _ in range(3))
+    z = torch.rand(n, 1, generator=gen).cuda() * 3
+    noise = torch.rand(2 * n, 3, generator=gen).cuda()
+    got = E.eik_points(uni, o, d, z, noise)
+    first = torch.cat([uni, o + z * d], 0)
+    want = torch.cat([first, first + (noise - 0.5) * 0.01], 0)
+    assert got.shape == (4 * n, 3)
+    assert float((got - want).abs().max()) < 1e-6
