@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(256) hash_bwd2_kernel(const float* __restrict_
 //   q0E  [nseed*B, *] row stride q_ps  (seed s, point p -> row s*B+p)
 //   dg   [nseed*B, 3]; NULL with nseed == 3: q0E rows are forward-mode tangent cotangents (seed s = unit vector e_s)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) hash_bwd_fused_kernel(const float* __restrict__ x, const int* __restrict__ offsets,
+constexpr int HBF_THREADS = 128;   // small CTAs (no shared memory, ~7k registers)
+__global__ void __launch_bounds__(HBF_THREADS) hash_bwd_fused_kernel(const float* __restrict__ x, const int* __restrict__ offsets,
                                                              const float* __restrict__ dE, long long e_ps,
                                                              const float* __restrict__ q0E, long long q_ps,
                                                              const float* __restrict__ dg, uint32_t nseed,
@@ -456,8 +457,8 @@ extern "C" int hsb_hash_backward_fused(const float* x_world, const int32_t* offs
                                        cudaStream_t stream) {
     if (B == 0) return HSB_OK;
     if (!x_world || !offsets || !grad_embeddings || L == 0 || L > 32 || (q0E && !dg && nseed != 3)) { set_error("hsb_hash_backward_fused: bad argument"); return HSB_ERR_ARG; }
-    dim3 grid(cdiv(B, 256), L);
-    hash_bwd_fused_kernel<<<grid, 256, 0, stream>>>(x_world, offsets, dE, e_point_stride, q0E, q_point_stride, dg, nseed,
+    dim3 grid(cdiv(B, HBF_THREADS), L);
+    hash_bwd_fused_kernel<<<grid, HBF_THREADS, 0, stream>>>(x_world, offsets, dE, e_point_stride, q0E, q_point_stride, dg, nseed,
                                                     reinterpret_cast<float2*>(grad_embeddings), B, L, S, H);
     return check_launch("hsb_hash_backward_fused");
 }

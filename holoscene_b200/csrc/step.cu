@@ -162,6 +162,7 @@ static void carve_all(Ctx* c, bool dry) {
 
 #define TRY(x) do { int _e = (x); if (_e != HSB_OK) return _e; } while (0)
 
+
 static Epi epi(int kind, float* out, long long ldo, int round_out = 0) {
     Epi e{}; e.kind = kind; e.out = out; e.ldo = ldo; e.round_out = round_out; return e;
 }

@@ -160,11 +160,12 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_rgb, d_depth, d_normal, d_opacity, d_gt, d_ssdf, d_bg_depth, d_bg_normal):
         eng = ctx.model.engine()
+        # scene pass first: its table scatters run on libhsb200's side stream underneath the eikonal pass's contractions
+        eng.render_backward(_engine.SLOT_MAIN, d_rgb, d_depth, d_normal, d_opacity)
         if ctx.has_eik and (d_gt is not None or d_ssdf is not None):
             if d_gt is None:
                 d_gt = torch.zeros((eng.K + 1) * ctx.model._last_ne, 3, device=eng.device)
             eng.eikonal_backward(d_gt, d_ssdf)
-        eng.render_backward(_engine.SLOT_MAIN, d_rgb, d_depth, d_normal, d_opacity)
         if ctx.has_bg and (d_bg_depth is not None or d_bg_normal is not None):
             eng.render_backward(_engine.SLOT_BG, None, d_bg_depth, d_bg_normal, None)
         eng.finish()
