@@ -372,14 +372,20 @@ __global__ void __launch_bounds__(256) rgb_head_kernel(const float* __restrict__
     }
 }
 
-// dU2[p,j] = (sum_c dO[p,c] R2e[c,j]) * [U2[p,j] > 0];  optionally colsum[j] += sum_p dU2[p,j] (the lin1 bias gradient of the
-// render net, taken here so that dU2 is not re-read by a separate column-sum pass).  A CTA owns 128 rows: thread = (row lane
-// 0..3, float4 column group 0..63), 32 rows per thread, four rows in flight.
+// dU2[p,j] = (sum_c dO[p,c] R2e[c,j]) * [U2[p,j] > 0].  With FOLD the kernel also takes, from the rows it has in registers anyway,
+//   colsum[j] += sum_p dU2[p,j]            (lin1 bias gradient of the render net)
+//   dR2e[c,j] += sum_p dO[p,c] U2[p,j]     (lin2 effective-weight gradient)      dRB2e[c] += sum_p dO[p,c]   (lin2 bias gradient)
+// so neither dU2 nor U2 is re-read by a column-sum pass / a 4-row wgrad contraction.  A CTA owns 128 rows: thread = (row lane
+// 0..3, float4 column group 0..63), 32 rows per thread, four rows in flight; partial sums meet in shared memory, one atomic
+// per column per CTA.
 constexpr int RHB_ROWS = 128;
+template <bool FOLD>
 __global__ void __launch_bounds__(256) rgb_head_bwd_kernel(const float* __restrict__ dO, const float* __restrict__ R2e,
                                                            const float* __restrict__ U2, long long N, float* __restrict__ dU2, int rtf,
-                                                           float* __restrict__ colsum) {
-    __shared__ float4 red[256];
+                                                           float* __restrict__ colsum, float* __restrict__ dR2e,
+                                                           float* __restrict__ dRB2e) {
+    __shared__ float4 red[FOLD ? 4 * 256 : 1];
+    __shared__ float redb[FOLD ? 4 * 4 : 1];
     const int j = threadIdx.x & 63, ry = threadIdx.x >> 6;
     const float4 w0 = reinterpret_cast<const float4*>(R2e)[j];
     const float4 w1 = reinterpret_cast<const float4*>(R2e + 256)[j];
@@ -387,6 +393,8 @@ __global__ void __launch_bounds__(256) rgb_head_bwd_kernel(const float* __restri
     const long long p0 = (long long)blockIdx.x * RHB_ROWS;
     const long long p1 = min(N, p0 + RHB_ROWS);
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a0 = cs, a1 = cs, a2 = cs;                    // dR2e rows 0..2, columns 4j..4j+3
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;                   // dRB2e (lanes with j == 0 only)
     for (long long pb = p0 + ry; pb < p1; pb += 16) {
         float4 g[4], u[4];
 #pragma unroll
@@ -407,20 +415,30 @@ __global__ void __launch_bounds__(256) rgb_head_bwd_kernel(const float* __restri
                 r.z = u[i].z > 0.f ? rtf32(g[i].x * w0.z + g[i].y * w1.z + g[i].z * w2.z, rtf) : 0.f;
                 r.w = u[i].w > 0.f ? rtf32(g[i].x * w0.w + g[i].y * w1.w + g[i].z * w2.w, rtf) : 0.f;
                 reinterpret_cast<float4*>(dU2 + p * 256)[j] = r;
-                cs.x += r.x; cs.y += r.y; cs.z += r.z; cs.w += r.w;
+                if (FOLD) {
+                    cs.x += r.x; cs.y += r.y; cs.z += r.z; cs.w += r.w;
+                    a0.x += g[i].x * u[i].x; a0.y += g[i].x * u[i].y; a0.z += g[i].x * u[i].z; a0.w += g[i].x * u[i].w;
+                    a1.x += g[i].y * u[i].x; a1.y += g[i].y * u[i].y; a1.z += g[i].y * u[i].z; a1.w += g[i].y * u[i].w;
+                    a2.x += g[i].z * u[i].x; a2.y += g[i].z * u[i].y; a2.z += g[i].z * u[i].z; a2.w += g[i].z * u[i].w;
+                    b0 += g[i].x; b1 += g[i].y; b2 += g[i].z;
+                }
             }
         }
     }
-    if (!colsum) return;
-    red[threadIdx.x] = cs;
+    if (!FOLD) return;
+    red[threadIdx.x] = cs; red[256 + threadIdx.x] = a0; red[512 + threadIdx.x] = a1; red[768 + threadIdx.x] = a2;
+    if (j == 0) { redb[ry * 4] = b0; redb[ry * 4 + 1] = b1; redb[ry * 4 + 2] = b2; }
     __syncthreads();
-    if (ry == 0) {
-        const float4 a = red[j], b = red[64 + j], c = red[128 + j], d = red[192 + j];
-        atomicAdd(colsum + 4 * j, (a.x + b.x) + (c.x + d.x));
-        atomicAdd(colsum + 4 * j + 1, (a.y + b.y) + (c.y + d.y));
-        atomicAdd(colsum + 4 * j + 2, (a.z + b.z) + (c.z + d.z));
-        atomicAdd(colsum + 4 * j + 3, (a.w + b.w) + (c.w + d.w));
+    {   // 256 threads: thread (k = ry, j) reduces quantity k (colsum, dR2e row 0..2) of column group j over the four row lanes
+        const float4* q = red + ry * 256;
+        const float4 a = q[j], b = q[64 + j], c = q[128 + j], d = q[192 + j];
+        float* dst = (ry == 0 ? colsum : dR2e + (ry - 1) * 256) + 4 * j;
+        atomicAdd(dst, (a.x + b.x) + (c.x + d.x));
+        atomicAdd(dst + 1, (a.y + b.y) + (c.y + d.y));
+        atomicAdd(dst + 2, (a.z + b.z) + (c.z + d.z));
+        atomicAdd(dst + 3, (a.w + b.w) + (c.w + d.w));
     }
+    if (threadIdx.x < 3) atomicAdd(dRB2e + threadIdx.x, (redb[threadIdx.x] + redb[4 + threadIdx.x]) + (redb[8 + threadIdx.x] + redb[12 + threadIdx.x]));
 }
 
 // dW2e[key(m), :] += dQ2[m, :]   with key = seed s (< K) or kstar[p]; rows m = s*N + p.
@@ -583,9 +601,10 @@ int launch_rgb_head(const float* U2, const float* R2e, const float* bias, long l
     return check_launch("rgb_head");
 }
 int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, int rtf, float* colsum,
-                        cudaStream_t st) {
+                        float* dR2e, float* dRB2e, cudaStream_t st) {
     if (N == 0) return HSB_OK;
-    rgb_head_bwd_kernel<<<cdiv(N, RHB_ROWS), 256, 0, st>>>(dO, R2e, U2, N, dU2, rtf, colsum);
+    if (colsum && dR2e && dRB2e) rgb_head_bwd_kernel<true><<<cdiv(N, RHB_ROWS), 256, 0, st>>>(dO, R2e, U2, N, dU2, rtf, colsum, dR2e, dRB2e);
+    else rgb_head_bwd_kernel<false><<<cdiv(N, RHB_ROWS), 256, 0, st>>>(dO, R2e, U2, N, dU2, rtf, nullptr, nullptr, nullptr);
     return check_launch("rgb_head_bwd");
 }
 int launch_scatter_rows(const float* dQ2, const int* kstar, long long N, int K, int Kp, int nseed, float* dW2e,

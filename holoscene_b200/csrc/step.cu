@@ -480,8 +480,10 @@ extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_r
     if (scene) {
         // render net
         const bool fold = (P == 0) && gemm_tc_available();
-        TRY(launch_rgb_head_bwd(s.dO, c->R2e, s.U2, N, s.dU2, rt, fold ? c->Gp(SEG_R1B) : nullptr, st));
-        TRY(gemm_wgrad(s.dO, 4, 4, s.U2, 256, 256, N, c->dR2e, 256, c->dRB2e, P, st));
+        // fast mode: lin1 bias gradient, lin2 weight and bias gradients are taken inside rgb_head_bwd (no extra pass over U2 / dU2)
+        TRY(launch_rgb_head_bwd(s.dO, c->R2e, s.U2, N, s.dU2, rt, fold ? c->Gp(SEG_R1B) : nullptr, fold ? c->dR2e : nullptr,
+                                fold ? c->dRB2e : nullptr, st));
+        if (!fold) TRY(gemm_wgrad(s.dO, 4, 4, s.U2, 256, 256, N, c->dR2e, 256, c->dRB2e, P, st));
         Epi e = epi(EPI_BWD_RELU, s.dU1, 256, rt); e.aux = s.U1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_R0B) : nullptr;
         TRY(gemm_tn(s.dU2, 256, c->R1eT, 256, N, 256, 256, e, P, st));
         TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, fold ? nullptr : c->Gp(SEG_R1B), P, st));

@@ -40,7 +40,8 @@ int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long 
 int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN, int rtf, cudaStream_t st);
 int launch_chain_end_bwd(float* dG, const float* dRIN, const float* RIN, const float* H0, const float* DY, long long N, int nseed, float* dQ0, int rtf, cudaStream_t st);
 int launch_rgb_head(const float* U2, const float* R2e, const float* bias, long long N, float* RGB, cudaStream_t st);
-int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, int rtf, float* colsum, cudaStream_t st);
+int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, int rtf, float* colsum, float* dR2e,
+                        float* dRB2e, cudaStream_t st);
 int launch_scatter_rows(const float* dQ2, const int* kstar, long long N, int K, int Kp, int nseed, float* dW2e, cudaStream_t st);
 int launch_tangent_seed(const float* H0, const float* DY, long long N, float* U0, int rtf, cudaStream_t st);
 int launch_jac_to_grad(const float* J, const int* kstar, long long N, int K, int Kp, float* G, cudaStream_t st);
