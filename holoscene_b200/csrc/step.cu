@@ -417,6 +417,13 @@ extern "C" int hsb_sdf_values(hsb_ctx* h, const float* o, const float* d, const 
     const long long N = (long long)R * S;
     if (N > s.cap_points || channel >= c->K) { set_error("hsb_sdf_values: batch exceeds max_points / bad channel"); return HSB_ERR_ARG; }
     TRY(launch_ray_points(o, d, z, R, S, s.X, s.H0, nullptr, c->rtf(), st));
+    if (!c->cfg.precise && sdf_trunk_tc_eligible(c->K)) {
+        // fast mode: hash features -> H0, then ONE kernel for the three layers and the min (hidden activations stay in TMEM)
+        const hsb_step_cfg& f = c->cfg;
+        TRY(hash_forward_ex(s.X, c->P(SEG_EMB), c->hoffs, s.H0 + 39, 2, LD_H0, nullptr, 96, (uint32_t)N, f.L, f.S, f.H, 1, 1, st));
+        return sdf_trunk_tc(s.H0, N, c->W0e, c->W1e, c->W2e, c->P(SEG_L0B), c->P(SEG_L1B), c->P(SEG_L2B), c->K, c->Kp, channel, sdf_out,
+                            s.SR, st);
+    }
     TRY(sdf_forward(c, s, N, false, st));
     TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, channel, sdf_out, nullptr, st));
     return HSB_OK;

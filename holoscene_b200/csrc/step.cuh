@@ -54,6 +54,11 @@ int launch_add_min_grad(const float* dsdf, const int* kstar, long long N, int Kp
 int launch_composite_fwd(const CompositeArgs& a, cudaStream_t st);
 int launch_composite_bwd(const CompositeArgs& a, const CompositeGrads& g, cudaStream_t st);
 
+// trunk_tc.cu: fused no-grad SDF trunk (three layers + min over objects in one tcgen05 kernel, activations in tensor memory)
+bool sdf_trunk_tc_eligible(int K);
+int sdf_trunk_tc(const float* H0, long long N, const float* W0e, const float* W1e, const float* W2e, const float* b0, const float* b1,
+                 const float* b2, int K, int Kp, int channel, float* sdf, float* sr, cudaStream_t stream);
+
 // optim.cu
 int launch_wn_forward(const float* v, const float* g, int rows, int cols, float* We, int ldw, float* WeT, int ldt, int rtf, cudaStream_t st);
 int launch_wn_backward(const float* dWe, int ldw, const float* v, const float* g, int rows, int cols, float* dv, float* dg, cudaStream_t st);

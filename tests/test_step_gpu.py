@@ -348,3 +348,33 @@ def test_eik_points_kernel():
     want = torch.cat([first, first + (noise - 0.5) * 0.01], 0)
     assert got.shape == (4 * n, 3)
     assert float((got - want).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("K,R,S,channel", [(3, 50, 33, -1), (3, 64, 98, 0), (32, 1, 100, -1), (32, 300, 128, -1), (64, 77, 64, 5), (21, 4096, 128, -1)])
+def test_fused_sdf_trunk_matches_layer_by_layer_path(K, R, S, channel):
+    """hsb_sdf_values in the fast mode = ONE tcgen05 kernel for the three SDF layers + min over objects, hidden activations
+    chained through tensor memory (csrc/trunk_tc.cu).  It must reproduce the layer-by-layer contraction path (the scene pass
+    of hsb_render_forward on the same points: same TF32-rounded operands, same accumulation order) and, through it, the oracle."""
+    from bench import model_conf
+    from holoscene_b200 import engine as E, synthetic
+    from holoscene_b200.network import HoloSceneNetwork
+    w = dict(name="t", R=R, K=K, N_samples=max(S - 34, 1), N_samples_eval=S, N_samples_extra=32, logmap=15)
+    torch.manual_seed(42)
+    m = HoloSceneNetwork(model_conf(w, precise=False, max_rays=max(R, 1024)))
+    m.load_state_dict(synthetic.perturb_state_dict(m.state_dict()))
+    m = m.cuda().eval()
+    eng = m.engine()
+    eng.prepare()
+    gen = torch.Generator().manual_seed(R * S + K)
+    o = (torch.rand(R, 3, generator=gen) * 0.6 - 0.3).cuda()
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=gen), dim=1).cuda()
+    z = (torch.rand(R, S, generator=gen) * 2.0).sort(dim=1)[0].cuda().contiguous()       # some points leave the hash grid's range
+    got = eng.sdf_values(o, d, z, channel)
+    raw_fused = eng.buffer("samp.SR")[: R * S, :K].clone()
+    eng.render_forward(E.SLOT_MAIN, o, d, z, torch.ones(R, 1).cuda(), torch.eye(3).cuda())
+    torch.cuda.synchronize()
+    raw_ref = eng.buffer("main.SR")[: R * S, :K]
+    want = raw_ref[:, channel] if channel >= 0 else raw_ref.min(dim=1)[0]
+    assert float(raw_ref.abs().max()) > 0.05
+    assert float((raw_fused - raw_ref).abs().max()) < 2e-6, float((raw_fused - raw_ref).abs().max())
+    assert float((got.reshape(-1) - want).abs().max()) < 2e-6
