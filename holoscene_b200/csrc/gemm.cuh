@@ -29,18 +29,27 @@ struct Epi {
 };
 
 // ---- epilogue math -----------------------------------------------------------------------------------
-// FAST = false: libm-grade expf / log1pf (the 3xTF32 parity mode).  FAST = true: MUFU-based __expf / __logf
-// (abs error ~1e-7 on softplus outputs of O(1e-2..1), far below the TF32 operand error of the fast mode).
+// FAST = false: libm-grade expf / log1pf (the 3xTF32 parity mode).  FAST = true: two raw MUFU ops per element
+// (ex2.approx / lg2.approx; abs error ~1e-7 on softplus outputs of O(1e-2..1), far below the TF32 operand error of the fast
+// mode) and NO branch: `if (t > 20) return a;` compiles to a divergent branch per element, which serialises the 32 elements a
+// lane owns behind one MUFU latency chain each (measured: 14 k cycles per 128x256 tile instead of ~4 k).  Out-of-range
+// arguments are harmless: ex2 overflows to +inf / flushes to 0, the linear branch is chosen by a select.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 template <bool FAST> __device__ __forceinline__ float epi_softplus(float a) {
+    if (FAST) {
+        const float l = lg2_approx(1.0f + ex2_approx(a * 144.26950408889634f)) * 0.006931471805599453f;   // 100 log2(e), ln(2)/100
+        return a * 100.0f > 20.0f ? a : l;
+    }
     const float t = 100.0f * a;
     if (t > 20.0f) return a;
-    return FAST ? __logf(1.0f + __expf(t)) * 0.01f : log1pf(expf(t)) * 0.01f;
+    return log1pf(expf(t)) * 0.01f;
 }
 template <bool FAST> __device__ __forceinline__ float epi_sigma(float h) {      // softplus'(a) from h = softplus(a)
-    return FAST ? 1.0f - __expf(-100.0f * h) : -expm1f(-100.0f * h);
+    return FAST ? 1.0f - ex2_approx(h * -144.26950408889634f) : -expm1f(-100.0f * h);
 }
 template <bool FAST> __device__ __forceinline__ float epi_sigmoid(float x) {
-    return FAST ? __fdividef(1.0f, 1.0f + __expf(-x)) : 1.0f / (1.0f + expf(-x));
+    return FAST ? __fdividef(1.0f, 1.0f + ex2_approx(x * -1.4426950408889634f)) : 1.0f / (1.0f + expf(-x));
 }
 
 // one element (used by the mma.sync kernels, whose accumulator fragments are scattered over rows)

@@ -48,15 +48,6 @@ constexpr int WG_SMEM_BYTES = WG_STAGES * TC_STAGE_BYTES + 256 + 1024;
 // buffer (tempty) so the MMA warp can start the tile after next.  Bias-gradient column sums are kept in registers
 // across all tiles of the CTA and flushed with one atomic per column per warp at the end (a per-chunk atomicAdd on
 // 256 addresses serialised in L2 and cost more than the whole contraction).
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
-}
-
 template <int KIND>
 __device__ __forceinline__ float4 epi_math4(const float4 acc, const float4 x4, const float4 y4, const float4 b4, float4& o2) {
     const float av[4] = {acc.x, acc.y, acc.z, acc.w};

@@ -116,6 +116,16 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
           "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+// explicit shared-space accesses: a pointer derived by integer arithmetic would otherwise compile to generic LD/ST
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // host side (gemm_tc.cu): tensor maps through the driver entry point; swizzle 0 = 128B (K-major operands), 1 = 128B with 32B atoms

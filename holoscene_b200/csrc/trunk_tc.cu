@@ -42,12 +42,12 @@ struct TrunkArgs {
 };
 
 // softplus epilogue of one hidden layer, in place in tensor memory: columns [32c, 32c+32) of the accumulator at `tbase`
-__device__ __forceinline__ void trunk_hidden_chunk(uint32_t taddr, const float* __restrict__ sbias) {
+__device__ __forceinline__ void trunk_hidden_chunk(uint32_t taddr, uint32_t sbias) {
     float v[32];
     tmem_ld32(taddr, v);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(sbias + i);   // same address in every lane: broadcast
+        const float4 b = lds128(sbias + 4u * i);                        // same address in every lane: broadcast
         v[i] = rtf32(epi_softplus<true>(v[i] + b.x), 1);
         v[i + 1] = rtf32(epi_softplus<true>(v[i + 1] + b.y), 1);
         v[i + 2] = rtf32(epi_softplus<true>(v[i + 2] + b.z), 1);
@@ -185,9 +185,9 @@ sdf_trunk_tc_kernel(const __grid_constant__ CUtensorMap mapH0, const __grid_cons
                 mbar_wait(acc_full, u & 1); ++u;
                 tc_fence_after();
                 const uint32_t base = (layer == 0 ? X : Y) + lane_off;
-                const float* sb = sbias + layer * 256;
-                trunk_hidden_chunk(base + (uint32_t)(g * 32), sb + g * 32);
-                trunk_hidden_chunk(base + (uint32_t)((g + 4) * 32), sb + (g + 4) * 32);
+                const uint32_t sb = smem_u32(sbias) + (uint32_t)layer * 1024u;
+                trunk_hidden_chunk(base + (uint32_t)(g * 32), sb + (uint32_t)g * 128u);
+                trunk_hidden_chunk(base + (uint32_t)((g + 4) * 32), sb + (uint32_t)(g + 4) * 128u);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
