@@ -36,11 +36,11 @@ WORKLOAD = dict(name="replica_room_0_stage1_full_conf_4096x128", R=4096, K=32, N
 METRIC = "rendered samples/sec (rays x samples) per Stage-1 SDF train step"
 
 
-def model_conf(w, precise=False, max_rays=None):
+def model_conf(w, precise=False, max_rays=None, speculative_sampler=True):
     from holoscene_b200 import conf as hconf
     return hconf.from_dict({
         "feature_vector_size": 256, "scene_bounding_sphere": 1.0, "use_bg_reg": True, "render_bg_iter": 10,
-        "hsb_precise": precise, "hsb_max_rays": max_rays or w["R"],
+        "hsb_precise": precise, "hsb_max_rays": max_rays or w["R"], "hsb_speculative_sampler": speculative_sampler,
         "implicit_network": {"d_in": 3, "d_out": w["K"], "dims": [256, 256], "geometric_init": True, "bias": 0.9,
                              "skip_in": [4], "weight_norm": True, "multires": 6, "inside_outside": True,
                              "use_grid_feature": True, "divide_factor": 1.0, "sigmoid": 10, "color_grid_feature": True,
@@ -151,6 +151,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precise", action="store_true", help="3xTF32 contractions (parity mode)")
     ap.add_argument("--rays", type=int, default=WORKLOAD["R"])
+    ap.add_argument("--exact-sampler", action="store_true",
+                    help="read the sampler's convergence flag after every round (pipeline drain) instead of speculating + verifying")
     ap.add_argument("--phases", action="store_true", help="after the timed runs, print a per-phase breakdown (synchronising)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +181,7 @@ def main():
     R, K = w["R"], w["K"]
     S = w["N_samples"] + w["N_samples_extra"] + 2
     torch.manual_seed(42)                       # identical replicas on every rank
-    model = HoloSceneNetwork(model_conf(w, precise=args.precise))
+    model = HoloSceneNetwork(model_conf(w, precise=args.precise, speculative_sampler=not args.exact_sampler))
     model.load_state_dict(synthetic.perturb_state_dict(model.state_dict()))
     model = model.cuda()
     model.train()

@@ -136,76 +136,79 @@ __global__ void __launch_bounds__(256) chain_seed_kernel(const float* __restrict
     reinterpret_cast<float4*>(P2 + ((long long)s * N + p) * 256)[j] = r;
 }
 
-// One thread per row; rows are 16-byte aligned (LD_H0 = 72, DY rows = 96 floats), so a row is moved as float4s: 4x fewer
-// load/store instructions than the scalar walk (these kernels are LSU-issue bound, not HBM bound).
-__device__ __forceinline__ void load_row72(const float* __restrict__ src, float (&r)[72]) {
-#pragma unroll
-    for (int i = 0; i < 18; ++i) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
-        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+// ---- the two ends of the input-gradient chain: g = (d h0 / d x)^T q0 and its transpose ----------------------------------
+// One WARP per row, lanes = columns of the 72-wide row (lane, lane + 32, lane + 64): every global access is a coalesced run of
+// a row (a thread-per-row walk touches 32 different rows per load instruction: 32 sectors per request, latency bound at a
+// third of the HBM rate).  The column roles are row-independent and decoded once per lane:
+//   j < 3                    identity        d h0_j / d x_d = [j == d]
+//   j = 3 + 6 i + c, c < 3   sin(2^i x_c)    derivative  2^i cos(2^i x_c) = 2^i * H0[j + 3]
+//   j = 3 + 6 i + 3 + c      cos(2^i x_c)    derivative -2^i sin(2^i x_c) = -2^i * H0[j - 3]
+//   j = 39 + 2 l + c         hash feature    derivative  0.5 * DY[6 l + 2 d + c]   (0.5: the [-1,1] -> [0,1] map)
+//   j = 71                   padding
+struct ChainCol { int kind, d, partner, dyoff; float f; };   // kind: 0 identity, 1 PE (f signed), 2 hash, 3 pad
+__device__ __forceinline__ ChainCol chain_col(int j) {
+    ChainCol c{3, 0, 0, 0, 0.0f};
+    if (j < 3) { c.kind = 0; c.d = j; }
+    else if (j < 39) {
+        const int i = (j - 3) / 6, r = (j - 3) - 6 * i;
+        c.kind = 1;
+        c.f = (float)(1 << i);
+        if (r < 3) { c.d = r; c.partner = j + 3; }
+        else { c.d = r - 3; c.partner = j - 3; c.f = -c.f; }
+    } else if (j < 71) { c.kind = 2; c.dyoff = 6 * ((j - 39) >> 1) + ((j - 39) & 1); }
+    return c;
+}
+// PE4 slot t (0..26) of a 3-vector g
+__device__ __forceinline__ float pe4_slot(int t, const float g[3]) {
+    if (t < 3) return g[t];
+    const int i = (t - 3) / 6, r = (t - 3) - 6 * i;
+    const float x = (r < 3 ? g[r] : g[r - 3]) * (float)(1 << i);
+    float sn, cs;
+    sincosf(x, &sn, &cs);
+    return r < 3 ? sn : cs;
+}
+
+constexpr int CE_WARPS = 8;
+// contribution of column j (role c) of row q to g = (dh0/dx)^T q
+__device__ __forceinline__ void chain_end_col(const ChainCol& c, int j, const float* __restrict__ q, const float* __restrict__ h,
+                                              const float* __restrict__ dy, float (&g)[3]) {
+    const float qj = __ldg(q + j);
+    if (c.kind == 0) { g[0] += c.d == 0 ? qj : 0.f; g[1] += c.d == 1 ? qj : 0.f; g[2] += c.d == 2 ? qj : 0.f; }
+    else if (c.kind == 1) {
+        const float v = c.f * __ldg(h + c.partner) * qj;
+        g[0] += c.d == 0 ? v : 0.f; g[1] += c.d == 1 ? v : 0.f; g[2] += c.d == 2 ? v : 0.f;
+    } else if (c.kind == 2) {
+        const float hq = 0.5f * qj;
+        g[0] += __ldg(dy + c.dyoff) * hq; g[1] += __ldg(dy + c.dyoff + 2) * hq; g[2] += __ldg(dy + c.dyoff + 4) * hq;
+    }
+}
+// end of the chain: G[m] = (dh0/dx)^T Q0[m];  rows m = s*N + p.  Optionally PE4(g) -> RIN[p, 54:81].
+__global__ void __launch_bounds__(32 * CE_WARPS) chain_end_kernel(const float* __restrict__ Q0, const float* __restrict__ H0,
+                                                                  const float* __restrict__ DY, long long N, long long rows,
+                                                                  float* __restrict__ G, float* __restrict__ RIN, int rtf) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * CE_WARPS + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * CE_WARPS;
+    const ChainCol c0 = chain_col(lane), c1 = chain_col(lane + 32), c2 = chain_col(lane < 8 ? lane + 64 : 71);
+#pragma unroll 2
+    for (long long m = warp; m < rows; m += nwarps) {
+        const long long p = m % N;
+        const float* q = Q0 + m * LD_H0;
+        const float* h = H0 + p * LD_H0;
+        const float* dy = DY + p * 96;
+        float g[3] = {0.f, 0.f, 0.f};
+        chain_end_col(c0, lane, q, h, dy, g);
+        chain_end_col(c1, lane + 32, q, h, dy, g);
+        if (lane < 8) chain_end_col(c2, lane + 64, q, h, dy, g);
+        g[0] = warp_sum(g[0]); g[1] = warp_sum(g[1]); g[2] = warp_sum(g[2]);
+        if (lane < 3) G[m * 3 + lane] = lane == 0 ? g[0] : (lane == 1 ? g[1] : g[2]);
+        if (RIN && lane < 27) RIN[p * LD_RIN + 54 + lane] = rtf32(pe4_slot(lane, g), rtf);
     }
 }
 
-// end of the chain: g = (dh0/dx)^T q0.  rows m = s*N + p.  Optionally writes PE4(g) into RIN[:, 54:81].
-__global__ void __launch_bounds__(128) chain_end_kernel(const float* __restrict__ Q0, const float* __restrict__ H0,
-                                                        const float* __restrict__ DY, long long N, int nseed,
-                                                        float* __restrict__ G, float* __restrict__ RIN, int rtf) {
-    __shared__ float sg[128][28];                          // PE4(g) of the CTA's rows (main pass only)
-    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = m < N * nseed;
-    const long long p = live ? m % N : 0;
-    float g[3] = {0.f, 0.f, 0.f};
-    if (live) {
-    float q[72];
-    load_row72(Q0 + m * LD_H0, q);
-    g[0] = q[0]; g[1] = q[1]; g[2] = q[2];
-    {
-        float h[40];                                       // PE part of the H0 row: columns 0..39
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(H0 + p * LD_H0) + i);
-            h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
-        }
-        float f = 1.0f;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const float sn = h[3 + 6 * i + d], cs = h[3 + 6 * i + 3 + d];
-                g[d] += f * (cs * q[3 + 6 * i + d] - sn * q[3 + 6 * i + 3 + d]);
-            }
-            f *= 2.0f;
-        }
-    }
-    float e[3] = {0.f, 0.f, 0.f};
-    const float4* dy4 = reinterpret_cast<const float4*>(DY + p * 96);
-#pragma unroll
-    for (int l2 = 0; l2 < 8; ++l2) {                       // two levels = 12 floats = three float4
-        const float4 a = __ldg(dy4 + 3 * l2), b = __ldg(dy4 + 3 * l2 + 1), c = __ldg(dy4 + 3 * l2 + 2);
-        const float dy[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const float q0 = q[39 + 2 * (2 * l2 + u)], q1 = q[40 + 2 * (2 * l2 + u)];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) e[d] += dy[u * 6 + d * 2] * q0 + dy[u * 6 + d * 2 + 1] * q1;
-        }
-    }
-#pragma unroll
-    for (int d = 0; d < 3; ++d) g[d] += 0.5f * e[d];
-    G[m * 3 + 0] = g[0]; G[m * 3 + 1] = g[1]; G[m * 3 + 2] = g[2];
-    }
-    if (!RIN) return;
-    // main pass (nseed == 1, m == p): PE4(g) -> RIN[:, 54:81], staged so that a row's 27 floats leave as one contiguous run
-    if (live) pe_write(sg[threadIdx.x], g[0], g[1], g[2], 4, rtf);
-    __syncthreads();
-    const long long m0 = (long long)blockIdx.x * blockDim.x;
-    const int nrows = (int)min((long long)blockDim.x, N * nseed - m0);
-    for (int idx = threadIdx.x; idx < nrows * 27; idx += blockDim.x) {
-        const int lr = idx / 27, c = idx - lr * 27;
-        RIN[((m0 + lr) % N) * LD_RIN + 54 + c] = sg[lr][c];
-    }
-}
-
+// (A warp-per-row version of this kernel, like chain_end above, measured 262 us against 149 us for this thread-per-row walk at
+// 4096 x 128: the row's reductions put three shuffle trees on every row's critical path, while here a thread streams its whole
+// row through L1 with 16-byte loads and needs no cross-lane traffic at all.)
 // backward of chain_end: dQ0 = (dh0/dx) dG, where for the main pass
 //   dG = dGn (normal-map term) + PE4(g)^T dRIN[:, 54:81]        (RIN holds sin/cos of g)
 // The total dG is written back to dGn (it feeds the second-order hash scatter).
@@ -586,7 +589,9 @@ int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long 
 int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN, int rtf,
                      cudaStream_t st) {
     if (N == 0) return HSB_OK;
-    chain_end_kernel<<<cdiv(N * nseed, 128), 128, 0, st>>>(Q0, H0, DY, N, nseed, G, RIN, rtf);
+    const long long rows = N * nseed;
+    const long long ctas = (rows + CE_WARPS * 8 - 1) / (CE_WARPS * 8);              // ~8 rows per warp
+    chain_end_kernel<<<(unsigned)(ctas < 1 ? 1 : ctas), 32 * CE_WARPS, 0, st>>>(Q0, H0, DY, N, rows, G, RIN, rtf);
     return check_launch("chain_end");
 }
 int launch_chain_end_bwd(float* dG, const float* dRIN, const float* RIN, const float* H0, const float* DY, long long N,

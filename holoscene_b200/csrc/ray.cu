@@ -33,16 +33,42 @@ __device__ __forceinline__ float warp_scan_incl_rev(float v, int lane) {   // su
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-object terms.  The K raw SDF values of a sample are one contiguous row of SR [P, Kp]; with lane = sample a per-channel
+// walk reads 4 bytes out of 32 different rows per load (32 sectors per request, and two warp reductions per channel).  Each
+// 32-sample chunk of a ray is therefore staged ONCE with coalesced 16-byte loads (the chunk is one contiguous 32*Kp-float run)
+// into a padded shared tile, and the roles flip for the per-object loop: lane = channel, loop over the 32 samples (tile column
+// reads are conflict-free, the per-sample scalars delta / T / w are shared-memory broadcasts, no shuffles).
+// Shared memory per warp: forward 32*(Kp+1) + 96 floats, backward 64*(Kp+1) + 64 floats.
+// ---------------------------------------------------------------------------------------------
+constexpr int CMP_WARPS = 4;   // rays per CTA
+
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int nrows, int Kp, int ldt, float* __restrict__ tile, int lane) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    const int total4 = nrows * Kp / 4;                       // Kp is a multiple of 8
+    for (int idx = lane; idx < total4; idx += 32) {
+        const float4 v = __ldg(s4 + idx);
+        const int e = idx * 4, row = e / Kp, col = e - row * Kp;
+        float* t = tile + row * ldt + col;
+        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward
 //   mode 0 (scene): weights from the scene (min) SDF; colour / semantics / opacity composites.
 //   mode 1 (bg patch, network.py:947-968): weights from SR[:, 0] for depth / normals; the scene-SDF
 //          weights are used only for the semantic arg-max (bg_mask).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) composite_fwd_kernel(CompositeArgs a) {
-    const int r = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
-    if (r >= a.R) return;
-    const int S = a.S, K = a.K, Kp = a.Kp;
+__global__ void __launch_bounds__(32 * CMP_WARPS) composite_fwd_kernel(CompositeArgs a) {
+    extern __shared__ float cmp_smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * CMP_WARPS + wid;
+    if (r >= a.R) return;                                    // warp-uniform; only __syncwarp below
+    const int S = a.S, K = a.K, Kp = a.Kp, ldt = Kp + 1;
+    float* tile = cmp_smem + (size_t)wid * (32 * ldt + 96);
+    float* sD = tile + 32 * ldt;                             // delta_i
+    float* sT = sD + 32;                                     // T_i
+    float* sW2 = sT + 32;                                    // semantic weights w2_i
     const float beta = beta_of(a.beta_param, a.beta_min);
     const float* z = a.Z + (long long)r * S;
     const long long p0 = (long long)r * S;
@@ -54,13 +80,16 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(CompositeArgs a) {
     for (int base = 0; base < S; base += 32) {
         const int i = base + lane;
         const bool ok = i < S;
+        const int nrows = min(32, S - base);
+        stage_rows(a.SR + (p0 + base) * Kp, nrows, Kp, ldt, tile, lane);
         float zi = 0.f, delta = 0.f, s_w = 0.f, s_scene = 0.f;
         if (ok) {
             zi = z[i];
             delta = (i + 1 < S) ? z[i + 1] - zi : 1e10f;
             s_scene = a.SDF[p0 + i];
-            s_w = (a.mode == 1) ? a.SR[(p0 + i) * Kp] : s_scene;
         }
+        __syncwarp();
+        if (ok) s_w = (a.mode == 1) ? tile[lane * ldt] : s_scene;
         const float E = ok ? delta * laplace_density(s_w, beta) : 0.0f;
         const float incl = warp_scan_incl(E, lane);
         // exclusive prefix through a shuffle, NOT incl - E: the last interval is 1e10 long, so E ~ 1e11 there and
@@ -71,16 +100,17 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(CompositeArgs a) {
         const float T = expf(-F);
         const float w = ok ? (1.0f - expf(-E)) * T : 0.0f;
         carry += __shfl_sync(0xffffffffu, incl, 31);
-        float T2 = T, w2 = w;
+        float w2 = w;
         if (a.mode == 1) {        // scene weights for the semantic composite
             const float E2 = ok ? delta * laplace_density(s_scene, beta) : 0.0f;
             const float incl2 = warp_scan_incl(E2, lane);
             float excl2 = __shfl_up_sync(0xffffffffu, incl2, 1);
             if (lane == 0) excl2 = 0.0f;
-            T2 = expf(-(carry2 + excl2));
+            const float T2 = expf(-(carry2 + excl2));
             w2 = ok ? (1.0f - expf(-E2)) * T2 : 0.0f;
             carry2 += __shfl_sync(0xffffffffu, incl2, 31);
         }
+        sD[lane] = delta; sT[lane] = T; sW2[lane] = w2;
         if (ok) {
             a.W[p0 + i] = w;
             a.T[p0 + i] = T;
@@ -90,22 +120,26 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(CompositeArgs a) {
             const float nrm = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]) + 1e-6f;
             acc_n[0] += w * g[0] / nrm; acc_n[1] += w * g[1] / nrm; acc_n[2] += w * g[2] / nrm;
             if (a.mode == 0) {
-                const float* c = a.RGB + (p0 + i) * 4;
-                acc_rgb[0] += w * c[0]; acc_rgb[1] += w * c[1]; acc_rgb[2] += w * c[2];
+                const float4 c = __ldg(reinterpret_cast<const float4*>(a.RGB) + p0 + i);
+                acc_rgb[0] += w * c.x; acc_rgb[1] += w * c.y; acc_rgb[2] += w * c.z;
             }
         }
-        // per-object composites: every lane walks the K channels of its own sample; the warp reduces per k.
-        for (int k = 0; k < K; ++k) {
-            float op = 0.f, sem = 0.f;
-            if (ok) {
-                const float sk = a.SR[(p0 + i) * Kp + k];
-                if (a.mode == 0) op = (1.0f - expf(-delta * laplace_density(sk, beta))) * T;
-                sem = w2 * a.sigmoid_scale / (1.0f + expf(a.sigmoid_scale * sk));
+        __syncwarp();
+        // per-object composites: lane = channel, loop over the chunk's samples
+#pragma unroll
+        for (int kb = 0; kb < HSB_MAX_K / 32; ++kb) {
+            const int k = kb * 32 + lane;
+            if (k < K) {
+                float op = 0.f, sem = 0.f;
+                for (int j = 0; j < nrows; ++j) {
+                    const float sk = tile[j * ldt + k];
+                    if (a.mode == 0) op += (1.0f - expf(-sD[j] * laplace_density(sk, beta))) * sT[j];
+                    sem += sW2[j] * a.sigmoid_scale / (1.0f + expf(a.sigmoid_scale * sk));
+                }
+                acc_op[kb] += op; acc_sem[kb] += sem;
             }
-            op = warp_sum(op);
-            sem = warp_sum(sem);
-            if (lane == (k & 31)) { acc_op[k >> 5] += op; acc_sem[k >> 5] += sem; }
         }
+        __syncwarp();                                        // the tile is re-staged by the next chunk
     }
     for (int k = lane; k < K; k += 32) {
         if (a.opacity) a.opacity[(long long)r * K + k] = acc_op[k >> 5];
@@ -137,14 +171,20 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(CompositeArgs a) {
 //   dGn  [P,3]  = dL/d(gradient) through the normal map
 //   dbeta (atomic) = dL/d beta
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeArgs a, CompositeGrads g) {
-    const int r = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(32 * CMP_WARPS) composite_bwd_kernel(CompositeArgs a, CompositeGrads g) {
+    extern __shared__ float cmp_smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * CMP_WARPS + wid;
     if (r >= a.R) return;
-    const int S = a.S, K = a.K, Kp = a.Kp;
+    const int S = a.S, K = a.K, Kp = a.Kp, ldt = Kp + 1;
+    float* tile = cmp_smem + (size_t)wid * (64 * ldt + 64);  // sdf_raw rows in, dS rows out (in place)
+    float* ctile = tile + 32 * ldt;                          // per-(sample, channel) opacity terms b_k (1 - e_k) T_i
+    float* sD = ctile + 32 * ldt;
+    float* sT = sD + 32;
     const float beta = beta_of(a.beta_param, a.beta_min);
     const float* z = a.Z + (long long)r * S;
     const long long p0 = (long long)r * S;
+    const bool per_object = a.mode == 0 && g.d_opacity != nullptr;
 
     float drgb[3] = {0.f, 0.f, 0.f}, dn[3] = {0.f, 0.f, 0.f}, ddepth = 0.f;
     if (g.d_rgb_values && a.mode == 0) { drgb[0] = g.d_rgb_values[r * 3]; drgb[1] = g.d_rgb_values[r * 3 + 1]; drgb[2] = g.d_rgb_values[r * 3 + 2]; }
@@ -154,33 +194,47 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeArgs a, Com
 #pragma unroll
         for (int c = 0; c < 3; ++c) dn[c] = a.rot[0 * 3 + c] * d[0] + a.rot[1 * 3 + c] * d[1] + a.rot[2 * 3 + c] * d[2];
     }
+    float bk[HSB_MAX_K / 32] = {0.f, 0.f};                   // d_opacity of the channels this lane owns
+    if (per_object) {
+#pragma unroll
+        for (int kb = 0; kb < HSB_MAX_K / 32; ++kb)
+            if (kb * 32 + lane < K) bk[kb] = g.d_opacity[(long long)r * K + kb * 32 + lane];
+    }
     const float Wt = a.wsum[r] + 1e-8f, Nz = a.wzsum[r];
     float dbeta = 0.0f;
     float carry = 0.0f;   // sum over j > current chunk of (a_j w_j + c_j)
     const int nchunk = (S + 31) / 32;
     for (int ch = nchunk - 1; ch >= 0; --ch) {
-        const int i = ch * 32 + lane;
+        const int base = ch * 32;
+        const int i = base + lane;
         const bool ok = i < S;
+        const int nrows = min(32, S - base);
+        if (per_object || a.mode == 1) stage_rows(a.SR + (p0 + base) * Kp, nrows, Kp, ldt, tile, lane);
         float aw = 0.f, cj = 0.f, ai = 0.f, T = 0.f, E = 0.f, delta = 0.f, s_w = 0.f, w = 0.f;
         if (ok) {
             const float zi = z[i];
             delta = (i + 1 < S) ? z[i + 1] - zi : 1e10f;
-            s_w = (a.mode == 1) ? a.SR[(p0 + i) * Kp] : a.SDF[p0 + i];
-            E = delta * laplace_density(s_w, beta);
             T = a.T[p0 + i];
             w = a.W[p0 + i];
+        }
+        sD[lane] = delta; sT[lane] = T;
+        __syncwarp();
+        if (ok) {
+            const float zi = z[i];
+            s_w = (a.mode == 1) ? tile[lane * ldt] : a.SDF[p0 + i];
+            E = delta * laplace_density(s_w, beta);
             const float* gg = a.G + (p0 + i) * 3;
             const float rn = sqrtf(gg[0] * gg[0] + gg[1] * gg[1] + gg[2] * gg[2]);
             const float den = rn + 1e-6f;
             const float gv = gg[0] * dn[0] + gg[1] * dn[1] + gg[2] * dn[2];
             ai = ddepth * (zi * Wt - Nz) / (Wt * Wt) + gv / den;
             if (a.mode == 0) {
-                const float* c = a.RGB + (p0 + i) * 4;
-                ai += drgb[0] * c[0] + drgb[1] * c[1] + drgb[2] * c[2];
+                const float4 c = __ldg(reinterpret_cast<const float4*>(a.RGB) + p0 + i);
+                ai += drgb[0] * c.x + drgb[1] * c.y + drgb[2] * c.z;
                 float4 o;
-                o.x = w * drgb[0] * c[0] * (1.0f - c[0]);
-                o.y = w * drgb[1] * c[1] * (1.0f - c[1]);
-                o.z = w * drgb[2] * c[2] * (1.0f - c[2]);
+                o.x = w * drgb[0] * c.x * (1.0f - c.x);
+                o.y = w * drgb[1] * c.y * (1.0f - c.y);
+                o.z = w * drgb[2] * c.z * (1.0f - c.z);
                 o.w = 0.0f;
                 reinterpret_cast<float4*>(g.dO)[p0 + i] = o;
             }
@@ -191,25 +245,36 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeArgs a, Com
             o3[1] = w * (dn[1] / den - gg[1] * coef);
             o3[2] = w * (dn[2] / den - gg[2] * coef);
             aw = ai * w;
-            // per-object opacity terms
-            float* ds = g.dS + (p0 + i) * Kp;
-            if (a.mode == 0 && g.d_opacity) {
-                for (int k = 0; k < K; ++k) {
-                    const float b = g.d_opacity[(long long)r * K + k];
-                    const float sk = a.SR[(p0 + i) * Kp + k];
-                    const float ek = expf(-delta * laplace_density(sk, beta));
-                    cj += b * (1.0f - ek) * T;
-                    float dsg, dbt;
-                    laplace_grads(sk, beta, dsg, dbt);
-                    const float common = b * T * delta * ek;     // dL/d sigma_k
-                    ds[k] = (common != 0.0f) ? rtf32(common * dsg, g.rtf) : 0.0f;
-                    dbeta += (common != 0.0f) ? common * dbt : 0.0f;
-                }
-            } else {
-                for (int k = 0; k < K; ++k) ds[k] = 0.0f;
-            }
-            for (int k = K; k < Kp; ++k) ds[k] = 0.0f;
         }
+        __syncwarp();                                        // every lane has read its own tile[lane][0] (mode 1)
+        // per-object opacity terms: lane = channel, loop over the chunk's samples; dS rows are built in place in the tile
+        if (per_object) {
+#pragma unroll
+            for (int kb = 0; kb < HSB_MAX_K / 32; ++kb) {
+                const int k = kb * 32 + lane;
+                if (k < K) {
+                    const float b = bk[kb];
+                    for (int j = 0; j < nrows; ++j) {
+                        const float sk = tile[j * ldt + k];
+                        const float dj = sD[j], Tj = sT[j];
+                        const float ek = expf(-dj * laplace_density(sk, beta));
+                        float dsg, dbt;
+                        laplace_grads(sk, beta, dsg, dbt);
+                        const float common = b * Tj * dj * ek;     // dL/d sigma_k
+                        ctile[j * ldt + k] = b * (1.0f - ek) * Tj;
+                        tile[j * ldt + k] = (common != 0.0f) ? rtf32(common * dsg, g.rtf) : 0.0f;
+                        dbeta += (common != 0.0f) ? common * dbt : 0.0f;
+                    }
+                } else if (k < Kp) {
+                    for (int j = 0; j < nrows; ++j) tile[j * ldt + k] = 0.0f;
+                }
+            }
+        } else {
+            for (int idx = lane; idx < nrows * Kp; idx += 32) { const int row = idx / Kp; tile[row * ldt + idx - row * Kp] = 0.0f; }
+        }
+        __syncwarp();
+        if (ok && per_object)
+            for (int k = 0; k < K; ++k) cj += ctile[lane * ldt + k];
         const float v = aw + cj;
         const float sfx = warp_scan_incl_rev(v, lane);
         float after = __shfl_down_sync(0xffffffffu, sfx, 1);       // sum over j > i within the chunk
@@ -224,21 +289,49 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompositeArgs a, Com
             const float dsdf = (dsig != 0.0f) ? dsig * dsg : 0.0f;
             dbeta += (dsig != 0.0f) ? dsig * dbt : 0.0f;
             const int kk = (a.mode == 1) ? 0 : a.KS[p0 + i];
-            g.dS[(p0 + i) * Kp + kk] = rtf32(g.dS[(p0 + i) * Kp + kk] + dsdf, g.rtf);
+            tile[lane * ldt + kk] = rtf32(tile[lane * ldt + kk] + dsdf, g.rtf);
         }
+        __syncwarp();
+        {   // the chunk's dS rows leave as one contiguous run of 16-byte stores
+            float4* d4 = reinterpret_cast<float4*>(g.dS + (p0 + base) * Kp);
+            const int total4 = nrows * Kp / 4;
+            for (int idx = lane; idx < total4; idx += 32) {
+                const int e = idx * 4, row = e / Kp, col = e - row * Kp;
+                const float* t = tile + row * ldt + col;
+                d4[idx] = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        __syncwarp();
     }
     dbeta = warp_sum(dbeta);
     if (lane == 0 && g.d_beta) atomicAdd(g.d_beta, dbeta * ((*a.beta_param >= 0.0f) ? 1.0f : -1.0f));
 }
 
+static int composite_smem(const void* fn, size_t bytes, size_t& have) {
+    if (bytes > have) {
+        if (bytes > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+            set_error("composite: shared-memory attribute rejected");
+            return HSB_ERR_CUDA;
+        }
+        have = bytes;
+    }
+    return HSB_OK;
+}
+
 int launch_composite_fwd(const CompositeArgs& a, cudaStream_t st) {
     if (a.R == 0) return HSB_OK;
-    composite_fwd_kernel<<<cdiv((long long)a.R * 32, 256), 256, 0, st>>>(a);
+    static size_t have = 0;
+    const size_t smem = (size_t)CMP_WARPS * (32 * (a.Kp + 1) + 96) * sizeof(float);
+    if (int e = composite_smem((const void*)composite_fwd_kernel, smem, have)) return e;
+    composite_fwd_kernel<<<cdiv(a.R, CMP_WARPS), 32 * CMP_WARPS, smem, st>>>(a);
     return check_launch("composite_fwd");
 }
 int launch_composite_bwd(const CompositeArgs& a, const CompositeGrads& g, cudaStream_t st) {
     if (a.R == 0) return HSB_OK;
-    composite_bwd_kernel<<<cdiv((long long)a.R * 32, 256), 256, 0, st>>>(a, g);
+    static size_t have = 0;
+    const size_t smem = (size_t)CMP_WARPS * (64 * (a.Kp + 1) + 64) * sizeof(float);
+    if (int e = composite_smem((const void*)composite_bwd_kernel, smem, have)) return e;
+    composite_bwd_kernel<<<cdiv(a.R, CMP_WARPS), 32 * CMP_WARPS, smem, st>>>(a, g);
     return check_launch("composite_bwd");
 }
 

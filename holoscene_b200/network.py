@@ -202,6 +202,7 @@ class HoloSceneNetwork(nn.Module):
         self.draws = None
         self._last_ne = 0
         self.phase_ms = None      # dict -> per-phase timing (debug)
+        self.speculative_sampler = bool(conf.get_bool("hsb_speculative_sampler", default=True))
 
     # ---- flat parameter storage -----------------------------------------------------------------------
     def _named_segments(self):
@@ -270,13 +271,32 @@ class HoloSceneNetwork(nn.Module):
             raise RuntimeError(f"{uv.shape[1]} rays exceed hsb_max_rays={eng.max_rays} (set model.hsb_max_rays in the conf)")
         draws = self.draws if self.draws is not None else LiveDraws(dev)
         self.draws = draws
+        # Speculative convergence test of the sampler (ray_sampler.get_z_vals): only with live random draws (a replayed log must be
+        # consumed exactly once) and in training; the first call of a kind always runs in exact mode.
+        speculate = self.training and isinstance(draws, LiveDraws) and self.speculative_sampler
         try:
-            return self._forward(eng, intrinsics, uv, pose, iter_step, draws, dev)
+            if speculate:
+                # a repeat must start over: forward shifts uv in place (reference behaviour) and consumes random numbers
+                uv0 = uv.clone()
+                rng = draws.gen.get_state() if draws.gen is not None else torch.cuda.get_rng_state(dev)
+                bg_step = self.use_bg_reg and iter_step % self.render_bg_iter == 0
+                np_rng = np.random.get_state() if bg_step else None
+                out = self._forward(eng, intrinsics, uv, pose, iter_step, draws, dev, True)
+                if self.ray_sampler.verify():
+                    return out
+                uv.copy_(uv0)
+                if draws.gen is not None:
+                    draws.gen.set_state(rng)
+                else:
+                    torch.cuda.set_rng_state(rng, dev)
+                if np_rng is not None:
+                    np.random.set_state(np_rng)
+            return self._forward(eng, intrinsics, uv, pose, iter_step, draws, dev, False)
         finally:
             if isinstance(draws, LiveDraws):
                 self.draws = None
 
-    def _forward(self, eng, intrinsics, uv, pose, iter_step, draws, dev):
+    def _forward(self, eng, intrinsics, uv, pose, iter_step, draws, dev, speculate=False):
         training = self.training
         if training:
             self._attach_grads()
@@ -291,7 +311,7 @@ class HoloSceneNetwork(nn.Module):
         if self.phase_ms is not None:
             import time
             torch.cuda.synchronize(); _t0 = time.perf_counter()
-        z_vals, z_samples_eik = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self)
+        z_vals, z_samples_eik = self.ray_sampler.get_z_vals(ray_dirs, cam_loc, self, speculate=speculate)
         z_vals = z_vals.contiguous()
         if self.phase_ms is not None:
             torch.cuda.synchronize(); self.phase_ms["sampler"] = self.phase_ms.get("sampler", 0.0) + (time.perf_counter() - _t0) * 1e3
@@ -326,7 +346,7 @@ class HoloSceneNetwork(nn.Module):
             gx, gy = np.meshgrid(np.arange(ps), np.arange(ps), indexing="xy")
             uv0 = torch.from_numpy(np.stack([gx + x0, gy + y0], -1).reshape(1, -1, 2)).float().to(dev)
             d0, c0, ds0 = _engine.camera_rays(uv0.contiguous(), pose, intrinsics)
-            bz, _ = self.ray_sampler.get_z_vals(d0, c0, self, idx=0)
+            bz, _ = self.ray_sampler.get_z_vals(d0, c0, self, idx=0, speculate=speculate)
             bz = bz.contiguous()
             _, bdepth, bnmap, _, bsem = eng.render_forward(_engine.SLOT_BG, c0, d0, bz, ds0, rot)
             output["bg_mask"] = torch.argmax(bsem, dim=-1, keepdim=True)

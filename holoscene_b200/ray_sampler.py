@@ -10,6 +10,8 @@ ray); the only host sync per round is the reference's own global convergence tes
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 
@@ -69,6 +71,10 @@ class ErrorBoundSampler:
         self.scene_bounding_sphere = scene_bounding_sphere
         self.add_tiny = add_tiny
         self.last_rounds = 0
+        self._rounds_guess = {}     # channel (-1 = scene) -> rounds the last call needed (speculative convergence test)
+        self._pending = []          # speculative calls awaiting verify()
+        self._flag_bufs = []
+        self.spec_hits = self.spec_misses = 0
 
     def get_error_bound(self, beta, sdf, z_vals, dists, d_star):
         density = _density(sdf.reshape(z_vals.shape), beta)
@@ -80,15 +86,24 @@ class ErrorBoundSampler:
         return bound_opacity.max(-1)[0]
 
     @torch.no_grad()
-    def get_z_vals(self, ray_dirs, cam_loc, model, idx=None):
+    def get_z_vals(self, ray_dirs, cam_loc, model, idx=None, speculate=False):
         """Same contract as the reference (ray_sampler.py:130-287).  Every refinement round is: fused SDF query of the new
-        samples (hsb_sdf_values) -> hsb_sampler_bound (merge, d*, beta bisection, global flag) -> ONE host read of the flag
-        (the reference's `beta.max() > beta0` sync) -> hsb_sampler_resample.  No other host round trips, no torch ops."""
+        samples (hsb_sdf_values) -> hsb_sampler_bound (merge, d*, beta bisection, global flag) -> the reference's global
+        convergence test `beta.max() > beta0` (:204) -> hsb_sampler_resample.  No torch ops in between.
+
+        The convergence test is a host decision.  Exact mode (speculate=False) reads the flag after every round -- a full
+        pipeline drain per round, like the reference's `.item()`.  With speculate=True the loop runs the number of rounds the
+        previous call of the same kind needed, the per-round flags are copied to pinned memory asynchronously, and
+        `verify()` -- called by the model once the rest of the forward is enqueued -- waits only for THAT copy (the GPU still
+        has the whole scene pass queued) and reports whether the guess was the reference's decision sequence; if not, the
+        model repeats its forward in exact mode.  Results are identical to exact mode whenever verify() returns True."""
         from . import _lib, engine as E
         dev = ray_dirs.device
         R = ray_dirs.shape[0]
         eng = model.engine()
         channel = -1 if idx is None else int(idx)
+        key = channel
+        guess = self._rounds_guess.get(key) if speculate else None
         o = cam_loc.contiguous()
         d = ray_dirs.contiguous()
         p, st = _lib.ptr, _lib.stream
@@ -99,7 +114,7 @@ class ErrorBoundSampler:
         _lib.check(E.sampler_init(p(o), p(d), R, Ne, float(self.near), float(self.far), float(self.scene_bounding_sphere),
                                   p(t_rand), float(self.eps), p(samples), p(beta), st()))
         beta_param = model.density.beta
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        flags = torch.zeros(max(self.max_total_iters, 1), dtype=torch.int32, device=dev)
         z_all = sdf_all = None
         n_old, total_iters, not_converge = 0, 0, True
         while not_converge and total_iters < self.max_total_iters:
@@ -108,13 +123,15 @@ class ErrorBoundSampler:
             n = n_old + n_new
             z_out = torch.empty(R, n, device=dev)
             sdf_out = torch.empty(R, n, device=dev)
-            flag.zero_()
             _lib.check(E.sampler_bound(p(z_all), p(sdf_all), n_old, p(samples), p(s_new), n_new, p(z_out), p(sdf_out), p(beta),
                                        p(beta_param), float(model.density.beta_min), float(self.eps), int(self.beta_iters), R,
-                                       p(flag), st()))
+                                       ctypes.c_void_p(flags.data_ptr() + 4 * total_iters), st()))
             z_all, sdf_all, n_old = z_out, sdf_out, n
             total_iters += 1
-            not_converge = bool(flag.item())                    # the reference's per-round host sync (:204)
+            if guess is None:
+                not_converge = bool(flags[total_iters - 1].item())     # the reference's per-round host sync (:204)
+            else:
+                not_converge = total_iters < guess                     # verified later against the device flags
             more = not_converge and total_iters < self.max_total_iters
             if more:
                 N, mode, u = Ne, 0, None
@@ -125,6 +142,14 @@ class ErrorBoundSampler:
             _lib.check(E.sampler_resample(p(z_all), p(sdf_all), n_old, p(beta), mode, p(u), N, float(self.add_tiny), R,
                                           p(samples), st()))
         self.last_rounds = total_iters
+        if guess is None:
+            self._rounds_guess[key] = total_iters
+        else:
+            host = self._pinned_flags()
+            host.copy_(flags[: host.numel()], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._pending.append((key, total_iters, host, ev))
         n = n_old
         if self.N_samples_extra > 0:
             if model.training:
@@ -141,6 +166,44 @@ class ErrorBoundSampler:
         _lib.check(E.sampler_finalize(p(z_all), n, p(samples), self.N_samples, p(extra), self.N_samples_extra, float(self.near),
                                       float(self.far), p(eidx), R, p(z_vals), p(z_eik), st()))
         return z_vals, z_eik
+
+    def _pinned_flags(self):
+        """A pinned int32 buffer per outstanding speculative call (two per forward at most: scene + background patch)."""
+        i = len(self._pending)
+        while len(self._flag_bufs) <= i:
+            self._flag_bufs.append(torch.zeros(max(self.max_total_iters, 1), dtype=torch.int32).pin_memory())
+        return self._flag_bufs[i]
+
+    def verify(self):
+        """True iff every speculative get_z_vals since the last verify() made the reference's decisions: all rounds before
+        the last reported 'not converged' and the last one reported 'converged' (or the round limit was hit).  Updates the
+        per-kind guess with the round count the flags imply, so a repeat in exact mode is needed at most once per change."""
+        if not self._pending:
+            return True
+        ok = True
+        for key, rounds, host, ev in self._pending:
+            ev.synchronize()
+            f = host.tolist()
+            actual = rounds
+            for j in range(rounds):
+                if f[j] == 0:                      # converged after round j + 1
+                    actual = j + 1
+                    break
+            else:
+                if rounds < self.max_total_iters:  # still not converged after the guessed number of rounds
+                    actual = None
+            if actual != rounds:
+                ok = False
+                if actual is None:
+                    self._rounds_guess.pop(key, None)   # unknown: the exact repeat will measure it
+                else:
+                    self._rounds_guess[key] = actual
+        self._pending = []
+        if ok:
+            self.spec_hits += 1
+        else:
+            self.spec_misses += 1
+        return ok
 
     @torch.no_grad()
     def get_z_vals_torch(self, ray_dirs, cam_loc, model, idx=None):

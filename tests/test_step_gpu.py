@@ -378,3 +378,41 @@ def test_fused_sdf_trunk_matches_layer_by_layer_path(K, R, S, channel):
     assert float(raw_ref.abs().max()) > 0.05
     assert float((raw_fused - raw_ref).abs().max()) < 2e-6, float((raw_fused - raw_ref).abs().max())
     assert float((got.reshape(-1) - want).abs().max()) < 2e-6
+
+
+def test_speculative_sampler_equals_exact_mode_and_recovers_from_a_wrong_guess():
+    """The sampler's convergence test is a host decision (reference ray_sampler.py:204).  Speculating on the previous step's
+    round count and verifying the device flags afterwards must give bit-identical outputs to reading the flag every round --
+    also when the guess is wrong (the forward is then repeated in exact mode)."""
+    g = common.load_golden("step_train")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    uv, pose, K, gt, _ = common.golden_inputs(g)
+    spec, exact = build_model(cfg, sd, False), build_model(cfg, sd, False)
+    exact.speculative_sampler = False
+    spec.train(); exact.train()
+    inp = lambda: {"uv": uv.clone().cuda(), "intrinsics": K.cuda(), "pose": pose.cuda()}
+
+    def both(step):
+        torch.manual_seed(100 + step)
+        a = spec(inp(), None, iter_step=step)
+        torch.manual_seed(100 + step)
+        b = exact(inp(), None, iter_step=step)
+        for k in ("z_vals", "rgb_values", "depth_values", "object_opacity", "grad_theta"):
+            assert torch.equal(a[k], b[k]), (step, k)
+
+    both(1)                                          # first call: no guess yet -> exact mode on both sides
+    assert spec.ray_sampler.spec_hits == 0 and spec.ray_sampler.spec_misses == 0
+    both(2)
+    both(3)
+    assert spec.ray_sampler.spec_hits == 2 and spec.ray_sampler.last_rounds == exact.ray_sampler.last_rounds >= 2
+    rounds, limit = exact.ray_sampler.last_rounds, spec.ray_sampler.max_total_iters
+    wrong = [r for r in (rounds - 1, rounds + 1) if 1 <= r <= limit]      # too few / too many rounds
+    for n, r in enumerate(wrong):
+        spec.ray_sampler._rounds_guess[-1] = r
+        both(4 + n)
+        assert spec.ray_sampler.spec_misses == n + 1
+        assert spec.ray_sampler._rounds_guess[-1] == rounds               # the repeat in exact mode measured the right count
+    both(10)                                         # background-patch step: two sampler calls (scene + channel 0)
+    both(20)
+    assert spec.ray_sampler.spec_misses <= len(wrong) + 1   # the background patch moves between steps: its round count may change once
