@@ -308,7 +308,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": w["name"], "rays_per_gpu": R, "samples": S, "K": K, "sampler_rounds": rounds,
                        "hash_table_rows": int(model.implicit_network.encoding.embeddings.shape[0]), "parallelism": f"ray-sharded dp{world}",
-                       "l2": "per-step working set ~17 GB of activations >> 126 MB L2 (no flush needed)"},
+                       "l2": f"per-step working set {model.engine().workspace.numel() / 1e9:.1f} GB of activations >> 126 MB L2 "
+                             "(no flush needed)"},
             "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
