@@ -81,6 +81,7 @@ struct Ctx {
     char* dwe_begin; size_t dwe_bytes;
     Slot slot[3];
     Slot scratch;   // X, H0, H1, H2, SR only: hsb_sdf_values between a slot's forward and its backward
+    long long block_tiles = 0;   // L2 blocking of the ray passes: 128-row tiles per block of rays (0 = one block)
     float* P(int seg) const { return params + off[seg]; }
     float* Gp(int seg) const { return grads + off[seg]; }
 };
@@ -162,6 +163,39 @@ static void carve_all(Ctx* c, bool dry) {
 
 #define TRY(x) do { int _e = (x); if (_e != HSB_OK) return _e; } while (0)
 
+// ---- L2 blocking --------------------------------------------------------------------------------------------------------
+// A ray pass is a chain of ~45 (forward) / ~50 (backward) kernels in which almost every kernel's main input is the tensor the
+// previous kernel wrote.  Run over all P = 524 288 points at once each of those tensors is 537 MB, four times the 126 MB L2, so
+// every hand-over goes through HBM.  The passes are therefore run in blocks of whole rays sized to two waves of 128-row tiles
+// (2 x 148 tiles = 37 888 points, 39 MB per [block,256] tensor): a kernel then finds what its predecessor wrote in L2.
+// The view of a block is the slot with every per-point pointer advanced by p0 rows and every per-ray pointer by r0.
+// MEASURED (4096 x 128, 1 x B200): launched kernel by kernel the blocked step is launch-bound -- 14 blocks x ~95 launches at
+// ~7 us of host time each: 17.6 ms/step against 10.4 ms unblocked (28 blocks: 25.7 ms, 4 blocks: 12.3 ms) -- so blocking is
+// OFF by default (block_tiles = 0) until the block chain is replayed from a CUDA graph; the mechanism and its parity test
+// (tests/test_step_gpu.py::test_ray_blocked_passes_equal_the_unblocked_pass) are kept for that.
+static Slot slot_block(const Slot& s, long long p0, long long r0, int Kp) {
+    Slot b = s;
+    auto adv = [&](float*& q, long long ld) { if (q) q += p0 * ld; };
+    adv(b.X, 3); adv(b.H0, LD_H0); adv(b.DY, 96); adv(b.H1, 256); adv(b.H2, 256); adv(b.SR, Kp); adv(b.SDF, 1);
+    if (b.KS) b.KS += p0;
+    adv(b.P2, 256); adv(b.P1, 256); adv(b.Q0, LD_H0); adv(b.G, 3);
+    adv(b.EC, 32); adv(b.C1, 256); adv(b.RIN, LD_RIN); adv(b.U1, 256); adv(b.U2, 256); adv(b.RGB, 4);
+    adv(b.W, 1); adv(b.T, 1); adv(b.ZV, 1);
+    if (b.WSUM) b.WSUM += r0;
+    if (b.WZSUM) b.WZSUM += r0;
+    if (b.DSCALE) b.DSCALE += r0;
+    adv(b.dO, 4); adv(b.dS, Kp); adv(b.dG, 3); adv(b.dQ0, LD_H0); adv(b.dQ1, 256); adv(b.dA1x, 256); adv(b.dQ2, 256);
+    adv(b.dA2x, 256); adv(b.dA2, 256); adv(b.dA1, 256); adv(b.dH0E, 32); adv(b.dU2, 256); adv(b.dU1, 256); adv(b.dRIN, LD_RIN);
+    adv(b.dFEAT, 256); adv(b.dC1, 256); adv(b.dEC, 32);
+    return b;
+}
+// rays per block (whole rays); block_tiles = 0 disables blocking
+static int block_rays(long long tiles, int R, int S) {
+    if (tiles <= 0) return R;
+    long long r = tiles * 128 / (S > 0 ? S : 1);
+    if (r < 1) r = 1;
+    return r < R ? (int)r : R;
+}
 
 static Epi epi(int kind, float* out, long long ldo, int round_out = 0) {
     Epi e{}; e.kind = kind; e.out = out; e.ldo = ldo; e.round_out = round_out; return e;
@@ -296,6 +330,66 @@ static CompositeArgs composite_args(Ctx* c, Slot& s, int mode) {
     return a;
 }
 
+// per-point part of the ray pass forward on one block of rays
+static int render_forward_block(Ctx* c, Slot& s, bool scene, const float* o, const float* d, const float* z, cudaStream_t st) {
+    const hsb_step_cfg& f = c->cfg;
+    const int P = f.precise;
+    const int rt = c->rtf();
+    const long long N = s.N;
+    TRY(launch_ray_points(o, d, z, s.R, s.S, s.X, s.H0, scene ? s.RIN : nullptr, rt, st));
+    TRY(sdf_forward(c, s, N, true, st));
+    TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, -1, s.SDF, s.KS, st));
+    TRY(chain_forward(c, s, N, 1, st));
+    if (scene) {
+        TRY(hash_forward_ex(s.X, c->P(SEG_CEMB), c->hoffs, s.EC, 2, 32, nullptr, 0, (uint32_t)N, f.L, f.S, f.H, 1, rt, st));
+        Epi e = epi(EPI_BIAS_RELU, s.C1, 256, rt); e.bias = c->P(SEG_C0B);
+        TRY(gemm_tn(s.EC, 32, c->C0e, 32, N, 256, 32, e, P, st));
+        e = epi(EPI_BIAS, s.RIN + 81, LD_RIN, rt); e.bias = c->P(SEG_C1B);
+        TRY(gemm_tn(s.C1, 256, c->C1e, 256, N, 256, 256, e, P, st));
+        e = epi(EPI_BIAS_RELU, s.U1, 256, rt); e.bias = c->P(SEG_R0B);
+        TRY(gemm_tn(s.RIN, LD_RIN, c->R0e, LD_RIN, N, 256, LD_RIN, e, P, st));
+        e = epi(EPI_BIAS_RELU, s.U2, 256, rt); e.bias = c->P(SEG_R1B);
+        TRY(gemm_tn(s.U1, 256, c->R1e, 256, N, 256, 256, e, P, st));
+        TRY(launch_rgb_head(s.U2, c->R2e, c->P(SEG_R2B), N, s.RGB, st));
+    }
+    return HSB_OK;
+}
+
+// per-point part of the ray pass backward on one block of rays (after its composite_bwd)
+static int render_backward_block(Ctx* c, Slot& s, bool scene, cudaStream_t st) {
+    const hsb_step_cfg& f = c->cfg;
+    const int P = f.precise;
+    const int rt = c->rtf();
+    const long long N = s.N;
+    if (scene) {
+        // render net
+        const bool fold = (P == 0) && gemm_tc_available();
+        // fast mode: lin1 bias gradient, lin2 weight and bias gradients are taken inside rgb_head_bwd (no extra pass over U2 / dU2)
+        TRY(launch_rgb_head_bwd(s.dO, c->R2e, s.U2, N, s.dU2, rt, fold ? c->Gp(SEG_R1B) : nullptr, fold ? c->dR2e : nullptr,
+                                fold ? c->dRB2e : nullptr, st));
+        if (!fold) TRY(gemm_wgrad(s.dO, 4, 4, s.U2, 256, 256, N, c->dR2e, 256, c->dRB2e, P, st));
+        Epi e = epi(EPI_BWD_RELU, s.dU1, 256, rt); e.aux = s.U1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_R0B) : nullptr;
+        TRY(gemm_tn(s.dU2, 256, c->R1eT, 256, N, 256, 256, e, P, st));
+        TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, fold ? nullptr : c->Gp(SEG_R1B), P, st));
+        e = epi(EPI_NONE, s.dRIN + 54, LD_RIN);
+        TRY(gemm_tn(s.dU1, 256, c->R0eT + 54 * 256, 256, N, 27, 256, e, P, st));     // d PE4(grad)
+        e = epi(EPI_NONE, s.dFEAT, 256, rt); e.colsum = fold ? c->Gp(SEG_C1B) : nullptr;
+        TRY(gemm_tn(s.dU1, 256, c->R0eT + 81 * 256, 256, N, 256, 256, e, P, st));    // d feature
+        TRY(gemm_wgrad(s.dU1, 256, 256, s.RIN, LD_RIN, LD_RIN, N, c->dR0e, LD_RIN, fold ? nullptr : c->Gp(SEG_R0B), P, st));
+        // colour-feature MLP + colour hash grid
+        TRY(gemm_wgrad(s.dFEAT, 256, 256, s.C1, 256, 256, N, c->Gp(SEG_C1W), 256, fold ? nullptr : c->Gp(SEG_C1B), P, st));
+        e = epi(EPI_BWD_RELU, s.dC1, 256, rt); e.aux = s.C1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_C0B) : nullptr;
+        TRY(gemm_tn(s.dFEAT, 256, c->C1T, 256, N, 256, 256, e, P, st));
+        TRY(gemm_wgrad(s.dC1, 256, 256, s.EC, 32, 32, N, c->Gp(SEG_C0W), 32, fold ? nullptr : c->Gp(SEG_C0B), P, st));
+        e = epi(EPI_NONE, s.dEC, 32);
+        TRY(gemm_tn(s.dC1, 256, c->C0T, 256, N, 32, 256, e, P, st));
+        TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dEC, 32, nullptr, 0, nullptr, 1, c->Gp(SEG_CEMB), (uint32_t)N, f.L, f.S, f.H, st));
+    }
+    TRY(chain_backward(c, s, N, 1, scene, st));
+    TRY(sdf_backward(c, s, N, true, st));
+    return HSB_OK;
+}
+
 }  // namespace hsb
 
 using namespace hsb;
@@ -345,11 +439,20 @@ extern "C" int hsb_ctx_create(const hsb_step_cfg* cfg, float* params, float* gra
         return HSB_ERR_ARG;
     }
     carve_all(c, false);
+    const char* bt = getenv("HSB_BLOCK_TILES");
+    c->block_tiles = bt ? atoll(bt) : 0;                        // off by default: see the note at slot_block
     *out = reinterpret_cast<hsb_ctx*>(c);
     return HSB_OK;
 }
 
 extern "C" void hsb_ctx_destroy(hsb_ctx* h) { delete reinterpret_cast<Ctx*>(h); }
+
+extern "C" int hsb_ctx_set_option(hsb_ctx* h, const char* name, int64_t value) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (c && name && !strcmp(name, "block_tiles") && value >= 0) { c->block_tiles = value; return HSB_OK; }
+    set_error("hsb_ctx_set_option: unknown option or bad value");
+    return HSB_ERR_ARG;
+}
 
 extern "C" int hsb_ctx_buffer(hsb_ctx* h, const char* name, int64_t* offset_bytes, int64_t* rows, int64_t* ld) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
@@ -444,27 +547,19 @@ extern "C" int hsb_render_forward(hsb_ctx* h, int32_t slot_id, const float* o, c
     cudaMemcpyAsync(s.ZV, z, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(s.DSCALE, depth_scale, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(s.ROT, rot, 9 * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    const int rt = c->rtf();
-    TRY(launch_ray_points(o, d, z, R, S, s.X, s.H0, scene ? s.RIN : nullptr, rt, st));
-    TRY(sdf_forward(c, s, N, true, st));
-    TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, -1, s.SDF, s.KS, st));
-    TRY(chain_forward(c, s, N, 1, st));
-    if (scene) {
-        TRY(hash_forward_ex(s.X, c->P(SEG_CEMB), c->hoffs, s.EC, 2, 32, nullptr, 0, (uint32_t)N, f.L, f.S, f.H, 1, rt, st));
-        Epi e = epi(EPI_BIAS_RELU, s.C1, 256, rt); e.bias = c->P(SEG_C0B);
-        TRY(gemm_tn(s.EC, 32, c->C0e, 32, N, 256, 32, e, P, st));
-        e = epi(EPI_BIAS, s.RIN + 81, LD_RIN, rt); e.bias = c->P(SEG_C1B);
-        TRY(gemm_tn(s.C1, 256, c->C1e, 256, N, 256, 256, e, P, st));
-        e = epi(EPI_BIAS_RELU, s.U1, 256, rt); e.bias = c->P(SEG_R0B);
-        TRY(gemm_tn(s.RIN, LD_RIN, c->R0e, LD_RIN, N, 256, LD_RIN, e, P, st));
-        e = epi(EPI_BIAS_RELU, s.U2, 256, rt); e.bias = c->P(SEG_R1B);
-        TRY(gemm_tn(s.U1, 256, c->R1e, 256, N, 256, 256, e, P, st));
-        TRY(launch_rgb_head(s.U2, c->R2e, c->P(SEG_R2B), N, s.RGB, st));
-    }
-    CompositeArgs a = composite_args(c, s, s.mode);
-    a.rgb_values = rgb_values; a.depth_values = depth_values; a.normal_map = normal_map; a.opacity = opacity; a.semantic = semantic;
     if (!depth_values || !normal_map || !semantic || (scene && (!rgb_values || !opacity))) { set_error("hsb_render_forward: null output"); return HSB_ERR_ARG; }
-    TRY(launch_composite_fwd(a, st));
+    const int rb = block_rays(c->block_tiles, R, S);
+    for (int r0 = 0; r0 < R; r0 += rb) {
+        const int nr = R - r0 < rb ? R - r0 : rb;
+        Slot b = slot_block(s, (long long)r0 * S, r0, c->Kp);
+        b.R = nr; b.N = (long long)nr * S;
+        TRY(render_forward_block(c, b, scene, o + 3LL * r0, d + 3LL * r0, z + (long long)r0 * S, st));
+        CompositeArgs a = composite_args(c, b, s.mode);
+        a.rgb_values = rgb_values ? rgb_values + 3LL * r0 : nullptr; a.depth_values = depth_values + r0;
+        a.normal_map = normal_map + 3LL * r0; a.opacity = opacity ? opacity + (long long)r0 * c->K : nullptr;
+        a.semantic = semantic + (long long)r0 * c->K;
+        TRY(launch_composite_fwd(a, st));
+    }
     return HSB_OK;
 }
 
@@ -477,39 +572,22 @@ extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_r
     const bool scene = slot_id == HSB_SLOT_MAIN;
     const hsb_step_cfg& f = c->cfg;
     const int P = f.precise;
-    const long long N = s.N;
-    CompositeArgs a = composite_args(c, s, s.mode);
-    CompositeGrads g{};
-    g.d_rgb_values = d_rgb_values; g.d_depth_values = d_depth_values; g.d_normal_map = d_normal_map; g.d_opacity = d_opacity;
-    const int rt = c->rtf();
-    g.dO = s.dO; g.dS = s.dS; g.dGn = s.dG; g.d_beta = c->Gp(SEG_BETA); g.rtf = rt;
-    TRY(launch_composite_bwd(a, g, st));
-    if (scene) {
-        // render net
-        const bool fold = (P == 0) && gemm_tc_available();
-        // fast mode: lin1 bias gradient, lin2 weight and bias gradients are taken inside rgb_head_bwd (no extra pass over U2 / dU2)
-        TRY(launch_rgb_head_bwd(s.dO, c->R2e, s.U2, N, s.dU2, rt, fold ? c->Gp(SEG_R1B) : nullptr, fold ? c->dR2e : nullptr,
-                                fold ? c->dRB2e : nullptr, st));
-        if (!fold) TRY(gemm_wgrad(s.dO, 4, 4, s.U2, 256, 256, N, c->dR2e, 256, c->dRB2e, P, st));
-        Epi e = epi(EPI_BWD_RELU, s.dU1, 256, rt); e.aux = s.U1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_R0B) : nullptr;
-        TRY(gemm_tn(s.dU2, 256, c->R1eT, 256, N, 256, 256, e, P, st));
-        TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, fold ? nullptr : c->Gp(SEG_R1B), P, st));
-        e = epi(EPI_NONE, s.dRIN + 54, LD_RIN);
-        TRY(gemm_tn(s.dU1, 256, c->R0eT + 54 * 256, 256, N, 27, 256, e, P, st));     // d PE4(grad)
-        e = epi(EPI_NONE, s.dFEAT, 256, rt); e.colsum = fold ? c->Gp(SEG_C1B) : nullptr;
-        TRY(gemm_tn(s.dU1, 256, c->R0eT + 81 * 256, 256, N, 256, 256, e, P, st));    // d feature
-        TRY(gemm_wgrad(s.dU1, 256, 256, s.RIN, LD_RIN, LD_RIN, N, c->dR0e, LD_RIN, fold ? nullptr : c->Gp(SEG_R0B), P, st));
-        // colour-feature MLP + colour hash grid
-        TRY(gemm_wgrad(s.dFEAT, 256, 256, s.C1, 256, 256, N, c->Gp(SEG_C1W), 256, fold ? nullptr : c->Gp(SEG_C1B), P, st));
-        e = epi(EPI_BWD_RELU, s.dC1, 256, rt); e.aux = s.C1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_C0B) : nullptr;
-        TRY(gemm_tn(s.dFEAT, 256, c->C1T, 256, N, 256, 256, e, P, st));
-        TRY(gemm_wgrad(s.dC1, 256, 256, s.EC, 32, 32, N, c->Gp(SEG_C0W), 32, fold ? nullptr : c->Gp(SEG_C0B), P, st));
-        e = epi(EPI_NONE, s.dEC, 32);
-        TRY(gemm_tn(s.dC1, 256, c->C0T, 256, N, 32, 256, e, P, st));
-        TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dEC, 32, nullptr, 0, nullptr, 1, c->Gp(SEG_CEMB), (uint32_t)N, f.L, f.S, f.H, st));
+    const int R = s.R, S = s.S, K = c->K;
+    const int rb = block_rays(c->block_tiles, R, S);
+    for (int r0 = 0; r0 < R; r0 += rb) {
+        const int nr = R - r0 < rb ? R - r0 : rb;
+        Slot b = slot_block(s, (long long)r0 * S, r0, c->Kp);
+        b.R = nr; b.N = (long long)nr * S;
+        CompositeArgs a = composite_args(c, b, s.mode);
+        CompositeGrads g{};
+        g.d_rgb_values = d_rgb_values ? d_rgb_values + 3LL * r0 : nullptr;
+        g.d_depth_values = d_depth_values ? d_depth_values + r0 : nullptr;
+        g.d_normal_map = d_normal_map ? d_normal_map + 3LL * r0 : nullptr;
+        g.d_opacity = d_opacity ? d_opacity + (long long)r0 * K : nullptr;
+        g.dO = b.dO; g.dS = b.dS; g.dGn = b.dG; g.d_beta = c->Gp(SEG_BETA); g.rtf = c->rtf();
+        TRY(launch_composite_bwd(a, g, st));
+        TRY(render_backward_block(c, b, scene, st));
     }
-    TRY(chain_backward(c, s, N, 1, scene, st));
-    TRY(sdf_backward(c, s, N, true, st));
     return HSB_OK;
 }
 

@@ -45,6 +45,7 @@ _lib.lib.hsb_ctx_destroy.argtypes = [_vp]
 _lib.lib.hsb_ctx_destroy.restype = None
 _ctx_buffer = declare("hsb_ctx_buffer", [_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                                          ctypes.POINTER(ctypes.c_int64)])
+_set_option = declare("hsb_ctx_set_option", [_vp, ctypes.c_char_p, ctypes.c_int64])
 _prepare = declare("hsb_prepare", [_vp, c_stream])
 _finish = declare("hsb_finish", [_vp, c_stream])
 _sdf_values = declare("hsb_sdf_values", [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, c_stream])
@@ -189,6 +190,10 @@ class StepEngine:
         start = self._ws_shift + off.value
         n = rows.value * ld.value
         return self.workspace[start: start + 4 * n].view(dtype).view(rows.value, ld.value)
+
+    def set_option(self, name: str, value: int):
+        """hsb_ctx_set_option (e.g. "block_tiles": L2 blocking of the ray passes, 0 = off)."""
+        check(_set_option(self._h, name.encode(), int(value)))
 
     # ---- phases ------------------------------------------------------------------------------------
     def prepare(self):

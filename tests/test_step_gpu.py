@@ -416,3 +416,70 @@ def test_speculative_sampler_equals_exact_mode_and_recovers_from_a_wrong_guess()
     both(10)                                         # background-patch step: two sampler calls (scene + channel 0)
     both(20)
     assert spec.ray_sampler.spec_misses <= len(wrong) + 1   # the background patch moves between steps: its round count may change once
+
+
+def test_eval_image_render_in_chunks():
+    """N3: full-image evaluation render in the reference's chunked loop (split_input / merge_output, eval mode).  The merged
+    image must be exactly the per-chunk model outputs laid end to end.  It is NOT chunk-size invariant bit for bit -- neither is
+    the reference: the sampler's convergence test is a maximum over the rays of a chunk (ray_sampler.py:204), so the number of
+    refinement rounds depends on the chunk -- but the images must agree closely."""
+    from holoscene_b200 import eval_render
+    g = common.load_golden("step_eval")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    _, pose, K, _, _ = common.golden_inputs(g)
+    m = build_model(cfg, sd, True, max_rays=1024)
+    H = W = 24
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    uv = torch.stack([xs * 20.0 + 10, ys * 20.0 + 10], -1).reshape(1, -1, 2).float().cuda()
+    inp = {"uv": uv, "intrinsics": K.cuda(), "pose": pose.cuda()}
+    a = eval_render.render_image(m, dict(inp, uv=uv.clone()), H * W, split_n_pixels=100)      # ragged last chunk
+    assert a["rgb_values"].shape == (H * W, 3) and a["depth_values"].shape[0] == H * W and a["semantic_values"].shape == (H * W,)
+    m.eval()
+    parts = [m(dict(inp, uv=uv[:, i:i + 100].clone().contiguous()), None) for i in range(0, H * W, 100)]
+    for k in ("rgb_values", "normal_map", "depth_values"):
+        want = torch.cat([p[k].reshape(-1, p[k].shape[-1]) for p in parts], 0)
+        assert torch.equal(a[k].reshape(want.shape), want), k
+    assert float(a["rgb_values"].min()) >= 0.0 and float(a["rgb_values"].max()) <= 1.0
+    b = eval_render.render_image(m, dict(inp, uv=uv.clone()), H * W, split_n_pixels=H * W)
+    assert float((a["rgb_values"] - b["rgb_values"]).abs().mean()) < 2e-2
+    assert float((a["depth_values"] - b["depth_values"]).abs().mean()) < 2e-2
+
+
+def test_ray_blocked_passes_equal_the_unblocked_pass():
+    """L2 blocking: hsb_render_forward / backward run the per-point kernel chain block of rays by block of rays.  Blocks of one
+    128-row tile (ragged last block, rays straddling tile boundaries) must give the single-block result: per-ray outputs and
+    per-sample buffers bit for bit (rows are independent), gradients up to the summation order of atomics / split reductions."""
+    from holoscene_b200 import engine as E
+    g = common.load_golden("step_train")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    R, S = g["out_z_vals"].shape
+    z = torch.from_numpy(g["out_z_vals"]).cuda().contiguous()
+    gen = torch.Generator().manual_seed(3)
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=gen), dim=1).cuda()
+    o = torch.tensor([[0.1, 0.0, -0.2]]).repeat(R, 1).cuda()
+    ds = (torch.rand(R, 1, generator=gen) + 0.5).cuda()
+    rot = torch.linalg.qr(torch.randn(3, 3, generator=gen))[0].contiguous().cuda()
+    cot = [torch.randn(R, 3, generator=gen).cuda(), torch.randn(R, 1, generator=gen).cuda(), torch.randn(R, 3, generator=gen).cuda(),
+           torch.randn(R, cfg.d_out, generator=gen).cuda()]
+    res = {}
+    for tiles in (0, 1, 7):
+        m = build_model(cfg, sd, False)
+        m.train()
+        eng = m.engine()
+        eng.set_option("block_tiles", tiles)
+        m._attach_grads()
+        eng.prepare()
+        outs = [t.clone() for t in eng.render_forward(E.SLOT_MAIN, o, d, z, ds, rot)]
+        bufs = {n: eng.buffer("main." + n)[: R * S].clone() for n in ("SDF", "G", "RGB", "W")}
+        eng.render_backward(E.SLOT_MAIN, *cot)
+        eng.finish()
+        torch.cuda.synchronize()
+        res[tiles] = (outs, bufs, m._flat_grad.clone())
+    for tiles in (1, 7):
+        for a, b in zip(res[tiles][0], res[0][0]):
+            assert torch.equal(a, b)
+        for n in res[0][1]:
+            assert torch.equal(res[tiles][1][n], res[0][1][n]), n
+        assert common.rel_err(res[tiles][2].cpu(), res[0][2].cpu()) < 1e-5
