@@ -133,7 +133,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "rays": w["R"], "samples": w["N_samples"] + w["N_samples_extra"] + 2, "K": w["K"]},
+            "config": {"workload": w["name"], "rays_per_gpu": w["R"], "samples": w["N_samples"] + w["N_samples_extra"] + 2, "K": w["K"],
+                       "parallelism": f"{threads} host threads (torch intra-op), rank 0 only"},
             "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
                              "sample": f"{rays} of {w['R']} rays x {w['N_samples'] + w['N_samples_extra'] + 2} samples, full tables, "
                                        f"median of {max(1, min(args.steps, 3))} full steps after 1 warm-up"},
@@ -147,7 +148,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-rays", type=int, default=1024, help="rays of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=4096, help="rays of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precise", action="store_true", help="3xTF32 contractions (parity mode)")
     ap.add_argument("--rays", type=int, default=WORKLOAD["R"])

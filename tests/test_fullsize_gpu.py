@@ -18,6 +18,8 @@ CASES = {
     "C2_4096x128_K32": dict(name="c2", R=4096, K=32, N_samples=94, N_samples_eval=128, N_samples_extra=32, logmap=19),
     "C3_4096x128_K21": dict(name="c3", R=4096, K=21, N_samples=94, N_samples_eval=128, N_samples_extra=32, logmap=19),
     "C5shard_1024x192_K64": dict(name="c5", R=1024, K=64, N_samples=158, N_samples_eval=128, N_samples_extra=32, logmap=19),
+    "C1_512x64_K2": dict(name="c1", R=512, K=2, N_samples=30, N_samples_eval=128, N_samples_extra=32, logmap=19),
+    "K1_300x98": dict(name="k1", R=300, K=1, N_samples=64, N_samples_eval=128, N_samples_extra=32, logmap=15),   # Stage-2 style single field
 }
 
 
@@ -70,7 +72,7 @@ def test_full_size_step_properties(case):
     for n, p in m.named_parameters():
         assert float(p.grad.abs().max()) > 0.0, n
     emb = m.implicit_network.encoding.embeddings.grad
-    assert int((emb.abs().sum(1) > 0).sum()) > 100000        # the step touches a large part of the 6.1 M-row table
+    assert int((emb.abs().sum(1) > 0).sum()) > min(100000, emb.shape[0] // 20)   # the step touches a large part of the table
 
 
 def test_full_size_backward_is_linear_in_the_cotangent_and_fast_matches_precise():
