@@ -7,11 +7,10 @@ from __future__ import annotations
 
 import ctypes
 
-import numpy as np
 import torch
 
 from . import _lib
-from ._lib import c_f32, c_f32p, c_int, c_ll, c_stream, c_u32, check, declare, ptr, stream
+from ._lib import c_f32, c_int, c_ll, c_stream, check, declare, ptr, stream
 
 NUM_SEGMENTS = 25
 SLOT_MAIN, SLOT_EIK, SLOT_BG = 0, 1, 2

@@ -14,11 +14,10 @@ import torch
 import torch.nn as nn
 
 from . import engine as _engine
-from . import rend_util
 from .density import LaplaceDensity
 from .hashgrid import HashEncoder
 from .ray_sampler import ErrorBoundSampler
-from .rng import LiveDraws, ReplayDraws
+from .rng import LiveDraws
 
 
 def _embed_dim(multires):

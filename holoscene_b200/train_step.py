@@ -9,7 +9,6 @@ average to the global mean; every rank then applies the identical Adam update (n
 from __future__ import annotations
 
 import torch
-import torch.distributed as dist
 
 from .optim import StageOneAdam
 from .parallel import allreduce_mean_
