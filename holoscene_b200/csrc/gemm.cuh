@@ -289,6 +289,11 @@ __device__ __forceinline__ void epilogue_tile_vec(const Epi& e, long long m_firs
 
 int num_sms();
 bool gemm_tc_available();   // tcgen05 path usable on this device (and not disabled by HSB_DISABLE_TCGEN05)
+// dual_tc.cu: both backward streams of a softplus layer in one kernel (two TMEM accumulators)
+bool gemm_dual_tc_eligible();
+int gemm_dual_tc(const float* A1, long long ld1, const float* B1, long long ldb1, int K1, const float* A2, long long ld2, const float* B2,
+                 long long ldb2, int K2, long long M, const float* aux, long long lda, const float* aux2, long long lda2, float* out1,
+                 long long ldo1, float* out, long long ldo, float* colsum, int round_out, cudaStream_t stream);
 bool gemm_tn_tc_eligible(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K);
 int gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K, const Epi& epi,
                cudaStream_t stream);

@@ -82,6 +82,7 @@ struct Ctx {
     Slot slot[3];
     Slot scratch;   // X, H0, H1, H2, SR only: hsb_sdf_values between a slot's forward and its backward
     long long block_tiles = 0;   // L2 blocking of the ray passes: 128-row tiles per block of rays (0 = one block)
+    bool dual_bwd = false;       // chain + SDF-net backward through the dual-accumulator layer kernel (csrc/dual_tc.cu)
     float* P(int seg) const { return params + off[seg]; }
     float* Gp(int seg) const { return grads + off[seg]; }
 };
@@ -280,6 +281,33 @@ static int sdf_backward(Ctx* c, Slot& s, long long N, bool have_chain, cudaStrea
     return HSB_OK;
 }
 
+// ---- chain + SDF-net backward of a reverse-mode slot with the dual-accumulator layer kernel (fast mode) ----
+// Same results as chain_backward + sdf_backward; the cross terms dA1x / dA2x never exist as tensors:
+//   dq1 = (dq0 W0^T) sg1                                        one contraction, EPI_MUL_SIGMA
+//   layer 2:  acc1 = dq1 W1^T, acc2 = ds W2   ->  dq2 = acc1 sg2,  da2 = acc2 sg2 + acc1 p2 100(1-sg2)
+//   layer 1:  acc1 = dq0 W0^T (again, K = 72), acc2 = da2 W1  ->  da1 = acc2 sg1 + acc1 p1 100(1-sg1)
+static int chain_sdf_backward_dual(Ctx* c, Slot& s, long long N, bool with_rin, cudaStream_t st) {
+    const hsb_step_cfg& f = c->cfg;
+    const int rt = c->rtf();
+    TRY(launch_chain_end_bwd(s.dG, with_rin ? s.dRIN : nullptr, with_rin ? s.RIN : nullptr, s.H0, s.DY, N, 1, s.dQ0, rt, st));
+    Epi e = epi(EPI_MUL_SIGMA, s.dQ1, 256, rt); e.aux = s.H1; e.lda = 256; e.aux_rows = N;
+    TRY(gemm_tn(s.dQ0, LD_H0, c->W0e, LD_H0, N, 256, LD_H0, e, 0, st));
+    TRY(gemm_wgrad(s.P1, 256, 256, s.dQ0, LD_H0, LD_H0, N, c->dW0e, LD_H0, nullptr, 0, st));
+    TRY(gemm_dual_tc(s.dQ1, 256, c->W1e, 256, 256, s.dS, c->Kp, c->W2eT, c->Kp, c->Kp, N, s.H2, 256, s.P2, 256, s.dQ2, 256, s.dA2, 256,
+                     c->Gp(SEG_L1B), rt, st));
+    TRY(gemm_wgrad(s.P2, 256, 256, s.dQ1, 256, 256, N, c->dW1e, 256, nullptr, 0, st));
+    TRY(launch_scatter_rows(s.dQ2, s.KS, N, c->K, c->Kp, 1, c->dW2e, st));
+    TRY(gemm_wgrad(s.dS, c->Kp, c->Kp, s.H2, 256, 256, N, c->dW2e, 256, c->dB2e, 0, st));
+    TRY(gemm_dual_tc(s.dQ0, LD_H0, c->W0e, LD_H0, LD_H0, s.dA2, 256, c->W1eT, 256, 256, N, s.H1, 256, s.P1, 256, nullptr, 0, s.dA1, 256,
+                     c->Gp(SEG_L0B), rt, st));
+    TRY(gemm_wgrad(s.dA2, 256, 256, s.H1, 256, 256, N, c->dW1e, 256, nullptr, 0, st));
+    e = epi(EPI_NONE, s.dH0E, 32);
+    TRY(gemm_tn(s.dA1, 256, c->W0eT + 39 * 256, 256, N, 32, 256, e, 0, st));
+    TRY(gemm_wgrad(s.dA1, 256, 256, s.H0, LD_H0, LD_H0, N, c->dW0e, LD_H0, nullptr, 0, st));
+    TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dH0E, 32, s.Q0 + 39, LD_H0, s.dG, 1u, c->Gp(SEG_EMB), (uint32_t)N, f.L, f.S, f.H, st));
+    return HSB_OK;
+}
+
 // ---- forward-mode Jacobian of the SDF net at N points (eikonal slot):  J[d*N + p, :] = d sdf_raw[p, :] / d x_d ----
 //   u0_d = d h0/d x_d ; t1_d = (W0 u0_d) * sg1 ; t2_d = (W1 t1_d) * sg2 ; J[:, d] = W2 t2_d
 static int tangent_forward(Ctx* c, Slot& s, long long N, cudaStream_t st) {
@@ -385,6 +413,7 @@ static int render_backward_block(Ctx* c, Slot& s, bool scene, cudaStream_t st) {
         TRY(gemm_tn(s.dC1, 256, c->C0T, 256, N, 32, 256, e, P, st));
         TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dEC, 32, nullptr, 0, nullptr, 1, c->Gp(SEG_CEMB), (uint32_t)N, f.L, f.S, f.H, st));
     }
+    if (P == 0 && c->dual_bwd && gemm_dual_tc_eligible()) return chain_sdf_backward_dual(c, s, N, scene, st);
     TRY(chain_backward(c, s, N, 1, scene, st));
     TRY(sdf_backward(c, s, N, true, st));
     return HSB_OK;
@@ -441,6 +470,8 @@ extern "C" int hsb_ctx_create(const hsb_step_cfg* cfg, float* params, float* gra
     carve_all(c, false);
     const char* bt = getenv("HSB_BLOCK_TILES");
     c->block_tiles = bt ? atoll(bt) : 0;                        // off by default: see the note at slot_block
+    const char* du = getenv("HSB_DUAL_BWD");
+    c->dual_bwd = du ? atoi(du) != 0 : false;
     *out = reinterpret_cast<hsb_ctx*>(c);
     return HSB_OK;
 }
@@ -450,6 +481,7 @@ extern "C" void hsb_ctx_destroy(hsb_ctx* h) { delete reinterpret_cast<Ctx*>(h); 
 extern "C" int hsb_ctx_set_option(hsb_ctx* h, const char* name, int64_t value) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (c && name && !strcmp(name, "block_tiles") && value >= 0) { c->block_tiles = value; return HSB_OK; }
+    if (c && name && !strcmp(name, "dual_bwd")) { c->dual_bwd = value != 0; return HSB_OK; }
     set_error("hsb_ctx_set_option: unknown option or bad value");
     return HSB_ERR_ARG;
 }

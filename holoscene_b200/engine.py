@@ -63,6 +63,8 @@ _camera_rays = declare("hsb_camera_rays", [_vp, _vp, _vp, _vp, i32, _vp, _vp, _v
 _eik_points = declare("hsb_eik_points", [_vp, _vp, _vp, _vp, _vp, i32, _vp, c_stream])
 gemm_tn = declare("hsb_gemm_tn", [_vp, c_ll, _vp, c_ll, c_ll, c_int, c_int, c_int, _vp, c_ll, _vp, _vp, c_ll, c_ll, _vp, c_ll,
                                   _vp, c_ll, c_int, c_int, c_stream])
+gemm_dual = declare("hsb_gemm_dual", [_vp, c_ll, _vp, c_ll, c_int, _vp, c_ll, _vp, c_ll, c_int, c_ll, _vp, c_ll, _vp, c_ll, _vp, c_ll, _vp, c_ll,
+                                      _vp, c_int, c_stream])
 gemm_wgrad = declare("hsb_gemm_wgrad", [_vp, c_ll, c_int, _vp, c_ll, c_int, c_ll, _vp, c_ll, _vp, c_int, c_stream])
 
 

@@ -135,7 +135,8 @@ int hsb_ctx_create(const hsb_step_cfg* cfg, float* params, float* grads, const i
 void hsb_ctx_destroy(hsb_ctx* ctx);
 /* Tuning options.  "block_tiles": the ray passes run in blocks of whole rays of about this many 128-row tiles, so that a kernel finds
  * the tensor its predecessor wrote in L2 (0 = the whole batch as one block, the default: kernel-by-kernel launches make the blocked
- * step launch-bound, see csrc/step.cu; env HSB_BLOCK_TILES sets the initial value). */
+ * step launch-bound, see csrc/step.cu; env HSB_BLOCK_TILES sets the initial value).  "dual_bwd": 1 = chain + SDF-net backward through
+ * the dual-accumulator layer kernel (csrc/dual_tc.cu; less HBM traffic, currently slower -- default 0; env HSB_DUAL_BWD). */
 int hsb_ctx_set_option(hsb_ctx* ctx, const char* name, int64_t value);
 /* Introspection for tests: byte offset / rows / row stride (floats) of a named workspace buffer, e.g. "main.H1". */
 int hsb_ctx_buffer(hsb_ctx* ctx, const char* name, int64_t* offset_bytes, int64_t* rows, int64_t* ld);
@@ -227,6 +228,14 @@ int hsb_gemm_tn(const float* A, long long lda, const float* B, long long ldb, lo
                 long long ld_aux2, float* out2, long long ldo2, int atomic2, int precise, hsb_stream_t stream);
 int hsb_gemm_wgrad(const float* A, long long lda, int N1, const float* B, long long ldb, int N2, long long M, float* C,
                    long long ldc, float* bias, int precise, hsb_stream_t stream);
+
+/* Both backward streams of one softplus layer of the SDF net in one launch (csrc/dual_tc.cu; fast mode, N = 256):
+ *   acc1 = A1 [M,K1] . B1 [256,K1]^T,  acc2 = A2 [M,K2] . B2 [256,K2]^T,  sigma = softplus'(.) from aux = h [M,256], p = aux2 [M,256]
+ *   out1 = acc1 * sigma (may be NULL),  out = acc2 * sigma + acc1 * p * 100 (1 - sigma),  colsum (may be NULL) += column sums of out. */
+int hsb_gemm_dual(const float* A1, long long ld1, const float* B1, long long ldb1, int K1, const float* A2, long long ld2,
+                  const float* B2, long long ldb2, int K2, long long M, const float* aux, long long ld_aux, const float* aux2,
+                  long long ld_aux2, float* out1, long long ldo1, float* out, long long ldo, float* colsum, int round_out,
+                  hsb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -125,3 +125,35 @@ def test_tcgen05_kernel_is_the_fast_path_and_matches_legacy_tensor_path():
     assert common.rel_err(a.cpu(), ref) < 5e-3 and common.rel_err(b.cpu(), ref) < 3e-3
     assert common.rel_err(a.cpu(), b.cpu()) < 5e-3
     assert not torch.equal(a, b)     # different arithmetic (operand truncation vs rounding): not the same kernel
+
+
+@pytest.mark.parametrize("M,K1,K2,with_out1", [(700, 256, 32, True), (128, 72, 256, False), (4097, 256, 8, True), (33, 72, 256, True),
+                                               (148 * 128 * 2 + 5, 256, 32, True)])
+def test_gemm_dual_backward_layer(M, K1, K2, with_out1):
+    """csrc/dual_tc.cu: two products into two TMEM accumulators, one epilogue
+         out1 = acc1 * sigma(h),   out = acc2 * sigma(h) + acc1 * p * 100 (1 - sigma(h)),   colsum += sum_rows(out)
+    against fp64 (operands are TF32 on the tensor core: same bound as the single-product tcgen05 kernel), ragged last tile,
+    K tails shorter than a 32-float k-block, several tiles per CTA (persistent loop + barrier phases)."""
+    from holoscene_b200 import _lib, engine
+    g = torch.Generator().manual_seed(M + K1 + K2)
+    A1 = torch.randn(M, K1, generator=g).cuda()
+    B1 = (torch.randn(256, K1, generator=g) / K1 ** 0.5).cuda()
+    A2 = torch.randn(M, K2, generator=g).cuda()
+    B2 = (torch.randn(256, K2, generator=g) / K2 ** 0.5).cuda()
+    h = (torch.rand(M, 256, generator=g) * 0.05).cuda()
+    p = torch.randn(M, 256, generator=g).cuda() * 0.01
+    out1 = torch.zeros(M, 256, device="cuda") if with_out1 else None
+    out = torch.zeros(M, 256, device="cuda")
+    colsum = torch.full((256,), 3.0, device="cuda")
+    _lib.check(engine.gemm_dual(_p(A1), K1, _p(B1), K1, K1, _p(A2), K2, _p(B2), K2, K2, M, _p(h), 256, _p(p), 256, _p(out1), 256, _p(out), 256,
+                                _p(colsum), 0, _lib.stream()))
+    torch.cuda.synchronize()
+    acc1 = A1.double() @ B1.double().t()
+    acc2 = A2.double() @ B2.double().t()
+    sg = _sigma(h.double())
+    want = acc2 * sg + acc1 * p.double() * 100.0 * (1.0 - sg)
+    tol = TOL[0]
+    if with_out1:
+        assert common.rel_err(out1.cpu(), (acc1 * sg).cpu()) < tol
+    assert common.rel_err(out.cpu(), want.cpu()) < tol
+    assert common.rel_err(colsum.cpu(), (want.sum(0) + 3.0).cpu()) < tol

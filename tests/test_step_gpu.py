@@ -483,3 +483,37 @@ def test_ray_blocked_passes_equal_the_unblocked_pass():
         for n in res[0][1]:
             assert torch.equal(res[tiles][1][n], res[0][1][n]), n
         assert common.rel_err(res[tiles][2].cpu(), res[0][2].cpu()) < 1e-5
+
+
+def test_dual_accumulator_backward_equals_the_layer_by_layer_backward():
+    """Opt-in path (hsb_ctx_set_option "dual_bwd"): chain + SDF-net backward through csrc/dual_tc.cu (two TMEM accumulators per
+    tile, the cross terms never stored) must give the gradients of the default EPI_BWD_CHAIN + EPI_BWD_SP sequence -- same
+    TF32-rounded operands, same products; only the association of the final sums differs."""
+    from holoscene_b200 import engine as E
+    g = common.load_golden("step_train")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    R, S = g["out_z_vals"].shape
+    z = torch.from_numpy(g["out_z_vals"]).cuda().contiguous()
+    gen = torch.Generator().manual_seed(3)
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=gen), dim=1).cuda()
+    o = torch.tensor([[0.1, 0.0, -0.2]]).repeat(R, 1).cuda()
+    ds = (torch.rand(R, 1, generator=gen) + 0.5).cuda()
+    rot = torch.linalg.qr(torch.randn(3, 3, generator=gen))[0].contiguous().cuda()
+    cot = [torch.randn(R, 3, generator=gen).cuda(), torch.randn(R, 1, generator=gen).cuda(), torch.randn(R, 3, generator=gen).cuda(),
+           torch.randn(R, cfg.d_out, generator=gen).cuda()]
+    grads = {}
+    for dual in (0, 1):
+        m = build_model(cfg, sd, False)
+        m.train()
+        eng = m.engine()
+        eng.set_option("dual_bwd", dual)
+        m._attach_grads()
+        eng.prepare()
+        eng.render_forward(E.SLOT_MAIN, o, d, z, ds, rot)
+        eng.render_backward(E.SLOT_MAIN, *cot)
+        eng.finish()
+        torch.cuda.synchronize()
+        grads[dual] = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    for n in grads[0]:
+        assert common.rel_err(grads[1][n].cpu(), grads[0][n].cpu()) < 2e-4, n
