@@ -10,27 +10,31 @@
 // EPI_BWD_SP (which READS it back, and h a second time): 16.4 units of HBM traffic for the two layers, 11.7 with this kernel
 // (1 unit = one [P,256] fp32 tensor).
 //
-// One persistent CTA per SM walks 128-row tiles.  Both products accumulate in tensor memory at the same time -- acc1 in columns
-// [0,256), acc2 in [256,512): the whole TMEM of the SM, so the accumulators are NOT double-buffered across tiles; the kernel stays
-// HBM-bound (about 650 KB of traffic per tile against ~15 k cycles of MMA + epilogue).  Warp roles: 0 = TMA producer (the
-// k-blocks of product 1, then of product 2, through one 3-stage ring), 1 = MMA issuer, 2..9 = eight epilogue warps (two per TMEM
-// lane quarter, four 32-column chunks each).  With 320 threads a lane may use ~200 registers: it prefetches the h and p rows of a
-// chunk (8 rows x 16 bytes each) BEFORE waiting for the accumulators, and the two accumulator chunks are transposed through two shared pads per warp.
+// One persistent CTA per SM walks 128-row tiles, each as two 128-COLUMN halves: acc1 and acc2 of a half-tile take 2 x 128 = 256
+// TMEM columns, so two half-tiles fit in the SM's 512 columns and the accumulators are double-buffered -- the MMA of half-tile
+// t+1 runs under the epilogue of half-tile t, as in gemm_tc.cu.  The A operands (dq_in, da_in) are fetched once per half; the
+// second fetch of a tile's rows is an L2 hit (128 rows, issued back to back by the same CTA).  (A first version with 256-column
+// accumulators used the whole TMEM per tile and serialised MMA and epilogue: 10.9 ms/step instead of 10.4.)
+// Warp roles: 0 = TMA producer (the k-blocks of product 1, then of product 2, through one 4-stage ring), 1 = MMA issuer,
+// 2..9 = eight epilogue warps (two per TMEM lane quarter, two 32-column chunks per half-tile each).  With 320 threads a lane may
+// use ~168 registers: it prefetches the h and p rows of a chunk (8 rows x 16 bytes each) BEFORE waiting for the accumulators;
+// the two accumulator chunks are transposed through two shared pads per warp.
 //
-// STATUS: opt-in (hsb_ctx_set_option("dual_bwd", 1) / HSB_DUAL_BWD=1), parity-tested, NOT the default.  Measured at 4096 x 128 on
-// one B200: 10.9 ms/step with it against 10.4 ms without -- the traffic drops as computed, but with the accumulators single-
-// buffered the TMA/MMA phase of a tile and its eight-warp epilogue run back to back, and that costs more than the 4.7 units
-// saved.  The way forward is to split N: 128 output columns per tile make acc1 + acc2 = 256 TMEM columns, which double-buffers
-// again (at the price of reading the A operands twice).
+// STATUS: opt-in (hsb_ctx_set_option("dual_bwd", 1) / HSB_DUAL_BWD=1), parity-tested (tests/test_gemm_gpu.py::test_gemm_dual_backward_layer,
+// tests/test_step_gpu.py::test_dual_accumulator_backward_equals_the_layer_by_layer_backward), NOT the default.  Measured at 4096 x 128
+// on one B200: 10.84 ms/step with it against 10.45 ms without (10.9 ms for the single-buffered first version).  The HBM traffic
+// drops as computed, but the epilogue -- two TMEM chunk transposes, two operand streams and two output streams per output chunk,
+// on eight warps -- is the bound, not HBM; it needs the sixteen-warp, register-lean epilogue of gemm_tc.cu to pay off.
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
 
 namespace hsb {
 
-constexpr int DU_STAGES = 3;
+constexpr int DU_STAGES = 4;
+constexpr int DU_NH = 128;                                 // output columns per half-tile
 constexpr int DU_A_BYTES = TC_BM * TC_BK * 4;              // 16 KB
-constexpr int DU_B_BYTES = 256 * TC_BK * 4;                // 32 KB
+constexpr int DU_B_BYTES = DU_NH * TC_BK * 4;              // 16 KB
 constexpr int DU_STAGE_BYTES = DU_A_BYTES + DU_B_BYTES;
 constexpr int DU_EPI_WARPS = 8;
 constexpr int DU_THREADS = 64 + 32 * DU_EPI_WARPS;
@@ -68,9 +72,9 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
     float* pads = reinterpret_cast<float*>(smem + DU_STAGES * DU_STAGE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + DU_STAGES * DU_STAGE_BYTES + DU_EPI_WARPS * DU_PAD_FLOATS * 4);
     uint64_t* empty = full + DU_STAGES;
-    uint64_t* tfull = empty + DU_STAGES;         // MMA -> epilogue: both accumulators of the tile are complete
-    uint64_t* tempty = tfull + 1;                // epilogue -> MMA: every epilogue warp has drained them
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 1);
+    uint64_t* tfull = empty + DU_STAGES;         // [2] MMA -> epilogue: both accumulators of the half-tile in buffer b are complete
+    uint64_t* tempty = tfull + 2;                // [2] epilogue -> MMA: every epilogue warp has drained buffer b
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb1 = (a.K1 + TC_BK - 1) / TC_BK, nkb2 = (a.K2 + TC_BK - 1) / TC_BK;
 
@@ -80,8 +84,7 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA2)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB2)) : "memory");
         for (int s = 0; s < DU_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(tfull, 1);
-        mbar_init(tempty, DU_EPI_WARPS);
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, DU_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -99,18 +102,20 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
                 const int m0 = tile * TC_BM;
-                for (int f = 0; f < nkb1 + nkb2; ++f, ++it) {
-                    const uint32_t s = it % DU_STAGES;
-                    const uint32_t ph = (it / DU_STAGES) & 1;
-                    mbar_wait(empty + s, ph ^ 1);
-                    mbar_expect_tx(full + s, DU_A_BYTES + DU_B_BYTES);
-                    uint8_t* st = smem + s * DU_STAGE_BYTES;
-                    if (f < nkb1) {
-                        tma_load_2d(&mapA1, full + s, st, f * TC_BK, m0);
-                        tma_load_2d(&mapB1, full + s, st + DU_A_BYTES, f * TC_BK, 0);
-                    } else {
-                        tma_load_2d(&mapA2, full + s, st, (f - nkb1) * TC_BK, m0);
-                        tma_load_2d(&mapB2, full + s, st + DU_A_BYTES, (f - nkb1) * TC_BK, 0);
+                for (int half = 0; half < 2; ++half) {
+                    for (int f = 0; f < nkb1 + nkb2; ++f, ++it) {
+                        const uint32_t s = it % DU_STAGES;
+                        const uint32_t ph = (it / DU_STAGES) & 1;
+                        mbar_wait(empty + s, ph ^ 1);
+                        mbar_expect_tx(full + s, DU_A_BYTES + DU_B_BYTES);
+                        uint8_t* st = smem + s * DU_STAGE_BYTES;
+                        if (f < nkb1) {
+                            tma_load_2d(&mapA1, full + s, st, f * TC_BK, m0);
+                            tma_load_2d(&mapB1, full + s, st + DU_A_BYTES, f * TC_BK, half * DU_NH);
+                        } else {
+                            tma_load_2d(&mapA2, full + s, st, (f - nkb1) * TC_BK, m0);
+                            tma_load_2d(&mapB2, full + s, st + DU_A_BYTES, (f - nkb1) * TC_BK, half * DU_NH);
+                        }
                     }
                 }
             }
@@ -119,101 +124,112 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             uint32_t it = 0;
-            int t = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++t) {
-                mbar_wait(tempty, (uint32_t)(t & 1) ^ 1);          // previous tile drained (free on first use)
-                tc_fence_after();
-                for (int f = 0; f < nkb1 + nkb2; ++f, ++it) {
-                    const uint32_t s = it % DU_STAGES, ph = (it / DU_STAGES) & 1;
-                    mbar_wait(full + s, ph);
+            int t = 0;                                                 // half-tiles issued
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                for (int half = 0; half < 2; ++half, ++t) {
+                    const int b = t & 1;
+                    const uint32_t use = (uint32_t)t >> 1;
+                    mbar_wait(tempty + b, (use & 1) ^ 1);              // epilogue has drained this buffer (free on first use)
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(smem + s * DU_STAGE_BYTES);
-                    const uint64_t ad = smem_desc_k_sw128(a0), bd = smem_desc_k_sw128(a0 + DU_A_BYTES);
-                    const bool second = f >= nkb1;
-                    const uint32_t acc = tmem + (second ? 256u : 0u);
-                    const int kb = second ? f - nkb1 : f;
+                    for (int f = 0; f < nkb1 + nkb2; ++f, ++it) {
+                        const uint32_t s = it % DU_STAGES, ph = (it / DU_STAGES) & 1;
+                        mbar_wait(full + s, ph);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(smem + s * DU_STAGE_BYTES);
+                        const uint64_t ad = smem_desc_k_sw128(a0), bd = smem_desc_k_sw128(a0 + DU_A_BYTES);
+                        const bool second = f >= nkb1;
+                        const uint32_t acc = tmem + (uint32_t)(b * 256) + (second ? (uint32_t)DU_NH : 0u);
+                        const int kb = second ? f - nkb1 : f;
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k) umma_tf32(acc, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-                    umma_commit(empty + s);
+                        for (int k = 0; k < TC_BK / 8; ++k) umma_tf32(acc, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                        umma_commit(empty + s);
+                    }
+                    umma_commit(tfull + b);
                 }
-                umma_commit(tfull);
             }
         }
     } else {
         // ===== epilogue: 8 warps =====
         const int ew = warp - 2;
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-        const int g = ew >> 2;                                    // 0 / 1: chunks g, g + 2, g + 4, g + 6
+        const int g = ew >> 2;                                    // 0 / 1: chunks g, g + 2 of every half-tile
         const uint32_t pad = smem_u32(pads + ew * DU_PAD_FLOATS);
         const int rl = lane >> 3;                                 // lane -> rows rl + 4 i (i = 0..7), columns n .. n + 3
         const int cl = 4 * (lane & 7);
         const int ro = a.round_out;
-        float4 cs[4];
+        float4 cs[4];                                             // column sums: [half][j]
 #pragma unroll
         for (int j = 0; j < 4; ++j) cs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         int t = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++t) {
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             const long long m_first = (long long)tile * TC_BM + q * 32;
             const long long left = a.M - m_first;
             const int rows = left < 32 ? (left > 0 ? (int)left : 0) : 32;
-            bool waited = false;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = g + 2 * j;
-                const int n = c * 32 + cl;
-                // (1) operands that do not depend on the accumulators: all eight rows of h and p
-                float4 hx[8], px[8];
+            for (int half = 0; half < 2; ++half, ++t) {
+                const int b = t & 1;
+                const uint32_t use = (uint32_t)t >> 1;
+                const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256);
+                bool waited = false;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = rl + 4 * i;
-                    hx[i] = make_float4(0.f, 0.f, 0.f, 0.f); px[i] = hx[i];
-                    if (r < rows) {
-                        hx[i] = __ldg(reinterpret_cast<const float4*>(a.aux + (m_first + r) * a.lda + n));
-                        px[i] = __ldg(reinterpret_cast<const float4*>(a.aux2 + (m_first + r) * a.lda2 + n));
-                    }
-                }
-                if (!waited) { mbar_wait(tfull, (uint32_t)(t & 1)); tc_fence_after(); waited = true; }
-                // (2) both accumulator chunks: TMEM -> the warp's two pads (read back transposed: this lane's 8 rows x 4 columns)
-                dual_chunk_to_pad(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), pad, lane);
-                dual_chunk_to_pad(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 + c * 32), pad + 32 * 36 * 4, lane);
-                if (j == 3) {                                     // last read of this tile's accumulators by this warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty);
-                }
-                __syncwarp();
-                // (4) math + coalesced 16-byte stores
+                for (int j = 0; j < 2; ++j) {
+                    const int c = g + 2 * j;                          // chunk within the half-tile (0..3)
+                    const int n = half * DU_NH + c * 32 + cl;
+                    // (1) operands that do not depend on the accumulators: all eight rows of h and p
+                    float4 hx[8], px[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = rl + 4 * i;
-                    if (r < rows) {
-                        const float4 a1 = lds128(pad + (uint32_t)(r * 36 + cl) * 4u);
-                        const float4 a2 = lds128(pad + (uint32_t)(32 * 36 + r * 36 + cl) * 4u);
-                        const float a1v[4] = {a1.x, a1.y, a1.z, a1.w};
-                        const float a2v[4] = {a2.x, a2.y, a2.z, a2.w};
-                        const float hv[4] = {hx[i].x, hx[i].y, hx[i].z, hx[i].w};
-                        const float pv[4] = {px[i].x, px[i].y, px[i].z, px[i].w};
-                        float o1[4], oa[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float sg = epi_sigma<true>(hv[k]);
-                            o1[k] = rtf32(a1v[k] * sg, ro);
-                            oa[k] = a2v[k] * sg + a1v[k] * pv[k] * 100.0f * (1.0f - sg);
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = rl + 4 * i;
+                        hx[i] = make_float4(0.f, 0.f, 0.f, 0.f); px[i] = hx[i];
+                        if (r < rows) {
+                            hx[i] = __ldg(reinterpret_cast<const float4*>(a.aux + (m_first + r) * a.lda + n));
+                            px[i] = __ldg(reinterpret_cast<const float4*>(a.aux2 + (m_first + r) * a.lda2 + n));
                         }
-                        cs[j].x += oa[0]; cs[j].y += oa[1]; cs[j].z += oa[2]; cs[j].w += oa[3];
-                        if (a.out1) *reinterpret_cast<float4*>(a.out1 + (m_first + r) * a.ldo1 + n) = make_float4(o1[0], o1[1], o1[2], o1[3]);
-                        *reinterpret_cast<float4*>(a.out + (m_first + r) * a.ldo + n) =
-                            make_float4(rtf32(oa[0], ro), rtf32(oa[1], ro), rtf32(oa[2], ro), rtf32(oa[3], ro));
                     }
+                    if (!waited) { mbar_wait(tfull + b, use & 1); tc_fence_after(); waited = true; }
+                    // (2) both accumulator chunks: TMEM -> the warp's two pads (read back transposed: this lane's 8 rows x 4 columns)
+                    dual_chunk_to_pad(tbase + (uint32_t)(c * 32), pad, lane);
+                    dual_chunk_to_pad(tbase + (uint32_t)(DU_NH + c * 32), pad + 32 * 36 * 4, lane);
+                    if (j == 1) {                                     // last read of this buffer by this warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty + b);
+                    }
+                    __syncwarp();
+                    // (3) math + coalesced 16-byte stores
+                    float4& csum = cs[half * 2 + j];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = rl + 4 * i;
+                        if (r < rows) {
+                            const float4 a1 = lds128(pad + (uint32_t)(r * 36 + cl) * 4u);
+                            const float4 a2 = lds128(pad + (uint32_t)(32 * 36 + r * 36 + cl) * 4u);
+                            const float a1v[4] = {a1.x, a1.y, a1.z, a1.w};
+                            const float a2v[4] = {a2.x, a2.y, a2.z, a2.w};
+                            const float hv[4] = {hx[i].x, hx[i].y, hx[i].z, hx[i].w};
+                            const float pv[4] = {px[i].x, px[i].y, px[i].z, px[i].w};
+                            float o1[4], oa[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float sg = epi_sigma<true>(hv[k]);
+                                o1[k] = rtf32(a1v[k] * sg, ro);
+                                oa[k] = a2v[k] * sg + a1v[k] * pv[k] * 100.0f * (1.0f - sg);
+                            }
+                            csum.x += oa[0]; csum.y += oa[1]; csum.z += oa[2]; csum.w += oa[3];
+                            if (a.out1) *reinterpret_cast<float4*>(a.out1 + (m_first + r) * a.ldo1 + n) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+                            *reinterpret_cast<float4*>(a.out + (m_first + r) * a.ldo + n) =
+                                make_float4(rtf32(oa[0], ro), rtf32(oa[1], ro), rtf32(oa[2], ro), rtf32(oa[3], ro));
+                        }
+                    }
+                    __syncwarp();                                     // the pads are reused by the next chunk
                 }
-                __syncwarp();                                     // the pad is reused by the next chunk
             }
         }
         if (a.colsum) {                                           // lanes l, l+8, l+16, l+24 hold the same four columns
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = (g + 2 * j) * 32 + cl;
-                float v[4] = {cs[j].x, cs[j].y, cs[j].z, cs[j].w};
+            for (int hj = 0; hj < 4; ++hj) {
+                const int n = (hj >> 1) * DU_NH + (g + 2 * (hj & 1)) * 32 + cl;
+                float v[4] = {cs[hj].x, cs[hj].y, cs[hj].z, cs[hj].w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);
@@ -256,13 +272,13 @@ int gemm_dual_tc(const float* A1, long long ld1, const float* B1, long long ldb1
         return HSB_ERR_ARG;
     }
     CUtensorMap mA1, mB1, mA2, mB2;
-    if (!tc_make_map(&mA1, A1, M, K1, ld1, TC_BM) || !tc_make_map(&mB1, B1, 256, K1, ldb1, 256) ||
-        !tc_make_map(&mA2, A2, M, K2, ld2, TC_BM) || !tc_make_map(&mB2, B2, 256, K2, ldb2, 256)) {
+    if (!tc_make_map(&mA1, A1, M, K1, ld1, TC_BM) || !tc_make_map(&mB1, B1, 256, K1, ldb1, DU_NH) ||
+        !tc_make_map(&mA2, A2, M, K2, ld2, TC_BM) || !tc_make_map(&mB2, B2, 256, K2, ldb2, DU_NH)) {
         set_error("gemm_dual: cuTensorMapEncodeTiled failed");
         return HSB_ERR_CUDA;
     }
-    // instruction descriptor: D = f32, A = B = tf32, K-major both, N = 256, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    // instruction descriptor: D = f32, A = B = tf32, K-major both, N = 128 (one half-tile), M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DU_NH >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     DualArgs a{};
     a.M = M; a.K1 = K1; a.K2 = K2; a.aux = aux; a.lda = lda; a.aux2 = aux2; a.lda2 = lda2; a.out1 = out1; a.ldo1 = ldo1;
     a.out = out; a.ldo = ldo; a.colsum = colsum; a.round_out = round_out;
