@@ -15,28 +15,30 @@
 // t+1 runs under the epilogue of half-tile t, as in gemm_tc.cu.  The A operands (dq_in, da_in) are fetched once per half; the
 // second fetch of a tile's rows is an L2 hit (128 rows, issued back to back by the same CTA).  (A first version with 256-column
 // accumulators used the whole TMEM per tile and serialised MMA and epilogue: 10.9 ms/step instead of 10.4.)
-// Warp roles: 0 = TMA producer (the k-blocks of product 1, then of product 2, through one 4-stage ring), 1 = MMA issuer,
-// 2..9 = eight epilogue warps (two per TMEM lane quarter, two 32-column chunks per half-tile each).  With 320 threads a lane may
-// use ~168 registers: it prefetches the h and p rows of a chunk (8 rows x 16 bytes each) BEFORE waiting for the accumulators;
-// the two accumulator chunks are transposed through two shared pads per warp.
+// Warp roles: 0 = TMA producer (the k-blocks of product 1, then of product 2, through one 2-stage ring), 1 = MMA issuer,
+// 2..17 = sixteen epilogue warps (four per TMEM lane quarter, one 32-column chunk of every half-tile each): a chunk's latency
+// chain (operand rows from HBM -> accumulators from TMEM -> stores) is long, throughput comes from sixteen chunks in flight.
+// A lane requests the h rows of its chunk BEFORE waiting for the accumulators; the two accumulator chunks are transposed
+// through two shared pads per warp (147 KB: hence the 2-stage ring of 32 KB stages).
 //
-// STATUS: opt-in (hsb_ctx_set_option("dual_bwd", 1) / HSB_DUAL_BWD=1), parity-tested (tests/test_gemm_gpu.py::test_gemm_dual_backward_layer,
-// tests/test_step_gpu.py::test_dual_accumulator_backward_equals_the_layer_by_layer_backward), NOT the default.  Measured at 4096 x 128
-// on one B200: 10.84 ms/step with it against 10.45 ms without (10.9 ms for the single-buffered first version).  The HBM traffic
-// drops as computed, but the epilogue -- two TMEM chunk transposes, two operand streams and two output streams per output chunk,
-// on eight warps -- is the bound, not HBM; it needs the sixteen-warp, register-lean epilogue of gemm_tc.cu to pay off.
+// MEASURED (4096 x 128, one B200, ms/step with / without this kernel): 10.06 / 10.43 with this version.  Two earlier versions
+// were correct but slower than the layer-by-layer path: 256-column accumulators single-buffered over the whole TMEM (10.9), and
+// 128-column halves double-buffered but drained by eight epilogue warps with two chunks each (10.84) -- the epilogue of a chunk
+// is a long latency chain, and only the number of chunks in flight per SM hides it.
+// Fast mode default for the reverse-mode slots (scene pass, background patch); hsb_ctx_set_option("dual_bwd", 0) / HSB_DUAL_BWD=0
+// selects the EPI_BWD_CHAIN + EPI_BWD_SP sequence (tests/test_step_gpu.py compares the two).
 #include "common.cuh"
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
 
 namespace hsb {
 
-constexpr int DU_STAGES = 4;
+constexpr int DU_STAGES = 2;
 constexpr int DU_NH = 128;                                 // output columns per half-tile
 constexpr int DU_A_BYTES = TC_BM * TC_BK * 4;              // 16 KB
 constexpr int DU_B_BYTES = DU_NH * TC_BK * 4;              // 16 KB
 constexpr int DU_STAGE_BYTES = DU_A_BYTES + DU_B_BYTES;
-constexpr int DU_EPI_WARPS = 8;
+constexpr int DU_EPI_WARPS = 16;
 constexpr int DU_THREADS = 64 + 32 * DU_EPI_WARPS;
 constexpr int DU_PAD_FLOATS = 2 * 32 * 36;                // two transpose pads per warp: acc1 chunk, acc2 chunk
 constexpr int DU_SMEM_BYTES = DU_STAGES * DU_STAGE_BYTES + DU_EPI_WARPS * DU_PAD_FLOATS * 4 + 256 + 1024;
@@ -149,64 +151,64 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
             }
         }
     } else {
-        // ===== epilogue: 8 warps =====
+        // ===== epilogue: 16 warps, one 32-column chunk of every half-tile each =====
         const int ew = warp - 2;
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-        const int g = ew >> 2;                                    // 0 / 1: chunks g, g + 2 of every half-tile
+        const int c = ew >> 2;                                    // chunk within the half-tile (0..3)
         const uint32_t pad = smem_u32(pads + ew * DU_PAD_FLOATS);
         const int rl = lane >> 3;                                 // lane -> rows rl + 4 i (i = 0..7), columns n .. n + 3
         const int cl = 4 * (lane & 7);
         const int ro = a.round_out;
-        float4 cs[4];                                             // column sums: [half][j]
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 cs0 = make_float4(0.f, 0.f, 0.f, 0.f), cs1 = cs0;                              // column sums per half
         int t = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             const long long m_first = (long long)tile * TC_BM + q * 32;
             const long long left = a.M - m_first;
             const int rows = left < 32 ? (left > 0 ? (int)left : 0) : 32;
-#pragma unroll
+#pragma unroll 1
             for (int half = 0; half < 2; ++half, ++t) {
+                float4 csum = half ? cs1 : cs0;
                 const int b = t & 1;
                 const uint32_t use = (uint32_t)t >> 1;
                 const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256);
-                bool waited = false;
+                const int n = half * DU_NH + c * 32 + cl;
+                // (1) h does not depend on the accumulators: all eight rows of this lane are requested first
+                float4 hx[8];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int c = g + 2 * j;                          // chunk within the half-tile (0..3)
-                    const int n = half * DU_NH + c * 32 + cl;
-                    // (1) operands that do not depend on the accumulators: all eight rows of h and p
-                    float4 hx[8], px[8];
+                for (int i = 0; i < 8; ++i) {
+                    const int r = rl + 4 * i;
+                    hx[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < rows) hx[i] = __ldg(reinterpret_cast<const float4*>(a.aux + (m_first + r) * a.lda + n));
+                }
+                mbar_wait(tfull + b, use & 1);
+                tc_fence_after();
+                // (2) both accumulator chunks: TMEM -> the warp's two pads (read back transposed: this lane's 8 rows x 4 columns)
+                dual_chunk_to_pad(tbase + (uint32_t)(c * 32), pad, lane);
+                dual_chunk_to_pad(tbase + (uint32_t)(DU_NH + c * 32), pad + 32 * 36 * 4, lane);
+                tc_fence_before();                                // last read of this buffer by this warp
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty + b);
+                __syncwarp();
+                // (3) math + coalesced 16-byte stores, four rows at a time (p is fetched per group: register budget)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = rl + 4 * i;
-                        hx[i] = make_float4(0.f, 0.f, 0.f, 0.f); px[i] = hx[i];
-                        if (r < rows) {
-                            hx[i] = __ldg(reinterpret_cast<const float4*>(a.aux + (m_first + r) * a.lda + n));
-                            px[i] = __ldg(reinterpret_cast<const float4*>(a.aux2 + (m_first + r) * a.lda2 + n));
-                        }
+                for (int hh = 0; hh < 2; ++hh) {
+                    float4 px[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = rl + 4 * (4 * hh + i);
+                        px[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r < rows) px[i] = __ldg(reinterpret_cast<const float4*>(a.aux2 + (m_first + r) * a.lda2 + n));
                     }
-                    if (!waited) { mbar_wait(tfull + b, use & 1); tc_fence_after(); waited = true; }
-                    // (2) both accumulator chunks: TMEM -> the warp's two pads (read back transposed: this lane's 8 rows x 4 columns)
-                    dual_chunk_to_pad(tbase + (uint32_t)(c * 32), pad, lane);
-                    dual_chunk_to_pad(tbase + (uint32_t)(DU_NH + c * 32), pad + 32 * 36 * 4, lane);
-                    if (j == 1) {                                     // last read of this buffer by this warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty + b);
-                    }
-                    __syncwarp();
-                    // (3) math + coalesced 16-byte stores
-                    float4& csum = cs[half * 2 + j];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = rl + 4 * i;
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = rl + 4 * (4 * hh + i);
                         if (r < rows) {
                             const float4 a1 = lds128(pad + (uint32_t)(r * 36 + cl) * 4u);
                             const float4 a2 = lds128(pad + (uint32_t)(32 * 36 + r * 36 + cl) * 4u);
+                            const float4 h4 = hx[4 * hh + i];
                             const float a1v[4] = {a1.x, a1.y, a1.z, a1.w};
                             const float a2v[4] = {a2.x, a2.y, a2.z, a2.w};
-                            const float hv[4] = {hx[i].x, hx[i].y, hx[i].z, hx[i].w};
+                            const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
                             const float pv[4] = {px[i].x, px[i].y, px[i].z, px[i].w};
                             float o1[4], oa[4];
 #pragma unroll
@@ -221,15 +223,17 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
                                 make_float4(rtf32(oa[0], ro), rtf32(oa[1], ro), rtf32(oa[2], ro), rtf32(oa[3], ro));
                         }
                     }
-                    __syncwarp();                                     // the pads are reused by the next chunk
                 }
+                if (half) cs1 = csum; else cs0 = csum;
+                __syncwarp();                                     // the pads are reused by the next half-tile
             }
         }
         if (a.colsum) {                                           // lanes l, l+8, l+16, l+24 hold the same four columns
 #pragma unroll
-            for (int hj = 0; hj < 4; ++hj) {
-                const int n = (hj >> 1) * DU_NH + (g + 2 * (hj & 1)) * 32 + cl;
-                float v[4] = {cs[hj].x, cs[hj].y, cs[hj].z, cs[hj].w};
+            for (int half = 0; half < 2; ++half) {
+                const int n = half * DU_NH + c * 32 + cl;
+                const float4 cc = half ? cs1 : cs0;
+                float v[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);

@@ -82,7 +82,7 @@ struct Ctx {
     Slot slot[3];
     Slot scratch;   // X, H0, H1, H2, SR only: hsb_sdf_values between a slot's forward and its backward
     long long block_tiles = 0;   // L2 blocking of the ray passes: 128-row tiles per block of rays (0 = one block)
-    bool dual_bwd = false;       // chain + SDF-net backward through the dual-accumulator layer kernel (csrc/dual_tc.cu)
+    bool dual_bwd = true;        // fast mode: chain + SDF-net backward through the dual-accumulator layer kernel (csrc/dual_tc.cu)
     float* P(int seg) const { return params + off[seg]; }
     float* Gp(int seg) const { return grads + off[seg]; }
 };
@@ -471,7 +471,7 @@ extern "C" int hsb_ctx_create(const hsb_step_cfg* cfg, float* params, float* gra
     const char* bt = getenv("HSB_BLOCK_TILES");
     c->block_tiles = bt ? atoll(bt) : 0;                        // off by default: see the note at slot_block
     const char* du = getenv("HSB_DUAL_BWD");
-    c->dual_bwd = du ? atoi(du) != 0 : false;
+    c->dual_bwd = du ? atoi(du) != 0 : true;
     *out = reinterpret_cast<hsb_ctx*>(c);
     return HSB_OK;
 }

@@ -486,7 +486,7 @@ def test_ray_blocked_passes_equal_the_unblocked_pass():
 
 
 def test_dual_accumulator_backward_equals_the_layer_by_layer_backward():
-    """Opt-in path (hsb_ctx_set_option "dual_bwd"): chain + SDF-net backward through csrc/dual_tc.cu (two TMEM accumulators per
+    """Fast-mode default (switch: hsb_ctx_set_option "dual_bwd"): chain + SDF-net backward through csrc/dual_tc.cu (two TMEM accumulators per
     tile, the cross terms never stored) must give the gradients of the default EPI_BWD_CHAIN + EPI_BWD_SP sequence -- same
     TF32-rounded operands, same products; only the association of the final sums differs."""
     from holoscene_b200 import engine as E
