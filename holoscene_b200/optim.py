@@ -18,6 +18,8 @@ class StageOneAdam:
                        dict(name="net", lo=o[2], hi=o[24], lr=lr),
                        dict(name="density", lo=o[24], hi=o[25], lr=lr)]
         self.betas, self.eps = betas, eps
+        self.base_lrs = [g["lr"] for g in self.groups]
+        self.sched_steps = 0
         self.gamma = decay_rate ** (1.0 / decay_steps)
         self.step_count = 0
         self.exp_avg = torch.zeros_like(eng.params)
@@ -44,6 +46,31 @@ class StageOneAdam:
     def scheduler_step(self):
         for g in self.groups:
             g["lr"] *= self.gamma
+        self.sched_steps += 1
+
+    # ---- the reference trainer's checkpoint formats (holoscene_b200/checkpoint.py) ---------------------------------
+    def torch_state_dict(self):
+        """torch.optim.Adam.state_dict() layout over the reference's three parameter groups."""
+        from . import checkpoint
+        return checkpoint.to_torch_adam_state_dict(self.model, self.exp_avg, self.exp_avg_sq, self.step_count,
+                                                   [g["lr"] for g in self.groups], self.base_lrs, self.betas, self.eps)
+
+    def load_torch_state_dict(self, sd):
+        from . import checkpoint
+        self.step_count, lrs = checkpoint.from_torch_adam_state_dict(self.model, sd, self.exp_avg, self.exp_avg_sq)
+        for g, lr in zip(self.groups, lrs):
+            g["lr"] = lr
+
+    def scheduler_state_dict(self):
+        from . import checkpoint
+        return checkpoint.scheduler_state_dict(self.gamma, self.base_lrs, [g["lr"] for g in self.groups], self.sched_steps)
+
+    def load_scheduler_state_dict(self, sd):
+        self.gamma = float(sd["gamma"])
+        self.base_lrs = [float(x) for x in sd["base_lrs"]]
+        self.sched_steps = int(sd["last_epoch"])
+        for g, lr in zip(self.groups, sd["_last_lr"]):
+            g["lr"] = float(lr)
 
     def total_grad_norm(self):
         """sqrt(sum g^2) of the last step (device scalar; reading it is the only sync)."""

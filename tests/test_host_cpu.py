@@ -148,3 +148,43 @@ def test_forward_without_cuda_fails_loudly():
     m = HoloSceneNetwork(c.get_config("model"))
     with pytest.raises(RuntimeError):
         m({"uv": torch.zeros(1, 4, 2), "intrinsics": torch.eye(4)[None], "pose": torch.eye(4)[None]}, torch.tensor([0]))
+
+
+def test_optimizer_checkpoint_round_trips_through_torch_adam():
+    """N4: the fused optimizer's flat moments <-> torch.optim.Adam.state_dict() over the reference's three parameter groups
+    (training/holoscene_train.py:156-164).  A real torch Adam built the reference's way must accept the converted state, hold
+    exactly the flat buffers' slices, and convert back bit for bit."""
+    from bench import model_conf
+    from holoscene_b200 import checkpoint
+    from holoscene_b200.network import HoloSceneNetwork
+    w = dict(name="t", R=8, K=3, N_samples=8, N_samples_eval=16, N_samples_extra=4, logmap=8)
+    torch.manual_seed(0)
+    m = HoloSceneNetwork(model_conf(w))
+    groups = checkpoint.reference_param_groups(m)
+    assert groups[0] == ["implicit_network.encoding.embeddings", "implicit_network.color_encoding.embeddings"]
+    assert groups[1][:3] == ["implicit_network.lin0.bias", "implicit_network.lin0.weight_g", "implicit_network.lin0.weight_v"]
+    assert groups[2] == ["density.beta"] and sum(len(g) for g in groups) == len(list(m.parameters()))
+    seg, total = checkpoint._segments(m)
+    g = torch.Generator().manual_seed(1)
+    ea, eas = torch.randn(total, generator=g), torch.rand(total, generator=g)
+    sd = checkpoint.to_torch_adam_state_dict(m, ea, eas, step=7, lrs=[1e-2, 5e-4, 5e-4], initial_lrs=[1e-2, 5e-4, 5e-4])
+    net = m.implicit_network
+    ref_opt = torch.optim.Adam([
+        {"name": "encoding", "params": list(net.grid_parameters()), "lr": 1e-2},
+        {"name": "net", "params": list(net.mlp_parameters()) + list(m.rendering_network.parameters()), "lr": 5e-4},
+        {"name": "density", "params": list(m.density.parameters()), "lr": 5e-4}], betas=(0.9, 0.99), eps=1e-15)
+    ref_opt.load_state_dict(sd)                       # the reference's resume path accepts it
+    named = dict(m.named_parameters())
+    for n, (o, k, shape) in seg.items():
+        st = ref_opt.state[named[n]]
+        assert torch.equal(st["exp_avg"].reshape(-1), ea[o:o + k]) and float(st["step"]) == 7.0
+    ea2, eas2 = torch.empty(total), torch.empty(total)
+    step, lrs = checkpoint.from_torch_adam_state_dict(m, ref_opt.state_dict(), ea2, eas2)
+    assert step == 7 and lrs == [1e-2, 5e-4, 5e-4]
+    covered = torch.zeros(total, dtype=torch.bool)
+    for o, k, _ in seg.values():
+        covered[o:o + k] = True
+    assert torch.equal(ea2[covered], ea[covered]) and torch.equal(eas2[covered], eas[covered])
+    sched = torch.optim.lr_scheduler.ExponentialLR(ref_opt, 0.99)
+    sched.load_state_dict(checkpoint.scheduler_state_dict(0.99, [1e-2, 5e-4, 5e-4], [9e-3, 4e-4, 4e-4], 11))
+    assert sched.last_epoch == 11 and sched.get_last_lr() == [9e-3, 4e-4, 4e-4]

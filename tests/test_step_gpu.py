@@ -517,3 +517,37 @@ def test_dual_accumulator_backward_equals_the_layer_by_layer_backward():
         grads[dual] = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
     for n in grads[0]:
         assert common.rel_err(grads[1][n].cpu(), grads[0][n].cpu()) < 2e-4, n
+
+
+def test_checkpoint_files_round_trip(tmp_path):
+    """N4: the reference's three-file checkpoint layout written from the fused model / optimizer and read back."""
+    from holoscene_b200 import checkpoint
+    from holoscene_b200.optim import StageOneAdam
+    g = common.load_golden("step_train")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    uv, pose, K, gt, _ = common.golden_inputs(g)
+    m = build_model(cfg, sd, False).train()
+    opt = StageOneAdam(m)
+    loss = make_loss()
+    for it in (1, 2):
+        opt.zero_grad()
+        out = m({"uv": uv.clone().cuda(), "intrinsics": K.cuda(), "pose": pose.cuda()}, None, iter_step=it)
+        out["iter_step"] = it
+        loss(out, gt)["loss"].backward()
+        opt.step()
+        opt.scheduler_step()
+    checkpoint.save_checkpoints(str(tmp_path), 3, m, opt)
+    for sub in checkpoint.SUBDIRS:
+        assert (tmp_path / sub / "3.pth").exists() and (tmp_path / sub / "latest.pth").exists()
+    saved = torch.load(tmp_path / "OptimizerParameters" / "3.pth")["optimizer_state_dict"]
+    assert [grp["name"] for grp in saved["param_groups"]] == ["encoding", "net", "density"]
+    m2 = build_model(cfg, common.seeded_state_dict(cfg, seed=1), False).train()
+    opt2 = StageOneAdam(m2)
+    assert checkpoint.load_checkpoints(str(tmp_path), "latest", m2, opt2) == 3
+    for (n, a), (_, b) in zip(m.named_parameters(), m2.named_parameters()):
+        assert torch.equal(a, b), n
+    seg, _ = checkpoint._segments(m)
+    for n, (o, k, _) in seg.items():
+        assert torch.equal(opt.exp_avg[o:o + k], opt2.exp_avg[o:o + k]) and torch.equal(opt.exp_avg_sq[o:o + k], opt2.exp_avg_sq[o:o + k]), n
+    assert opt2.step_count == 2 and [grp["lr"] for grp in opt2.groups] == [grp["lr"] for grp in opt.groups]
