@@ -170,7 +170,19 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: whatever libraries print while the communicator comes up (NCCL's version banner
+        # goes to stdout) is sent to stderr instead
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from holoscene_b200 import _lib, engine as E, synthetic
     from holoscene_b200.loss import HoloSceneLoss
