@@ -573,8 +573,6 @@ extern "C" int hsb_render_forward(hsb_ctx* h, int32_t slot_id, const float* o, c
     const long long N = (long long)R * S;
     if (N > s.cap_points || R > s.cap_rays) { set_error("hsb_render_forward: batch exceeds slot capacity"); return HSB_ERR_ARG; }
     const bool scene = slot_id == HSB_SLOT_MAIN;
-    const hsb_step_cfg& f = c->cfg;
-    const int P = f.precise;
     s.N = N; s.R = R; s.S = S; s.nseed = 1; s.mode = scene ? 0 : 1;
     cudaMemcpyAsync(s.ZV, z, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(s.DSCALE, depth_scale, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -602,8 +600,6 @@ extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_r
     Slot& s = c->slot[slot_id];
     if (s.N == 0) { set_error("hsb_render_backward: no forward recorded in this slot"); return HSB_ERR_ARG; }
     const bool scene = slot_id == HSB_SLOT_MAIN;
-    const hsb_step_cfg& f = c->cfg;
-    const int P = f.precise;
     const int R = s.R, S = s.S, K = c->K;
     const int rb = block_rays(c->block_tiles, R, S);
     for (int r0 = 0; r0 < R; r0 += rb) {
