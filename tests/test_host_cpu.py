@@ -188,3 +188,61 @@ def test_optimizer_checkpoint_round_trips_through_torch_adam():
     sched = torch.optim.lr_scheduler.ExponentialLR(ref_opt, 0.99)
     sched.load_state_dict(checkpoint.scheduler_state_dict(0.99, [1e-2, 5e-4, 5e-4], [9e-3, 4e-4, 4e-4], 11))
     assert sched.last_epoch == 11 and sched.get_last_lr() == [9e-3, 4e-4, 4e-4]
+
+
+def _reference_pixel_sampling(segs, classes, sampling_size, gen):
+    """datasets/ns_dataset.py:411-432 restated (one nonzero + randperm per class)."""
+    half = sampling_size // 2
+    per = half // len(classes)
+    bg = half - per * (len(classes) - 1)
+    out = []
+    for i, c in enumerate(classes):
+        m = torch.nonzero(segs.reshape(-1) == c).reshape(-1)
+        q = bg if i == 0 else per
+        if len(m) > q:
+            m = m[torch.randperm(len(m), generator=gen)[:q]]
+        out.append(m)
+    out.append(torch.randperm(segs.numel(), generator=gen)[: sampling_size - half])
+    return torch.cat(out, 0)
+
+
+def test_pixel_sampler_matches_reference_semantics():
+    """N4: the keyed-sort per-class pixel sampler selects, class by class, what the reference's loop selects in distribution:
+    same block order and block sizes (incl. classes smaller than their quota and the background remainder), members of the right
+    class, no repeats inside a class block, uniform tail of the right length; and every pixel of a class is equally likely."""
+    from holoscene_b200 import pixel_sampler
+    g = torch.Generator().manual_seed(0)
+    H = W = 48
+    segs = torch.zeros(H * W, 1, dtype=torch.int64)
+    segs[:300, 0] = 3
+    segs[300:310, 0] = 7          # a class smaller than its quota
+    segs[310:900, 0] = 5
+    classes = [0, 3, 7, 5]        # background first, then the objects present in the frame
+    S = 256
+    ref = _reference_pixel_sampling(segs, classes, S, g)
+    got = pixel_sampler.sample_pixels(segs, classes, S, generator=g)
+    assert got.dtype == torch.int64 and got.shape == ref.shape
+    bg, per, n_uni = pixel_sampler.class_quotas(len(classes), S)
+    assert (bg, per, n_uni) == (128 - 3 * 32, 32, 128)
+    sizes = [bg, per, 10, per]
+    pos = 0
+    for c, n in zip(classes, sizes):
+        blk = got[pos:pos + n]
+        assert bool((segs[blk, 0] == c).all()) and blk.unique().numel() == n
+        pos += n
+    tail = got[pos:]
+    assert tail.numel() == n_uni and tail.unique().numel() == n_uni and int(tail.max()) < H * W
+    # uniformity inside a class: class 3 has 300 pixels, 32 picks per call -> each pixel is picked with probability 32/300
+    hits = torch.zeros(H * W)
+    for _ in range(400):
+        idx = pixel_sampler.sample_pixels(segs, classes, S, generator=g)
+        hits[idx[bg:bg + per]] += 1
+    freq = hits[:300] / 400
+    assert abs(float(freq.mean()) - 32 / 300) < 1e-6 and float(freq.std()) < 0.03 and float(hits[300:].sum()) == 0.0
+    # gather: the sampled view of a frame
+    sample = {"uv": torch.rand(H * W, 2), "intrinsics": torch.eye(4), "pose": torch.eye(4)}
+    gt = {"rgb": torch.rand(H * W, 3), "depth": torch.rand(H * W, 1), "mask": torch.ones(H * W, 1), "normal": torch.rand(H * W, 3),
+          "segs": segs}
+    s2, gt2 = pixel_sampler.gather_batch(sample, gt, got)
+    assert s2["uv"].shape == (got.numel(), 2) and gt2["rgb"].shape == (got.numel(), 3) and gt2["full_rgb"].shape == (H * W, 3)
+    assert torch.equal(gt2["segs"][:, 0], segs[got, 0])
