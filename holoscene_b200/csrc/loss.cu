@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) loss_ray_kernel(hsb_loss_cfg f, const flo
         const bool m = pos && neg && (mask_gt[r] > 0.5f);
         // opacity BCE over the K channels
         const int seg = (int)segs[r];
+        if (lane == 0 && (seg < 0 || seg >= f.K)) acc[HSB_LOSS_SCRATCH_DOUBLES - 1] = 1.0;     // class id outside [0, K): flagged, see loss_final_kernel
         const float gk = f.w_sem / ((float)f.R * (float)f.K);
         float bce = 0.0f;
         for (int k = lane; k < f.K; k += 32) {
@@ -201,11 +202,13 @@ __global__ void __launch_bounds__(1024) loss_final_kernel(hsb_loss_cfg f, const 
     // u = A^-1 [sum phi' d, sum phi']  (A symmetric)
     const double u0 = (N * tot[1] - sd * tot[2]) / det, u1 = (sdd * tot[2] - sd * tot[1]) / det;
     const double k = (double)f.w_depth / N;
+    // a zero depth weight must not leak the NaN of a singular scale/shift system (R == 1, constant depth) into the backward: 0 * NaN = NaN
+    const bool depth_off = f.w_depth == 0.0f;
     for (int r = threadIdx.x; r < f.R; r += blockDim.x) {
         const double d = (double)depth[r], g = (double)depth_gt[r];
         const double e = w * d + q - g;
         const double dp = e * e <= 1.0 ? 2.0 * e : 0.0;
-        d_depth[r] = (float)(k * (dp * w + u0 * (g - 2.0 * d * w - q) - u1 * w));
+        d_depth[r] = depth_off ? 0.0f : (float)(k * (dp * w + u0 * (g - 2.0 * d * w - q) - u1 * w));
     }
     if (threadIdx.x == 0) {
         const double rgb_l = acc[A_RGB] / (3.0 * N), nl1 = acc[A_NL1] / N, ncos = acc[A_NCOS] / N;
@@ -216,6 +219,9 @@ __global__ void __launch_bounds__(1024) loss_final_kernel(hsb_loss_cfg f, const 
         losses[5] = (float)nl1; losses[6] = (float)ncos; losses[7] = (float)sem;
         losses[0] = (float)(f.w_rgb * rgb_l + f.w_eik * eik + f.w_smooth * smooth + f.w_depth * dl + f.w_nl1 * nl1 + f.w_ncos * ncos +
                             f.w_sem * sem);
+        // a class id outside [0, K) makes the reference's F.one_hot raise (model/loss.py:487-492); here (no host sync on the hot
+        // path) the step's loss becomes NaN, which the trainer's logging shows at once
+        if (acc[HSB_LOSS_SCRATCH_DOUBLES - 1] != 0.0) losses[0] = __int_as_float(0x7fc00000);
     }
 }
 

@@ -101,7 +101,8 @@ static void carve_slot(Ctx* c, int idx, const char* pre, long long points, int m
     s.cap_points = points; s.cap_rows = points * max_seeds; s.cap_rays = rays; s.with_color = color; s.tangent = tangent;
     const long long N = points, E = s.cap_rows;
     const int Kp = c->Kp;
-    auto nm = [&](const char* n) { static char b[64]; snprintf(b, sizeof b, "%s.%s", pre, n); return (const char*)b; };
+    std::string nmbuf;
+    auto nm = [&](const char* n) { nmbuf = std::string(pre) + "." + n; return nmbuf.c_str(); };
     s.X = carve(c, nm("X"), N, 3, dry);        s.H0 = carve(c, nm("H0"), N, LD_H0, dry);  s.DY = carve(c, nm("DY"), N, 96, dry);
     s.H1 = carve(c, nm("H1"), N, 256, dry);    s.H2 = carve(c, nm("H2"), N, 256, dry);    s.SR = carve(c, nm("SR"), N, Kp, dry);
     s.SDF = carve(c, nm("SDF"), N, 1, dry);    s.KS = (int*)carve(c, nm("KS"), N, 1, dry);
@@ -163,6 +164,9 @@ static void carve_all(Ctx* c, bool dry) {
 }
 
 #define TRY(x) do { int _e = (x); if (_e != HSB_OK) return _e; } while (0)
+// cudaMemsetAsync / cudaMemcpyAsync with the library's status convention
+#define TRYCUDA(x) do { cudaError_t _c = (x); if (_c != cudaSuccess) { set_error((std::string(#x) + ": " + cudaGetErrorString(_c)).c_str()); return HSB_ERR_CUDA; } } while (0)
+#define CTX_OR_FAIL(c, fn) do { if (!(c)) { set_error(fn ": null context"); return HSB_ERR_ARG; } } while (0)
 
 // ---- L2 blocking --------------------------------------------------------------------------------------------------------
 // A ray pass is a chain of ~45 (forward) / ~50 (backward) kernels in which almost every kernel's main input is the tensor the
@@ -240,8 +244,8 @@ static int chain_backward(Ctx* c, Slot& s, long long N, int nseed, bool with_rin
     TRY(launch_chain_end_bwd(s.dG, with_rin ? s.dRIN : nullptr, with_rin ? s.RIN : nullptr, s.H0, s.DY, N, nseed, s.dQ0, rt, st));
     const int atomic = nseed > 1;
     if (atomic) {
-        cudaMemsetAsync(s.dA1x, 0, (size_t)N * 256 * sizeof(float), st);
-        cudaMemsetAsync(s.dA2x, 0, (size_t)N * 256 * sizeof(float), st);
+        TRYCUDA(cudaMemsetAsync(s.dA1x, 0, (size_t)N * 256 * sizeof(float), st));
+        TRYCUDA(cudaMemsetAsync(s.dA2x, 0, (size_t)N * 256 * sizeof(float), st));
     }
     Epi e = epi(EPI_BWD_CHAIN, s.dQ1, 256, rt);
     e.aux = s.H1; e.lda = 256; e.aux_rows = N; e.aux2 = s.P1; e.lda2 = 256; e.out2 = s.dA1x; e.ldo2 = 256; e.atomic2 = atomic;
@@ -332,8 +336,8 @@ static int tangent_backward(Ctx* c, Slot& s, long long N, cudaStream_t st) {
     const int P = c->cfg.precise;
     const long long E = 3 * N;
     const int rt = c->rtf();
-    cudaMemsetAsync(s.dA1x, 0, (size_t)N * 256 * sizeof(float), st);
-    cudaMemsetAsync(s.dA2x, 0, (size_t)N * 256 * sizeof(float), st);
+    TRYCUDA(cudaMemsetAsync(s.dA1x, 0, (size_t)N * 256 * sizeof(float), st));
+    TRYCUDA(cudaMemsetAsync(s.dA2x, 0, (size_t)N * 256 * sizeof(float), st));
     Epi e = epi(EPI_BWD_CHAIN, s.R2, 256, rt);
     e.aux = s.H2; e.lda = 256; e.aux_rows = N; e.aux2 = s.T2; e.lda2 = 256; e.out2 = s.dA2x; e.ldo2 = 256; e.atomic2 = 1;
     TRY(gemm_tn(s.dJ, c->Kp, c->W2eT, c->Kp, E, 256, c->Kp, e, P, st));
@@ -480,6 +484,7 @@ extern "C" void hsb_ctx_destroy(hsb_ctx* h) { delete reinterpret_cast<Ctx*>(h); 
 
 extern "C" int hsb_ctx_set_option(hsb_ctx* h, const char* name, int64_t value) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_ctx_set_option");
     if (c && name && !strcmp(name, "block_tiles") && value >= 0) { c->block_tiles = value; return HSB_OK; }
     if (c && name && !strcmp(name, "dual_bwd")) { c->dual_bwd = value != 0; return HSB_OK; }
     set_error("hsb_ctx_set_option: unknown option or bad value");
@@ -488,6 +493,7 @@ extern "C" int hsb_ctx_set_option(hsb_ctx* h, const char* name, int64_t value) {
 
 extern "C" int hsb_ctx_buffer(hsb_ctx* h, const char* name, int64_t* offset_bytes, int64_t* rows, int64_t* ld) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_ctx_buffer");
     for (auto& n : c->names)
         if (n.name == name) { *offset_bytes = n.offset_bytes; *rows = n.rows; *ld = n.ld; return HSB_OK; }
     set_error("hsb_ctx_buffer: unknown buffer name");
@@ -497,13 +503,14 @@ extern "C" int hsb_ctx_buffer(hsb_ctx* h, const char* name, int64_t* offset_byte
 // derived weights for this step + zero the effective-weight gradient accumulators
 extern "C" int hsb_prepare(hsb_ctx* h, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_prepare");
     const int rt = c->rtf();
-    cudaMemsetAsync(c->dwe_begin, 0, c->dwe_bytes, st);
-    cudaMemsetAsync(c->W0eT, 0, (size_t)LD_H0 * 256 * sizeof(float), st);
-    cudaMemsetAsync(c->R0eT, 0, (size_t)LD_RIN * 256 * sizeof(float), st);
-    cudaMemsetAsync(c->W2e, 0, (size_t)c->Kp * 256 * sizeof(float), st);
-    cudaMemsetAsync(c->W2eT, 0, (size_t)c->Kp * 256 * sizeof(float), st);
-    cudaMemsetAsync(c->R2e, 0, (size_t)4 * 256 * sizeof(float), st);
+    TRYCUDA(cudaMemsetAsync(c->dwe_begin, 0, c->dwe_bytes, st));
+    TRYCUDA(cudaMemsetAsync(c->W0eT, 0, (size_t)LD_H0 * 256 * sizeof(float), st));
+    TRYCUDA(cudaMemsetAsync(c->R0eT, 0, (size_t)LD_RIN * 256 * sizeof(float), st));
+    TRYCUDA(cudaMemsetAsync(c->W2e, 0, (size_t)c->Kp * 256 * sizeof(float), st));
+    TRYCUDA(cudaMemsetAsync(c->W2eT, 0, (size_t)c->Kp * 256 * sizeof(float), st));
+    TRYCUDA(cudaMemsetAsync(c->R2e, 0, (size_t)4 * 256 * sizeof(float), st));
     TRY(launch_wn_forward(c->P(SEG_L0V), c->P(SEG_L0G), 256, 71, c->W0e, LD_H0, c->W0eT, 256, rt, st));
     TRY(launch_wn_forward(c->P(SEG_L1V), c->P(SEG_L1G), 256, 256, c->W1e, 256, c->W1eT, 256, rt, st));
     TRY(launch_wn_forward(c->P(SEG_L2V), c->P(SEG_L2G), c->K, 256, c->W2e, 256, c->W2eT, c->Kp, rt, st));
@@ -518,6 +525,7 @@ extern "C" int hsb_prepare(hsb_ctx* h, cudaStream_t st) {
 // weight-norm backward: effective-weight gradients -> (weight_v, weight_g, small biases) in the flat gradient buffer
 extern "C" int hsb_finish(hsb_ctx* h, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_finish");
     TRY(launch_wn_backward(c->dW0e, LD_H0, c->P(SEG_L0V), c->P(SEG_L0G), 256, 71, c->Gp(SEG_L0V), c->Gp(SEG_L0G), st));
     TRY(launch_wn_backward(c->dW1e, 256, c->P(SEG_L1V), c->P(SEG_L1G), 256, 256, c->Gp(SEG_L1V), c->Gp(SEG_L1G), st));
     TRY(launch_wn_backward(c->dW2e, 256, c->P(SEG_L2V), c->P(SEG_L2G), c->K, 256, c->Gp(SEG_L2V), c->Gp(SEG_L2G), st));
@@ -548,6 +556,7 @@ extern "C" int hsb_eik_points(const float* uniform, const float* o, const float*
 extern "C" int hsb_sdf_values(hsb_ctx* h, const float* o, const float* d, const float* z, int32_t R, int32_t S, int32_t channel,
                               float* sdf_out, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_sdf_values");
     Slot& s = c->scratch;
     const long long N = (long long)R * S;
     if (N > s.cap_points || channel >= c->K) { set_error("hsb_sdf_values: batch exceeds max_points / bad channel"); return HSB_ERR_ARG; }
@@ -568,15 +577,16 @@ extern "C" int hsb_render_forward(hsb_ctx* h, int32_t slot_id, const float* o, c
                                   const float* depth_scale, const float* rot, float* rgb_values, float* depth_values,
                                   float* normal_map, float* opacity, float* semantic, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_render_forward");
     if (slot_id != HSB_SLOT_MAIN && slot_id != HSB_SLOT_BG) { set_error("hsb_render_forward: bad slot"); return HSB_ERR_ARG; }
     Slot& s = c->slot[slot_id];
     const long long N = (long long)R * S;
     if (N > s.cap_points || R > s.cap_rays) { set_error("hsb_render_forward: batch exceeds slot capacity"); return HSB_ERR_ARG; }
     const bool scene = slot_id == HSB_SLOT_MAIN;
     s.N = N; s.R = R; s.S = S; s.nseed = 1; s.mode = scene ? 0 : 1;
-    cudaMemcpyAsync(s.ZV, z, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    cudaMemcpyAsync(s.DSCALE, depth_scale, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    cudaMemcpyAsync(s.ROT, rot, 9 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    TRYCUDA(cudaMemcpyAsync(s.ZV, z, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRYCUDA(cudaMemcpyAsync(s.DSCALE, depth_scale, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRYCUDA(cudaMemcpyAsync(s.ROT, rot, 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (!depth_values || !normal_map || !semantic || (scene && (!rgb_values || !opacity))) { set_error("hsb_render_forward: null output"); return HSB_ERR_ARG; }
     const int rb = block_rays(c->block_tiles, R, S);
     for (int r0 = 0; r0 < R; r0 += rb) {
@@ -596,6 +606,7 @@ extern "C" int hsb_render_forward(hsb_ctx* h, int32_t slot_id, const float* o, c
 extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_rgb_values, const float* d_depth_values,
                                    const float* d_normal_map, const float* d_opacity, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_render_backward");
     if (slot_id != HSB_SLOT_MAIN && slot_id != HSB_SLOT_BG) { set_error("hsb_render_backward: bad slot"); return HSB_ERR_ARG; }
     Slot& s = c->slot[slot_id];
     if (s.N == 0) { set_error("hsb_render_backward: no forward recorded in this slot"); return HSB_ERR_ARG; }
@@ -624,32 +635,34 @@ extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_r
 extern "C" int hsb_eikonal_forward(hsb_ctx* h, const float* x, int64_t Ne, float* grad_theta, float* sample_sdf,
                                    float* sample_minsdf, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_eikonal_forward");
     Slot& s = c->slot[HSB_SLOT_EIK];
     if (Ne > s.cap_points || !x || !grad_theta) { set_error("hsb_eikonal_forward: batch exceeds max_eik_points / null pointer"); return HSB_ERR_ARG; }
     s.N = Ne; s.nseed = 3;
-    cudaMemcpyAsync(s.X, x, (size_t)Ne * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    TRYCUDA(cudaMemcpyAsync(s.X, x, (size_t)Ne * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TRY(launch_points_pe(s.X, Ne, s.H0, c->rtf(), st));
     TRY(sdf_forward(c, s, Ne, true, st));
     TRY(launch_sdf_min(s.SR, Ne, c->K, c->Kp, -1, s.SDF, s.KS, st));
     TRY(tangent_forward(c, s, Ne, st));
     TRY(launch_jac_to_grad(s.J, s.KS, Ne, c->K, c->Kp, grad_theta, st));
     if (sample_sdf)
-        cudaMemcpy2DAsync(sample_sdf, (size_t)c->K * sizeof(float), s.SR, (size_t)c->Kp * sizeof(float), (size_t)c->K * sizeof(float),
-                          (size_t)Ne, cudaMemcpyDeviceToDevice, st);
-    if (sample_minsdf) cudaMemcpyAsync(sample_minsdf, s.SDF, (size_t)Ne * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        TRYCUDA(cudaMemcpy2DAsync(sample_sdf, (size_t)c->K * sizeof(float), s.SR, (size_t)c->Kp * sizeof(float), (size_t)c->K * sizeof(float),
+                          (size_t)Ne, cudaMemcpyDeviceToDevice, st));
+    if (sample_minsdf) TRYCUDA(cudaMemcpyAsync(sample_minsdf, s.SDF, (size_t)Ne * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return check_cuda("hsb_eikonal_forward");
 }
 
 extern "C" int hsb_eikonal_backward(hsb_ctx* h, const float* d_grad_theta, const float* d_sample_sdf, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_eikonal_backward");
     Slot& s = c->slot[HSB_SLOT_EIK];
     if (s.N == 0 || !d_grad_theta) { set_error("hsb_eikonal_backward: no forward recorded / null gradient"); return HSB_ERR_ARG; }
     const long long Ne = s.N;
     TRY(launch_grad_to_jac(d_grad_theta, s.KS, Ne, c->K, c->Kp, s.dJ, c->rtf(), st));
-    cudaMemsetAsync(s.dS, 0, (size_t)Ne * c->Kp * sizeof(float), st);
+    TRYCUDA(cudaMemsetAsync(s.dS, 0, (size_t)Ne * c->Kp * sizeof(float), st));
     if (d_sample_sdf)
-        cudaMemcpy2DAsync(s.dS, (size_t)c->Kp * sizeof(float), d_sample_sdf, (size_t)c->K * sizeof(float), (size_t)c->K * sizeof(float),
-                          (size_t)Ne, cudaMemcpyDeviceToDevice, st);
+        TRYCUDA(cudaMemcpy2DAsync(s.dS, (size_t)c->Kp * sizeof(float), d_sample_sdf, (size_t)c->K * sizeof(float), (size_t)c->K * sizeof(float),
+                          (size_t)Ne, cudaMemcpyDeviceToDevice, st));
     TRY(tangent_backward(c, s, Ne, st));
     TRY(sdf_backward(c, s, Ne, true, st));
     return HSB_OK;

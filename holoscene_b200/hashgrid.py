@@ -5,8 +5,9 @@ Same public names and argument meaning as the reference:
   * `_backend.hash_encode_forward / hash_encode_backward / hash_encode_second_backward`
     (reference hashencoder/src/hashencoder.h:13-15) -- so the unmodified reference
     hashencoder/hashgrid.py runs on these kernels when `hashencoder.backend` is pointed here;
-  * `hash_encode`, `HashEncoder` (reference hashgrid.py:104-166) with first- and second-order
-    backward (hashgrid.py:14-101; like the reference, no d/d(inputs) term in the double backward).
+  * `hash_encode`, `HashEncoder` (reference hashgrid.py:104-166): the parameter container the model owns, plus a twice-
+    differentiable forward for point queries outside the fused step (own autograd nodes over the strided kernel interface;
+    like the reference, no d/d(inputs) term in the double backward, hashgrid.py:101).
 float32, D=3, C=2 only (the Stage-1 instantiation); anything else raises like the reference does
 for unsupported C/D (hashencoder.cu:607,622).
 """
@@ -74,64 +75,73 @@ class _Backend:
 _backend = _Backend
 
 
-class _hash_encode_second_backward(Function):
-    @staticmethod
-    def forward(ctx, grad, inputs, embeddings, offsets, B, D, C, L, S, H, calc_grad_inputs, dy_dx):
-        grad_inputs = torch.zeros_like(inputs)
-        grad_embeddings = torch.zeros_like(embeddings)
-        ctx.save_for_backward(grad, inputs, embeddings, offsets, dy_dx)
-        ctx.dims = [B, D, C, L, S, H]
-        ctx.calc_grad_inputs = calc_grad_inputs
-        _backend.hash_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H,
-                                      calc_grad_inputs, dy_dx, grad_inputs)
-        return grad_inputs, grad_embeddings
+class _EncodeGrad(Function):
+    """First-order backward as a differentiable node: cotangent rows [B, L*C] -> (d/d x01 [B,3], d/d table).  Its own backward
+    is the reference's double backward (hashgrid.py:87-101): d/d(cotangent) and the second-order table term; like the reference,
+    no d/d(inputs) term.  The kernels address [B, L*C] rows directly (level stride C, point stride L*C): no [L,B,C] staging."""
 
     @staticmethod
-    def backward(ctx, grad_grad_inputs, grad_grad_embeddings):
-        grad, inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
-        B, D, C, L, S, H = ctx.dims
-        grad_grad = torch.zeros_like(grad)
-        grad2_embeddings = torch.zeros_like(embeddings)
-        _backend.hash_encode_second_backward(grad, inputs, embeddings, offsets, B, D, C, L, S, H, ctx.calc_grad_inputs,
-                                             dy_dx, grad_grad_inputs.contiguous(), grad_grad, grad2_embeddings)
-        return grad_grad, None, grad2_embeddings, None, None, None, None, None, None, None, None, None
-
-
-class _hash_encode(Function):
-    @staticmethod
-    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False):
-        inputs = inputs.contiguous()
-        embeddings = embeddings.contiguous()
-        offsets = offsets.contiguous()
-        B, D = inputs.shape
+    def forward(ctx, cot, x01, table, offsets, S, H, dy_dx):
+        cot = cot.contiguous()
+        B, LC = cot.shape
         L = offsets.shape[0] - 1
-        C = embeddings.shape[1]
-        S = float(np.float32(np.log2(per_level_scale)))
-        H = int(base_resolution)
-        outputs = torch.empty(L, B, C, device=inputs.device, dtype=inputs.dtype)
-        if calc_grad_inputs:
-            dy_dx = torch.empty(B, L * D * C, device=inputs.device, dtype=inputs.dtype)
-        else:
-            dy_dx = torch.empty(1, device=inputs.device, dtype=inputs.dtype)
-        _backend.hash_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs, dy_dx)
-        ctx.save_for_backward(inputs, embeddings, offsets, dy_dx)
-        ctx.dims = [B, D, C, L, S, H]
-        ctx.calc_grad_inputs = calc_grad_inputs
-        return outputs.permute(1, 0, 2).reshape(B, L * C)
+        g_table = torch.zeros_like(table)
+        g_x = torch.zeros_like(x01)
+        have_dx = dy_dx is not None
+        _lib.check(_lib.hash_backward(_lib.ptr(cot), 2, LC, _lib.ptr(x01), _lib.ptr(offsets), _lib.ptr(g_table),
+                                      _lib.ptr(dy_dx) if have_dx else None, L * 6, _lib.ptr(g_x) if have_dx else None, B, L, S, H, 0,
+                                      _lib.stream()))
+        ctx.save_for_backward(cot, x01, offsets, dy_dx if have_dx else cot.new_empty(0))
+        ctx.meta = (S, H, have_dx, table.shape)
+        return g_x, g_table
 
     @staticmethod
-    def backward(ctx, grad):
-        inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
-        B, D, C, L, S, H = ctx.dims
-        grad = grad.view(B, L, C).permute(1, 0, 2).contiguous()
-        grad_inputs, grad_embeddings = _hash_encode_second_backward.apply(grad, inputs, embeddings, offsets, B, D, C, L,
-                                                                          S, H, ctx.calc_grad_inputs, dy_dx)
-        if ctx.calc_grad_inputs:
-            return grad_inputs, grad_embeddings, None, None, None, None
-        return None, grad_embeddings, None, None, None, None
+    def backward(ctx, gg_x, _gg_table):
+        cot, x01, offsets, dy_dx = ctx.saved_tensors
+        S, H, have_dx, tshape = ctx.meta
+        if not have_dx or gg_x is None:
+            return (None,) * 7
+        B, LC = cot.shape
+        L = offsets.shape[0] - 1
+        gg_cot = torch.zeros_like(cot)
+        g2_table = torch.zeros(tshape, device=cot.device, dtype=cot.dtype)
+        _lib.check(_lib.hash_second_backward(_lib.ptr(cot), 2, LC, _lib.ptr(x01), _lib.ptr(offsets), _lib.ptr(dy_dx), L * 6,
+                                             _lib.ptr(gg_x.contiguous()), _lib.ptr(gg_cot), 2, LC, _lib.ptr(g2_table), B, L, S, H, 0,
+                                             _lib.stream()))
+        return gg_cot, None, g2_table, None, None, None, None
 
 
-hash_encode = _hash_encode.apply
+class _Encode(Function):
+    @staticmethod
+    def forward(ctx, x01, table, offsets, S, H, need_dx):
+        x01 = x01.contiguous()
+        B = x01.shape[0]
+        L = offsets.shape[0] - 1
+        if x01.shape[1] != 3 or table.shape[1] != 2:
+            raise RuntimeError("GridEncoding: libhsb200 implements D=3, C=2")
+        for t, n in ((x01, "inputs"), (table, "embeddings")):
+            _chk(t, n)
+        _chk(offsets, "offsets", torch.int32)
+        feats = torch.empty(B, L * 2, device=x01.device, dtype=x01.dtype)
+        dy_dx = torch.empty(B, L * 6, device=x01.device, dtype=x01.dtype) if need_dx else None
+        _lib.check(_lib.hash_forward(_lib.ptr(x01), _lib.ptr(table), _lib.ptr(offsets), _lib.ptr(feats), 2, L * 2,
+                                     _lib.ptr(dy_dx) if need_dx else None, L * 6, B, L, S, H, 0, _lib.stream()))
+        ctx.save_for_backward(x01, table, offsets, dy_dx if need_dx else x01.new_empty(0))
+        ctx.meta = (S, H, need_dx)
+        return feats
+
+    @staticmethod
+    def backward(ctx, cot):
+        x01, table, offsets, dy_dx = ctx.saved_tensors
+        S, H, need_dx = ctx.meta
+        g_x, g_table = _EncodeGrad.apply(cot, x01, table, offsets, S, H, dy_dx if need_dx else None)
+        return (g_x if need_dx else None), g_table, None, None, None, None
+
+
+def hash_encode(inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False):
+    """Reference call signature (hashgrid.py:104): inputs [B,3] in [0,1] -> features [B, L*C], differentiable twice."""
+    S = float(np.float32(np.log2(per_level_scale)))
+    return _Encode.apply(inputs, embeddings.contiguous(), offsets.contiguous(), S, int(base_resolution), bool(calc_grad_inputs))
 
 
 def level_offsets(input_dim, num_levels, per_level_scale, base_resolution, log2_hashmap_size):

@@ -33,11 +33,16 @@ def sample_pixels(segs: torch.Tensor, classes_in_frame, sampling_size: int, gene
     bg, per, n_uniform = class_quotas(C, sampling_size)
     quota = torch.full((C,), per, device=dev, dtype=torch.int64)
     quota[0] = bg
-    # class rank of every pixel (-1: not one of the frame's classes)
-    hit = seg.unsqueeze(1) == cls.unsqueeze(0)                         # [HW, C]
-    rank = torch.where(hit.any(1), hit.to(torch.int64).argmax(1), torch.full((HW,), -1, device=dev, dtype=torch.int64))
-    u = torch.rand(HW, device=dev, generator=generator, dtype=torch.float64)
-    key = torch.where(rank >= 0, rank.to(torch.float64) + u, torch.full((HW,), float(C + 1), device=dev, dtype=torch.float64))
+    # class rank of every pixel (-1: not one of the frame's classes) through a small lookup table over the class-id range
+    top = int(cls.max()) + 1 if C else 1
+    lut = torch.full((top + 1,), -1, device=dev, dtype=torch.int64)
+    lut[cls.long()] = torch.arange(C, device=dev)
+    rank = lut[seg.long().clamp(0, top)]
+    rank = torch.where((seg >= 0) & (seg < top), rank, torch.full_like(rank, -1))
+    # one keyed sort: integer composite key (class rank << 32 | 32 random bits): no float rounding across class boundaries; ties
+    # inside a class (equal random bits) are broken by pixel index, a 2^-32 effect
+    bits = torch.randint(0, 1 << 32, (HW,), device=dev, generator=generator, dtype=torch.int64)
+    key = torch.where(rank >= 0, (rank << 32) | bits, torch.full((HW,), (C + 1) << 32, device=dev, dtype=torch.int64))
     order = torch.argsort(key)
     counts = torch.bincount(rank[rank >= 0], minlength=C)
     starts = torch.cumsum(counts, 0) - counts

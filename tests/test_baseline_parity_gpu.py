@@ -1,0 +1,183 @@
+"""Oracle-vs-CUDA parity AT BASELINE.json's configurations (round-1 verdict item 1): the CPU oracle is run on the spot.
+
+  * C1 (512 rays x 64 samples, K = 2, full 2^19 tables) END TO END: sampler + scene pass + eikonal pass + loss + backward, same
+    weights / rays / random draws on both sides, in the fp32-grade mode (3xTF32) and in the fast mode the benchmark runs.
+  * the K-dependent kernels (Kp padding, >1 32-column chunk of SR, scatter_rows, jac_to_grad, per-object opacity with lane =
+    channel, the K = 21 -> Kp = 24 / n_mma = 32 tail) at K = 32 / 21 / 64 with the full 2^19 tables, on IDENTICAL sample
+    positions (the pattern of test_main_pass_backward_matches_oracle_on_identical_samples): per-ray outputs and every parameter
+    gradient of the fused backward against autograd on the oracle, both modes; same for the eikonal pass.
+  * get_shift_sdf_raw against the reference rule (model/network.py:460-479).
+
+Tolerances.  precise (3xTF32): outputs 5e-4, gradients common.grad_tol(2e-3).  fast (single-pass TF32 on tcgen05): the measured
+errors are printed by every test ([...] tables, -s); the asserts are ~2x the measured values recorded in DESIGN.md section 2.
+"""
+import pytest
+import torch
+
+from tests import common
+from tests.test_step_gpu import _oracle_main_pass, build_model, make_loss, report
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(K, S, logmap=19, n_eval=128):
+    from oracle import model as om
+    return om.StepConfig(d_out=K, logmap=logmap, N_samples=S - 34, N_samples_eval=n_eval, N_samples_extra=32)
+
+
+def _rays(R, S, seed):
+    """Rays from inside the unit cube with sampler-like depths: sorted, first = near = 0, last = far = 3.5 (outside the hash grid:
+    the out-of-range rule is exercised on every ray, as in the reference: ray_sampler.py:263-272)."""
+    gen = torch.Generator().manual_seed(seed)
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=gen), dim=1)
+    o = torch.tensor([[0.1, 0.0, -0.2]]).repeat(R, 1)
+    z = (torch.rand(R, S, generator=gen) * 2.2).sort(dim=1)[0]
+    z[:, 0] = 0.0
+    z[:, -1] = 3.5
+    ds = torch.rand(R, 1, generator=gen) + 0.5
+    rot = torch.linalg.qr(torch.randn(3, 3, generator=gen))[0].contiguous()
+    return gen, o, d, z.contiguous(), ds, rot
+
+
+# (K, R, S): BASELINE configs[1] (K = 32), [2] (K = 21), [4] (K = 64, 192 samples), [0] (K = 2, 64 samples)
+BASE_CASES = [(32, 256, 128), (21, 256, 128), (64, 128, 192), (2, 512, 64)]
+# fast mode: relative-L2 bound per output / gradient family = ~2x the errors measured on a B200
+FAST_OUT_TOL = 1e-2
+FAST_GRAD_TOL = 6e-2
+
+
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("K,R,S", BASE_CASES)
+def test_main_pass_backward_matches_oracle_at_baseline_K(K, R, S, precise):
+    from holoscene_b200 import engine as E
+    from oracle import model as om
+    cfg = _cfg(K, S)
+    sd = common.seeded_state_dict(cfg)
+    m = build_model(cfg, sd, precise, max_rays=R)
+    m.train()
+    eng = m.engine()
+    m._attach_grads()
+    eng.prepare()
+    gen, o, d, z, ds, rot = _rays(R, S, 3 + K)
+    cot = [torch.randn(R, 3, generator=gen), torch.randn(R, 1, generator=gen), torch.randn(R, 3, generator=gen),
+           torch.randn(R, K, generator=gen)]
+    p = om.trainable(sd)
+    outs = _oracle_main_pass(p, cfg, o, d, z, rot, ds)
+    sum((a * b).sum() for a, b in zip(outs, cot)).backward()
+    got = eng.render_forward(E.SLOT_MAIN, o.cuda(), d.cuda(), z.cuda(), ds.cuda(), rot.cuda())
+    eng.render_backward(E.SLOT_MAIN, *[c.cuda() for c in cot])
+    eng.finish()
+    torch.cuda.synchronize()
+    names = ("rgb_values", "depth_values", "normal_map", "object_opacity")
+    rows = [(names[i], common.rel_err(got[i].cpu(), outs[i].detach()), 5e-4 if precise else FAST_OUT_TOL) for i in range(4)]
+    for n, prm in m.named_parameters():
+        ref = p[n].grad if p[n].grad is not None else torch.zeros_like(p[n])
+        tol = common.grad_tol(n, 2e-3) if precise else max(FAST_GRAD_TOL, 3 * common.grad_tol(n, 2e-3))
+        rows.append(("grad_" + n, common.rel_err(prm.grad.cpu(), ref), tol))
+    report(f"main pass K={K} R={R} S={S} logmap 19 precise={precise}", rows)
+    bad = [r for r in rows if not (r[1] <= r[2])]
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("K", [32, 21, 64])
+def test_eikonal_pass_backward_matches_oracle_at_baseline_K(K, precise):
+    from oracle import model as om
+    cfg = _cfg(K, 128)
+    sd = common.seeded_state_dict(cfg)
+    n = 512
+    m = build_model(cfg, sd, precise, max_rays=n // 4)
+    m.train()
+    eng = m.engine()
+    m._attach_grads()
+    eng.prepare()
+    gen = torch.Generator().manual_seed(11 + K)
+    x = torch.rand(n, 3, generator=gen) * 2.1 - 1.05          # a few points outside the hash grid's range
+    cot_g = torch.randn((K + 1) * n, 3, generator=gen)
+    cot_s = torch.randn(n, K, generator=gen)
+    p = om.trainable(sd)
+    gt = om.all_gradients(p, cfg, x)
+    raw, _ = om.implicit_forward(p, cfg, x)
+    ((gt * cot_g).sum() + (raw * cot_s).sum()).backward()
+    ggt, ssdf, smin = eng.eikonal_forward(x.cuda())
+    eng.eikonal_backward(cot_g.cuda(), cot_s.cuda())
+    eng.finish()
+    torch.cuda.synchronize()
+    ot = 1e-3 if precise else FAST_OUT_TOL
+    rows = [("grad_theta", common.rel_err(ggt.cpu(), gt.detach()), ot), ("sample_sdf", common.rel_err(ssdf.cpu(), raw.detach()), ot / 2),
+            ("sample_minsdf", common.rel_err(smin.cpu()[:, 0], raw.detach().min(1)[0]), ot / 2)]
+    for nm, prm in m.named_parameters():
+        if p[nm].grad is None:
+            continue
+        rows.append(("grad_" + nm, common.rel_err(prm.grad.cpu(), p[nm].grad), 2e-3 if precise else FAST_GRAD_TOL))
+    report(f"eikonal pass K={K} logmap 19 precise={precise}", rows)
+    bad = [r for r in rows if not (r[1] <= r[2])]
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("precise", [True, False])
+def test_c1_step_end_to_end_matches_oracle(precise):
+    """BASELINE configs[0]: 'Replica room_0 Stage-1, 1 object + background, 512 rays x 64 samples' -- the whole train step
+    (error-bound sampler, scene pass, eikonal pass, loss, backward) against the CPU oracle on identical weights / rays / draws."""
+    from holoscene_b200 import synthetic
+    from holoscene_b200.rng import ReplayDraws
+    from oracle import model as om
+    K, R = 2, 512
+    cfg = _cfg(K, 64)
+    sd = common.seeded_state_dict(cfg)
+    Kmat, pose = synthetic.camera()
+    uv, gt = synthetic.rays_and_gt(R, K)
+    torch.manual_seed(7)
+    draws = om.Draws()
+    p = om.trainable(sd)
+    ref = om.model_forward(p, cfg, uv.clone(), pose, Kmat, True, 1, draws)
+    ref_loss = om.loss_forward(cfg, ref, gt)
+    ref_loss["loss"].backward()
+    m = build_model(cfg, sd, precise, max_rays=R).train()
+    m.draws = ReplayDraws(draws.log, "cuda")
+    out = m({"uv": uv.clone().cuda(), "intrinsics": Kmat.cuda(), "pose": pose.cuda()}, None, iter_step=1)
+    out["iter_step"] = 1
+    losses = make_loss()(out, gt)
+    losses["loss"].backward()
+    torch.cuda.synchronize()
+    rows = []
+    ot = 5e-3 if precise else 2e-2
+    for k in ("z_vals", "rgb_values", "depth_values", "normal_map", "object_opacity", "grad_theta", "sample_sdf"):
+        rows.append((k, common.rel_err(out[k].detach().cpu(), ref[k].detach()), 3e-4 if k == "z_vals" else ot))
+    for k in ("loss", "rgb_loss", "eikonal_loss", "depth_loss", "normal_l1", "normal_cos", "semantic_loss"):
+        a, b = float(losses[k]), float(ref_loss[k])
+        rows.append(("loss:" + k, abs(a - b) / max(abs(b), 1e-3), 2e-3 if precise else 2e-2))
+    for n, prm in m.named_parameters():
+        ref_g = p[n].grad if p[n].grad is not None else torch.zeros_like(p[n])
+        if precise:
+            tol = 0.2 if n == "density.beta" else common.grad_tol(n, 1e-2, e2e=True)   # beta: one scalar, cancelling per-ray terms
+            rows.append(("grad_" + n, common.rel_err(prm.grad.cpu(), ref_g), tol))
+        else:
+            a, b = prm.grad.cpu().double().flatten(), ref_g.double().flatten()
+            rows.append(("grad_" + n + " (1 - cosine)", 1.0 - float((a @ b) / (a.norm() * b.norm() + 1e-300)), 5e-2))
+    report(f"C1 512x64 K=2 end to end precise={precise} (sampler rounds {m.ray_sampler.last_rounds})", rows)
+    bad = [r for r in rows if not (r[1] <= r[2])]
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("K", [3, 32])
+def test_shift_sdf_raw_matches_reference_rule(K):
+    """get_shift_sdf_raw (reference model/network.py:460-479): where the scene SDF is negative every other object's value is
+    raised to at least -sdf, and the arg-min channel keeps the min.  Point queries run on the fused SDF trunk."""
+    from oracle import model as om
+    cfg = _cfg(K, 128, logmap=15)
+    sd = common.seeded_state_dict(cfg)
+    m = build_model(cfg, sd, True, max_rays=64).eval()
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(3000, 3, generator=gen) * 1.9 - 0.95
+    raw, _ = om.implicit_forward(sd, cfg, x, with_color=False)
+    raw = raw.detach()
+    sdf, idx = raw.min(dim=1, keepdim=True)
+    want = torch.where((sdf < 0).expand_as(raw), torch.max(raw, (-sdf).expand_as(raw)), raw)
+    want[torch.arange(x.shape[0]), idx.squeeze(1)] = sdf.squeeze(1)
+    assert int((sdf < 0).sum()) > 100 and int((sdf > 0).sum()) > 100          # both branches of the rule are exercised
+    got = m.implicit_network.get_shift_sdf_raw(x.cuda()).cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < 2e-4, float((got - want).abs().max())
+    assert float((m.implicit_network.get_sdf_raw(x.cuda()).cpu() - raw).abs().max()) < 2e-4
+    assert float((m.implicit_network.get_sdf_vals(x.cuda()).cpu() - sdf).abs().max()) < 2e-4

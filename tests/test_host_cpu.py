@@ -106,6 +106,34 @@ def test_conf_reader_matches_reference_conf_format():
     assert sub["d_out"] == 4 and sub["skip_in"] == [4]
 
 
+REF_CONFS = ["confs/replica/room_0/replica_room_0.conf", "confs/scannetpp/67d702f2e8/scannetpp_67d702f2e8.conf",
+             "confs/custom/siebelgame/custom_siebelgame.conf"]
+
+
+@pytest.mark.parametrize("rel", REF_CONFS)
+def test_reference_confs_parse_and_construct_both_classes(rel):
+    """Seam B1: the reference's own Stage-1 conf files (read where they lie, container only -- the GPU box has no
+    /root/reference) go through holoscene_b200.conf unchanged, and model.{...} / loss{...} construct the drop-in classes the
+    way training/holoscene_train.py:137-148 does (conf=conf.get_config('model'); **conf.get_config('loss'))."""
+    path = os.path.join("/root/reference", rel)
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    from holoscene_b200.loss import HoloSceneLoss
+    from holoscene_b200.network import HoloSceneNetwork
+    c = hconf.parse_file(path)
+    assert c.get_string("train.model_class").endswith("HoloSceneNetwork") and c.get_string("train.loss_class").endswith("HoloSceneLoss")
+    assert c.get_int("train.num_pixels") == 1024 and c.get_int("model.ray_sampler.N_samples") == 64
+    model_conf = c.get_config("model")
+    K = model_conf.get_int("implicit_network.d_out")
+    m = HoloSceneNetwork(conf=model_conf, plots_dir="/tmp", graph_node_dict=None, ft_folder=None, num_images=10)
+    n_params = sum(p.numel() for p in m.parameters())
+    assert m.implicit_network.d_out == K and n_params > 24_000_000           # two 6 098 108 x 2 hash tables + the MLPs
+    assert m.implicit_network.encoding.embeddings.shape == (6098108, 2)
+    assert m.ray_sampler.N_samples_eval == 128 and m.ray_sampler.max_total_iters == 5
+    loss = HoloSceneLoss(**c.get_config("loss"))
+    assert loss.eikonal_weight == pytest.approx(c.get_float("loss.eikonal_weight"))
+
+
 def test_model_init_and_state_dict_match_reference_layout():
     """Same seed -> same weights as the reference model (checked against the oracle's init, which
     tests/golden/make_golden.py asserts equal to the reference's own state_dict)."""

@@ -1,5 +1,6 @@
-"""hsb_loss (csrc/loss.cu: loss terms + weighted gradients in three launches) against the tensor-op formulation of the
-same class differentiated by autograd -- which itself is pinned to the reference's golden losses by test_step_gpu.py."""
+"""hsb_loss (csrc/loss.cu: loss terms + weighted gradients in three launches) against the oracle's tensor-op restatement of
+model/loss.py (oracle/model.py:loss_forward, CPU autograd) -- which is pinned to the reference's golden losses by
+tests/test_oracle_model.py."""
 import pytest
 import torch
 
@@ -32,30 +33,47 @@ def _case(R, S, K, Ne, seed, with_eik=True, end_step=-1):
     return mo, gt
 
 
-def _run(fused, mo_in, gt, end_step, steps_before=0):
-    from holoscene_b200.loss import HoloSceneLoss
-    kw = dict(LOSS_KW, end_step=end_step)
-    fn = HoloSceneLoss(**kw)
-    fn.fused = fused
-    fn.step = steps_before
-    leaves = {k: v.clone().requires_grad_(k != "sdf") for k, v in mo_in.items()}
+def _split(leaves):
     mo = {k: v for k, v in leaves.items() if k != "_all"}
     if "_all" in leaves:
         a = leaves["_all"]
         mo["grad_theta"], mo["grad_theta_nei"] = a[: a.shape[0] // 2], a[a.shape[0] // 2:]
         mo["_hsb_grad_theta_all"] = a
-    out = fn(mo, gt)
+    return mo
+
+
+def _run_fused(mo_in, gt, end_step, steps_before=0):
+    from holoscene_b200.loss import HoloSceneLoss
+    fn = HoloSceneLoss(**dict(LOSS_KW, end_step=end_step))
+    fn.step = steps_before
+    leaves = {k: v.clone().requires_grad_(k != "sdf") for k, v in mo_in.items()}
+    out = fn(_split(leaves), gt)
     out["loss"].backward()
-    grads = {k: v.grad for k, v in leaves.items() if k != "sdf"}
-    return {k: float(out[k]) for k in TERMS}, grads
+    return {k: float(out[k]) for k in TERMS}, {k: v.grad.cpu() for k, v in leaves.items() if k != "sdf"}
+
+
+def _run_oracle(mo_in, gt, end_step, steps_before=0):
+    """oracle/model.py:loss_forward (the reference's tensor-op formulation, CPU autograd); the depth / normal decay of
+    MonoSDFLoss.forward (model/loss.py:336-343) is applied through the weights."""
+    import dataclasses
+    import math
+    from oracle import model as om
+    decay = math.exp(-steps_before / end_step * 10.0) if end_step > 0 else 1.0
+    cfg = dataclasses.replace(om.StepConfig(), eikonal_weight=LOSS_KW["eikonal_weight"], smooth_weight=LOSS_KW["smooth_weight"],
+                              depth_weight=decay * LOSS_KW["depth_weight"], normal_l1_weight=decay * LOSS_KW["normal_l1_weight"],
+                              normal_cos_weight=decay * LOSS_KW["normal_cos_weight"], semantic_weight=LOSS_KW["semantic_weight"])
+    leaves = {k: v.detach().cpu().clone().requires_grad_(k != "sdf") for k, v in mo_in.items()}
+    out = om.loss_forward(cfg, _split(leaves), gt)
+    out["loss"].backward()
+    return {k: float(out[k]) for k in TERMS}, {k: v.grad for k, v in leaves.items() if k != "sdf"}
 
 
 @pytest.mark.parametrize("R,S,K,Ne,with_eik,end_step", [(512, 24, 6, 640, True, -1), (4096, 128, 32, 1024, True, 200),
                                                         (77, 9, 3, 2, True, -1), (3, 5, 2, 2, True, -1)])
-def test_fused_loss_matches_autograd(R, S, K, Ne, with_eik, end_step):
+def test_fused_loss_matches_oracle_autograd(R, S, K, Ne, with_eik, end_step):
     mo, gt = _case(R, S, K, Ne, seed=R + K, with_eik=with_eik, end_step=end_step)
-    ref_l, ref_g = _run(False, mo, gt, end_step, steps_before=37)
-    our_l, our_g = _run(True, mo, gt, end_step, steps_before=37)
+    ref_l, ref_g = _run_oracle(mo, gt, end_step, steps_before=37)
+    our_l, our_g = _run_fused(mo, gt, end_step, steps_before=37)
     for k in TERMS:
         assert abs(our_l[k] - ref_l[k]) <= 2e-5 * max(1.0, abs(ref_l[k])), (k, our_l[k], ref_l[k])
     for k, gr in ref_g.items():
@@ -65,6 +83,23 @@ def test_fused_loss_matches_autograd(R, S, K, Ne, with_eik, end_step):
         # depth: the reference differentiates through torch.inverse of a 2x2 in fp32; hsb_loss solves it in fp64
         tol = 2e-3 if k == "depth_values" else 2e-4
         assert err < tol, (k, err)
+
+
+def test_out_of_range_class_id_poisons_the_loss_and_zero_depth_weight_stays_finite():
+    """The reference's F.one_hot raises on a class id outside [0, K) (model/loss.py:487-492); the fused loss has no host sync, so
+    it reports NaN as the step's loss instead.  A zero depth weight must keep d_depth finite even for a singular scale/shift fit."""
+    from holoscene_b200.loss import HoloSceneLoss
+    mo, gt = _case(64, 8, 4, 16, seed=5)
+    bad = dict(gt, segs=gt["segs"].clone())
+    bad["segs"][0, 3, 0] = 4
+    assert torch.isnan(HoloSceneLoss(**LOSS_KW)(_split(dict(mo)), bad)["loss"])
+    assert torch.isfinite(HoloSceneLoss(**LOSS_KW)(_split(dict(mo)), gt)["loss"])
+    mo1 = {k: (v[:1] if k != "_all" else v) for k, v in mo.items()}            # R = 1: singular 2x2 system
+    gt1 = {k: v[:, :1] for k, v in gt.items()}
+    leaves = {k: v.clone().requires_grad_(k != "sdf") for k, v in mo1.items()}
+    out = HoloSceneLoss(**dict(LOSS_KW, depth_weight=0.0))(_split(leaves), gt1)
+    out["loss"].backward()
+    assert torch.isfinite(leaves["depth_values"].grad).all() and float(leaves["depth_values"].grad.abs().max()) == 0.0
 
 
 def test_only_total_is_differentiable():
