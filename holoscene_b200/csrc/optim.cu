@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 // Adam over one flat segment; optionally accumulates ||g||^2 (the trainer's grad-norm statistic,
 // holoscene_train.py:367-372) in the same pass.
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float b1, float b2, float eps, float step,
-                                         float bc2_sqrt, float& acc) {
+                                         float bc2_sqrt, float& acc, float gscale) {
+    g *= gscale;                               // 1/world of the data-parallel mean, folded in (exactly 1.0f on one GPU)
     m = b1 * m + (1.0f - b1) * g;
     v = b2 * v + (1.0f - b2) * g * g;
     p -= step * m / (sqrtf(v) / bc2_sqrt + eps);
@@ -80,7 +81,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 // 4-byte accesses left the kernel at 4 TB/s.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, long long n4, float lr, float b1, float b2,
-                                                   float eps, float bc1, float bc2_sqrt, float* __restrict__ gnorm2) {
+                                                   float eps, float bc1, float bc2_sqrt, float* __restrict__ gnorm2, float gscale) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float acc = 0.0f;
@@ -92,15 +93,15 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     for (long long i = t0; i < n4; i += stride) {
         const float4 gi = g4[i];
         float4 mi = m4[i], vi = v4[i], pi = p4[i];
-        adam_one(pi.x, gi.x, mi.x, vi.x, b1, b2, eps, step, bc2_sqrt, acc);
-        adam_one(pi.y, gi.y, mi.y, vi.y, b1, b2, eps, step, bc2_sqrt, acc);
-        adam_one(pi.z, gi.z, mi.z, vi.z, b1, b2, eps, step, bc2_sqrt, acc);
-        adam_one(pi.w, gi.w, mi.w, vi.w, b1, b2, eps, step, bc2_sqrt, acc);
+        adam_one(pi.x, gi.x, mi.x, vi.x, b1, b2, eps, step, bc2_sqrt, acc, gscale);
+        adam_one(pi.y, gi.y, mi.y, vi.y, b1, b2, eps, step, bc2_sqrt, acc, gscale);
+        adam_one(pi.z, gi.z, mi.z, vi.z, b1, b2, eps, step, bc2_sqrt, acc, gscale);
+        adam_one(pi.w, gi.w, mi.w, vi.w, b1, b2, eps, step, bc2_sqrt, acc, gscale);
         m4[i] = mi; v4[i] = vi; p4[i] = pi;
     }
     for (long long i = 4 * n4 + t0; i < n; i += stride) {
         float mi = m[i], vi = v[i], pi = p[i];
-        adam_one(pi, g[i], mi, vi, b1, b2, eps, step, bc2_sqrt, acc);
+        adam_one(pi, g[i], mi, vi, b1, b2, eps, step, bc2_sqrt, acc, gscale);
         m[i] = mi; v[i] = vi; p[i] = pi;
     }
     if (gnorm2) {
@@ -135,7 +136,7 @@ int launch_transpose(const float* W, int rows, int cols, float* WT, int ldt, flo
     return check_launch("transpose");
 }
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1,
-                float bc2_sqrt, float* gnorm2, cudaStream_t st) {
+                float bc2_sqrt, float* gnorm2, float gscale, cudaStream_t st) {
     if (n <= 0) return HSB_OK;
     const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
     const long long n4 = aligned ? n / 4 : 0;
@@ -143,16 +144,21 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, float
     long long cap = 148LL * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, n4, lr, b1, b2, eps, bc1, bc2_sqrt, gnorm2);
+    adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, n4, lr, b1, b2, eps, bc1, bc2_sqrt, gnorm2, gscale);
     return check_launch("adam");
 }
 
 }  // namespace hsb
 
-extern "C" int hsb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
-                             float beta1, float beta2, float eps, int step, float* grad_norm_sq, cudaStream_t stream) {
+extern "C" int hsb_adam_step_scaled(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                                    float beta1, float beta2, float eps, int step, float grad_scale, float* grad_norm_sq,
+                                    cudaStream_t stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || step < 1) { hsb::set_error("hsb_adam_step: bad argument"); return HSB_ERR_ARG; }
     const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     return hsb::launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2),
-                            grad_norm_sq, stream);
+                            grad_norm_sq, grad_scale, stream);
+}
+extern "C" int hsb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                             float beta1, float beta2, float eps, int step, float* grad_norm_sq, cudaStream_t stream) {
+    return hsb_adam_step_scaled(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, 1.0f, grad_norm_sq, stream);
 }

@@ -66,6 +66,6 @@ int launch_add_into(const float* src, float* dst, int n, cudaStream_t st);
 int launch_transpose(const float* W, int rows, int cols, float* WT, int ldt, float* Wcopy, int rtf, cudaStream_t st);
 int hash_forward_ex(const float* x, const float* emb, const int32_t* offs, float* out, long long ls, long long ps, float* dy, long long dps,
                     uint32_t B, uint32_t L, float S, uint32_t H, int map01, int rtf, cudaStream_t st);
-int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float* gnorm2, cudaStream_t st);
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float* gnorm2, float gscale, cudaStream_t st);
 
 }  // namespace hsb

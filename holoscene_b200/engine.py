@@ -54,6 +54,7 @@ _render_bwd = declare("hsb_render_backward", [_vp, ctypes.c_int32, _vp, _vp, _vp
 _eik_fwd = declare("hsb_eikonal_forward", [_vp, _vp, ctypes.c_int64, _vp, _vp, _vp, c_stream])
 _eik_bwd = declare("hsb_eikonal_backward", [_vp, _vp, _vp, c_stream])
 _adam = declare("hsb_adam_step", [_vp, _vp, _vp, _vp, c_ll, c_f32, c_f32, c_f32, c_f32, c_int, _vp, c_stream])
+_adam_scaled = declare("hsb_adam_step_scaled", [_vp, _vp, _vp, _vp, c_ll, c_f32, c_f32, c_f32, c_f32, c_int, c_f32, _vp, c_stream])
 i32 = ctypes.c_int32
 sampler_init = declare("hsb_sampler_init", [_vp, _vp, i32, i32, c_f32, c_f32, c_f32, _vp, c_f32, _vp, _vp, c_stream])
 sampler_bound = declare("hsb_sampler_bound", [_vp, _vp, i32, _vp, _vp, i32, _vp, _vp, _vp, _vp, c_f32, c_f32, i32, i32, _vp, c_stream])
@@ -241,9 +242,10 @@ class StepEngine:
         b = None if d_sample_sdf is None else d_sample_sdf.contiguous()
         check(_eik_bwd(self._h, ptr(a), ptr(b), stream()))
 
-    def adam(self, lo, hi, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.99), eps=1e-15, grad_norm_sq=None):
-        """Adam over params[lo:hi] (one learning-rate group is a contiguous range of segments)."""
+    def adam(self, lo, hi, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.99), eps=1e-15, grad_norm_sq=None, grad_scale=1.0):
+        """Adam over params[lo:hi] (one learning-rate group is a contiguous range of segments); gradients are multiplied by
+        grad_scale on the way in (1/world after a SUM all-reduce)."""
         n = hi - lo
         off = lambda t: _vp(t.data_ptr() + 4 * lo)
-        check(_adam(off(self.params), off(self.grads), off(exp_avg), off(exp_avg_sq), n, float(lr), float(betas[0]),
-                    float(betas[1]), float(eps), int(step), ptr(grad_norm_sq), stream()))
+        check(_adam_scaled(off(self.params), off(self.grads), off(exp_avg), off(exp_avg_sq), n, float(lr), float(betas[0]),
+                           float(betas[1]), float(eps), int(step), float(grad_scale), ptr(grad_norm_sq), stream()))

@@ -277,6 +277,10 @@ class HoloSceneNetwork(nn.Module):
         # consumed exactly once) and in training; the first call of a kind always runs in exact mode.
         speculate = self.training and isinstance(draws, LiveDraws) and self.speculative_sampler
         try:
+            if speculate and torch.cuda.is_current_stream_capturing():
+                # being recorded into TrainStep's CUDA graph: the guessed round count is baked in, the flags travel to the host
+                # inside the graph and TrainStep judges them after every replay (ray_sampler.judge)
+                return self._forward(eng, intrinsics, uv, pose, iter_step, draws, dev, "capture")
             if speculate:
                 # a repeat must start over: forward shifts uv in place (reference behaviour) and consumes random numbers
                 uv0 = uv.clone()

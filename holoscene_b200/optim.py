@@ -35,13 +35,13 @@ class StageOneAdam:
         self.model._attach_grads()
 
     @torch.no_grad()
-    def step(self):
+    def step(self, grad_scale=1.0):
         eng = self.model.engine()
         self.step_count += 1
         self.grad_norm_sq.zero_()
         for g in self.groups:
             eng.adam(g["lo"], g["hi"], self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count, self.betas, self.eps,
-                     self.grad_norm_sq)
+                     self.grad_norm_sq, grad_scale)
 
     def scheduler_step(self):
         for g in self.groups:

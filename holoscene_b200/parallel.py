@@ -35,6 +35,14 @@ def allreduce_mean_(flat_grads: torch.Tensor, world: int) -> torch.Tensor:
     return flat_grads
 
 
+def allreduce_sum_(flat_grads: torch.Tensor, world: int) -> torch.Tensor:
+    """In-place SUM over ranks of the flat gradient buffer; the 1/world of the mean is applied by the fused Adam
+    (hsb_adam_step_scaled), which saves a pass over the buffer."""
+    if world > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+    return flat_grads
+
+
 def assert_replicas_in_sync(flat_params: torch.Tensor, world: int, atol: float = 0.0) -> None:
     """Debug check: replicas apply identical updates, so their parameters must stay bit-identical."""
     if world <= 1:

@@ -34,6 +34,7 @@ class ErrorBoundSampler:
         self.last_rounds = 0
         self._rounds_guess = {}     # channel (-1 = scene) -> rounds the last call needed (speculative convergence test)
         self._pending = []          # speculative calls awaiting verify()
+        self.capture_flags = None   # (kind, rounds, device flags) of the last call made under CUDA-graph capture
         self._flag_bufs = []
         self.spec_hits = self.spec_misses = 0
 
@@ -55,7 +56,10 @@ class ErrorBoundSampler:
         eng = model.engine()
         channel = -1 if idx is None else int(idx)
         key = channel
+        capture = speculate == "capture"          # under CUDA-graph capture: no events, the caller ships the flags to the host
         guess = self._rounds_guess.get(key) if speculate else None
+        if capture and guess is None:
+            raise RuntimeError("graph capture of the sampler needs a round-count guess from a previous exact call")
         o = cam_loc.contiguous()
         d = ray_dirs.contiguous()
         p, st = _lib.ptr, _lib.stream
@@ -96,6 +100,8 @@ class ErrorBoundSampler:
         self.last_rounds = total_iters
         if guess is None:
             self._rounds_guess[key] = total_iters
+        elif capture:
+            self.capture_flags = (key, total_iters, flags)
         else:
             host = self._pinned_flags()
             host.copy_(flags[: host.numel()], non_blocking=True)
@@ -126,6 +132,25 @@ class ErrorBoundSampler:
             self._flag_bufs.append(torch.zeros(max(self.max_total_iters, 1), dtype=torch.int32).pin_memory())
         return self._flag_bufs[i]
 
+    def judge(self, key, rounds, f):
+        """Were `rounds` refinement rounds the reference's decision sequence, given the per-round device flags f (1 = some ray
+        still had beta > beta0 after that round)?  On a wrong guess the per-kind guess is corrected (or dropped when unknown)."""
+        actual = rounds
+        for j in range(rounds):
+            if f[j] == 0:                      # converged after round j + 1
+                actual = j + 1
+                break
+        else:
+            if rounds < self.max_total_iters:  # still not converged after the guessed number of rounds
+                actual = None
+        if actual == rounds:
+            return True
+        if actual is None:
+            self._rounds_guess.pop(key, None)   # unknown: the exact repeat will measure it
+        else:
+            self._rounds_guess[key] = actual
+        return False
+
     def verify(self):
         """True iff every speculative get_z_vals since the last verify() made the reference's decisions: all rounds before
         the last reported 'not converged' and the last one reported 'converged' (or the round limit was hit).  Updates the
@@ -135,21 +160,7 @@ class ErrorBoundSampler:
         ok = True
         for key, rounds, host, ev in self._pending:
             ev.synchronize()
-            f = host.tolist()
-            actual = rounds
-            for j in range(rounds):
-                if f[j] == 0:                      # converged after round j + 1
-                    actual = j + 1
-                    break
-            else:
-                if rounds < self.max_total_iters:  # still not converged after the guessed number of rounds
-                    actual = None
-            if actual != rounds:
-                ok = False
-                if actual is None:
-                    self._rounds_guess.pop(key, None)   # unknown: the exact repeat will measure it
-                else:
-                    self._rounds_guess[key] = actual
+            ok = self.judge(key, rounds, host.tolist()) and ok
         self._pending = []
         if ok:
             self.spec_hits += 1

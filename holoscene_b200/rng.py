@@ -19,7 +19,9 @@ class LiveDraws:
         return torch.rand(*shape, device=self.device, generator=self.gen)
 
     def randperm(self, name, n):
-        return torch.randperm(n, device=self.device, generator=self.gen)
+        # argsort of uniforms: a uniform random permutation like torch.randperm, but with no host-side branch, so the draw can be
+        # captured into the step's CUDA graph (train_step.TrainStep)
+        return torch.rand(n, device=self.device, generator=self.gen).argsort()
 
     def randint(self, name, high, shape):
         return torch.randint(high, shape, device=self.device, generator=self.gen)

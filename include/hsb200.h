@@ -221,6 +221,10 @@ int hsb_loss(const hsb_loss_cfg* cfg, const float* rgb_values, const float* dept
  * accumulates sum(g^2) in the same pass (the trainer's total_norm statistic, :367-372). */
 int hsb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                   float beta2, float eps, int step, float* grad_norm_sq, hsb_stream_t stream);
+/* Same with every gradient multiplied by grad_scale on the way in: the 1/world of the data-parallel mean after a SUM all-reduce of
+ * the per-shard gradients (no separate scaling pass over the 99 MB buffer); grad_norm_sq accumulates the scaled gradients. */
+int hsb_adam_step_scaled(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                         float beta2, float eps, int step, float grad_scale, float* grad_norm_sq, hsb_stream_t stream);
 
 /* Contraction kernels, exposed for their parity tests (epilogue kinds: csrc/gemm.cuh). */
 int hsb_gemm_tn(const float* A, long long lda, const float* B, long long ldb, long long M, int N, int K, int epi_kind, float* out,

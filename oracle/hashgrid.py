@@ -54,9 +54,27 @@ def _ip(t: torch.Tensor):
     return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_int))
 
 
+# CUDA tensors: the REFERENCE's own kernels (oracle/_ref/_hash_encoder_ref.so = hashencoder/src/hashencoder.cu compiled unchanged
+# by oracle/build_ref.py).  Used by bench.py's reference-on-GPU leg: the oracle's torch op sequence on `cuda` with the reference's
+# hash-grid extension underneath -- the reference's GPU path as far as it can travel to the GPU box.
+_ref_mod = None
+
+
+def _ref():
+    global _ref_mod
+    if _ref_mod is None:
+        from . import build_ref
+        _ref_mod = build_ref.load_ref()
+        if _ref_mod is None:
+            raise RuntimeError("oracle/_ref/_hash_encoder_ref.so is not built (needs /root/reference at build time)")
+    return _ref_mod
+
+
 # ---- the three FFI entry points, same argument meaning as hashencoder/src/hashencoder.h:13-15 ----
 def hash_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs, dy_dx):
     assert D == 3, "oracle restates the D=3 path only"
+    if inputs.is_cuda:
+        return _ref().hash_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, float(S), H, bool(calc_grad_inputs), dy_dx)
     lib().hso_forward(_fp(inputs), _fp(embeddings), _ip(offsets), _fp(outputs), B, C, L, float(S), H,
                       int(bool(calc_grad_inputs)), _fp(dy_dx))
 
@@ -64,6 +82,9 @@ def hash_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, 
 def hash_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H,
                          calc_grad_inputs, dy_dx, grad_inputs):
     assert D == 3
+    if inputs.is_cuda:
+        return _ref().hash_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, float(S), H,
+                                           bool(calc_grad_inputs), dy_dx, grad_inputs)
     lib().hso_backward(_fp(grad), _fp(inputs), _fp(embeddings), _ip(offsets), _fp(grad_embeddings), B, C, L,
                        float(S), H, int(bool(calc_grad_inputs)), _fp(dy_dx), _fp(grad_inputs))
 
@@ -71,6 +92,9 @@ def hash_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, 
 def hash_encode_second_backward(grad, inputs, embeddings, offsets, B, D, C, L, S, H, calc_grad_inputs,
                                 dy_dx, grad_grad_inputs, grad_grad, grad2_embeddings):
     assert D == 3
+    if inputs.is_cuda:
+        return _ref().hash_encode_second_backward(grad, inputs, embeddings, offsets, B, D, C, L, float(S), H, bool(calc_grad_inputs),
+                                                  dy_dx, grad_grad_inputs, grad_grad, grad2_embeddings)
     lib().hso_second_backward(_fp(grad), _fp(inputs), _fp(embeddings), _ip(offsets), B, C, L, float(S), H,
                               _fp(dy_dx), _fp(grad_grad_inputs), _fp(grad_grad), _fp(grad2_embeddings))
 
@@ -128,8 +152,9 @@ class _Encode(torch.autograd.Function):
         B = x01.shape[0]
         L = offsets.shape[0] - 1
         C = emb.shape[1]
-        out = torch.empty(L, B, C)
-        dy_dx = torch.empty(B, L * 3 * C) if need_dx else torch.empty(1)
+        offsets = offsets.to(x01.device)
+        out = torch.empty(L, B, C, device=x01.device)
+        dy_dx = torch.empty(B, L * 3 * C, device=x01.device) if need_dx else torch.empty(1, device=x01.device)
         hash_encode_forward(x01, emb.contiguous(), offsets, out, B, 3, C, L, S, H, need_dx, dy_dx)
         ctx.save_for_backward(x01, emb, offsets, dy_dx)
         ctx.meta = (S, H, need_dx)

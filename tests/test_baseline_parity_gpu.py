@@ -41,9 +41,12 @@ def _rays(R, S, seed):
 
 # (K, R, S): BASELINE configs[1] (K = 32), [2] (K = 21), [4] (K = 64, 192 samples), [0] (K = 2, 64 samples)
 BASE_CASES = [(32, 256, 128), (21, 256, 128), (64, 128, 192), (2, 512, 64)]
-# fast mode: relative-L2 bound per output / gradient family = ~2x the errors measured on a B200
-FAST_OUT_TOL = 1e-2
-FAST_GRAD_TOL = 6e-2
+# fast mode: relative-L2 bounds = ~2x the errors measured on a B200 (gpurun r02_tests1): per-ray outputs
+# <= 2.1e-3 (K = 2; 3.4e-4 at K >= 21); parameter gradients <= 8.2e-3, except the colour path (PE4 of the raw gradient into ReLUs,
+# see common.grad_tol) <= 2.9e-2; eikonal pass: outputs <= 5.8e-4, gradients <= 2.0e-3
+FAST_OUT_TOL = 5e-3
+FAST_GRAD_TOL = 2e-2
+FAST_GRAD_TOL_COLOUR = 6e-2
 
 
 @pytest.mark.parametrize("precise", [True, False])
@@ -72,7 +75,7 @@ def test_main_pass_backward_matches_oracle_at_baseline_K(K, R, S, precise):
     rows = [(names[i], common.rel_err(got[i].cpu(), outs[i].detach()), 5e-4 if precise else FAST_OUT_TOL) for i in range(4)]
     for n, prm in m.named_parameters():
         ref = p[n].grad if p[n].grad is not None else torch.zeros_like(p[n])
-        tol = common.grad_tol(n, 2e-3) if precise else max(FAST_GRAD_TOL, 3 * common.grad_tol(n, 2e-3))
+        tol = common.grad_tol(n, 2e-3) if precise else (FAST_GRAD_TOL if common.grad_tol(n, 2e-3) == 2e-3 else FAST_GRAD_TOL_COLOUR)
         rows.append(("grad_" + n, common.rel_err(prm.grad.cpu(), ref), tol))
     report(f"main pass K={K} R={R} S={S} logmap 19 precise={precise}", rows)
     bad = [r for r in rows if not (r[1] <= r[2])]
@@ -103,27 +106,29 @@ def test_eikonal_pass_backward_matches_oracle_at_baseline_K(K, precise):
     eng.eikonal_backward(cot_g.cuda(), cot_s.cuda())
     eng.finish()
     torch.cuda.synchronize()
-    ot = 1e-3 if precise else FAST_OUT_TOL
+    ot = 1e-3 if precise else 2e-3
     rows = [("grad_theta", common.rel_err(ggt.cpu(), gt.detach()), ot), ("sample_sdf", common.rel_err(ssdf.cpu(), raw.detach()), ot / 2),
-            ("sample_minsdf", common.rel_err(smin.cpu()[:, 0], raw.detach().min(1)[0]), ot / 2)]
+            ("sample_minsdf", common.rel_err(smin.cpu()[:, 0], raw.detach().min(1)[0]), ot)]
     for nm, prm in m.named_parameters():
         if p[nm].grad is None:
             continue
-        rows.append(("grad_" + nm, common.rel_err(prm.grad.cpu(), p[nm].grad), 2e-3 if precise else FAST_GRAD_TOL))
+        rows.append(("grad_" + nm, common.rel_err(prm.grad.cpu(), p[nm].grad), 2e-3 if precise else 5e-3))
     report(f"eikonal pass K={K} logmap 19 precise={precise}", rows)
     bad = [r for r in rows if not (r[1] <= r[2])]
     assert not bad, bad
 
 
+@pytest.mark.parametrize("beta_init", [0.1, 0.01])
 @pytest.mark.parametrize("precise", [True, False])
-def test_c1_step_end_to_end_matches_oracle(precise):
+def test_c1_step_end_to_end_matches_oracle(precise, beta_init):
     """BASELINE configs[0]: 'Replica room_0 Stage-1, 1 object + background, 512 rays x 64 samples' -- the whole train step
     (error-bound sampler, scene pass, eikonal pass, loss, backward) against the CPU oracle on identical weights / rays / draws."""
     from holoscene_b200 import synthetic
     from holoscene_b200.rng import ReplayDraws
     from oracle import model as om
     K, R = 2, 512
-    cfg = _cfg(K, 64)
+    import dataclasses
+    cfg = dataclasses.replace(_cfg(K, 64), beta_init=beta_init)      # 0.01: a sharp density, the sampler needs several refinement rounds
     sd = common.seeded_state_dict(cfg)
     Kmat, pose = synthetic.camera()
     uv, gt = synthetic.rays_and_gt(R, K)
@@ -141,7 +146,7 @@ def test_c1_step_end_to_end_matches_oracle(precise):
     losses["loss"].backward()
     torch.cuda.synchronize()
     rows = []
-    ot = 5e-3 if precise else 2e-2
+    ot = 5e-3 if precise else 1e-2
     for k in ("z_vals", "rgb_values", "depth_values", "normal_map", "object_opacity", "grad_theta", "sample_sdf"):
         rows.append((k, common.rel_err(out[k].detach().cpu(), ref[k].detach()), 3e-4 if k == "z_vals" else ot))
     for k in ("loss", "rgb_loss", "eikonal_loss", "depth_loss", "normal_l1", "normal_cos", "semantic_loss"):
@@ -154,8 +159,10 @@ def test_c1_step_end_to_end_matches_oracle(precise):
             rows.append(("grad_" + n, common.rel_err(prm.grad.cpu(), ref_g), tol))
         else:
             a, b = prm.grad.cpu().double().flatten(), ref_g.double().flatten()
-            rows.append(("grad_" + n + " (1 - cosine)", 1.0 - float((a @ b) / (a.norm() * b.norm() + 1e-300)), 5e-2))
-    report(f"C1 512x64 K=2 end to end precise={precise} (sampler rounds {m.ray_sampler.last_rounds})", rows)
+            rows.append(("grad_" + n + " (1 - cosine)", 1.0 - float((a @ b) / (a.norm() * b.norm() + 1e-300)), 5e-3))
+    report(f"C1 512x64 K=2 end to end precise={precise} beta={beta_init} (sampler rounds {m.ray_sampler.last_rounds})", rows)
+    if beta_init < 0.05:
+        assert m.ray_sampler.last_rounds >= 2
     bad = [r for r in rows if not (r[1] <= r[2])]
     assert not bad, bad
 

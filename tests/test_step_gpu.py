@@ -109,20 +109,21 @@ def test_step_fast_tf32_within_stated_tolerance():
     truncated to a 10-bit mantissa by the MMA).  The per-object SDF values then carry ~2e-3 relative error, which
     flips the arg-min over objects for points where two channels are within that distance; the gradient of the
     min-SDF is discontinuous there, so element-wise gradient agreement is not a meaningful bound for this mode
-    (the kernel-level test on identical samples holds it to 6e-2).  Held here: per-ray outputs and the loss to
-    2e-2, and every parameter gradient must point the same way as the reference's (cosine > 0.9)."""
+    (the kernel-level tests on identical samples hold it to 2e-2 / 6e-2 relative L2, tests/test_baseline_parity_gpu.py).  Held
+    here at ~2x the measured values: per-ray outputs and the loss to 2e-3 (measured 4.5e-4), and every parameter gradient's
+    1 - cosine vs the reference's <= 2e-2 (measured <= 7.8e-3)."""
     g = common.load_golden("step_train")
     m, out, losses, grads = run_product(g, precise=False)
     rows = []
     for k in ("rgb_values", "depth_values", "object_opacity"):
         ref = g["out_" + k]
-        rows.append((k, float(np.abs(out[k].detach().cpu().numpy() - ref).max()) / max(1.0, float(np.abs(ref).max())), 2e-2))
-    rows.append(("loss", abs(float(losses["loss"]) - float(g["loss_loss"])) / abs(float(g["loss_loss"])), 2e-2))
+        rows.append((k, float(np.abs(out[k].detach().cpu().numpy() - ref).max()) / max(1.0, float(np.abs(ref).max())), 2e-3))
+    rows.append(("loss", abs(float(losses["loss"]) - float(g["loss_loss"])) / abs(float(g["loss_loss"])), 2e-3))
     for k, ref in g.items():
         if k.startswith("grad_"):
             a, b = grads[k[5:]].double().flatten(), torch.from_numpy(ref).double().flatten()
             cos = float((a @ b) / (a.norm() * b.norm() + 1e-300))
-            rows.append((k + " (1 - cosine)", 1.0 - cos, 0.1))
+            rows.append((k + " (1 - cosine)", 1.0 - cos, 2e-2))
     report("step_train fast", rows)
     bad = [r for r in rows if not (r[1] <= r[2])]
     assert not bad, bad
@@ -238,7 +239,7 @@ def test_main_pass_backward_matches_oracle_on_identical_samples(precise, tol):
     rows = [(f"out{i}", common.rel_err(got[i].cpu(), outs[i].detach()), 5e-4 if precise else 2e-2) for i in range(4)]
     for n, prm in m.named_parameters():
         ref = p[n].grad if p[n].grad is not None else torch.zeros_like(p[n])
-        rows.append(("grad_" + n, common.rel_err(prm.grad.cpu(), ref), common.grad_tol(n, tol) if precise else 3 * common.grad_tol(n, tol)))
+        rows.append(("grad_" + n, common.rel_err(prm.grad.cpu(), ref), common.grad_tol(n, tol) if precise else (2e-2 if common.grad_tol(n, 2e-3) == 2e-3 else 6e-2)))
     report(f"main pass backward, identical samples, precise={precise}", rows)
     bad = [r for r in rows if not (r[1] <= r[2])]
     assert not bad, bad
@@ -552,3 +553,40 @@ def test_checkpoint_files_round_trip(tmp_path):
     for n, (o, k, _) in seg.items():
         assert torch.equal(opt.exp_avg[o:o + k], opt2.exp_avg[o:o + k]) and torch.equal(opt.exp_avg_sq[o:o + k], opt2.exp_avg_sq[o:o + k]), n
     assert opt2.step_count == 2 and [grp["lr"] for grp in opt2.groups] == [grp["lr"] for grp in opt.groups]
+
+
+def test_cuda_graph_step_matches_kernel_by_kernel_step():
+    """TrainStep(use_graph=True): after two kernel-by-kernel steps the device part of a step is recorded into a CUDA graph and
+    replayed; the sampler's host decision is judged from flags the graph ships to pinned memory.  Same seeds -> the same random
+    draws (torch's graph-safe Philox offsets) -> the same loss sequence as launching every kernel (up to the summation order of
+    atomics).  Background-patch steps (iter % 10 == 0) stay kernel by kernel.  A wrong round-count guess must be detected and the
+    step repeated in exact mode."""
+    from holoscene_b200 import synthetic
+    from holoscene_b200.optim import StageOneAdam
+    from holoscene_b200.train_step import TrainStep
+    g = common.load_golden("step_train")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    uv, pose, K, gt, _ = common.golden_inputs(g)
+    runs = {}
+    for use_graph in (False, True):
+        m = build_model(cfg, sd, False).train()
+        step = TrainStep(m, make_loss(), StageOneAdam(m), use_graph=use_graph)
+        step.iter_step = 1
+        torch.manual_seed(77)
+        losses = []
+        for it in range(12):
+            if use_graph and it == 7:
+                m.ray_sampler._rounds_guess[-1] = max(1, m.ray_sampler._rounds_guess[-1] - 1)      # poison the guess once
+            out, lo = step({"uv": uv.clone().cuda(), "intrinsics": K.cuda(), "pose": pose.cuda()}, gt)
+            losses.append(float(lo["loss"]))
+        torch.cuda.synchronize()
+        runs[use_graph] = (losses, step.graph_stats(), m._flat.clone())
+    st = runs[True][1]
+    assert st["captures"] >= 1 and st["replays"] >= 5 and st["misses"] >= 1, st
+    assert runs[False][1]["replays"] == 0
+    a, b = runs[True][0], runs[False][0]
+    print("\n[graph vs eager losses]", [f"{x:.5f}/{y:.5f}" for x, y in zip(a, b)], st)
+    for x, y in zip(a[:7], b[:7]):                    # identical random streams until the poisoned step repeats (and re-draws)
+        assert abs(x - y) <= 2e-3 * abs(y), (a, b)
+    assert all(np.isfinite(a))
