@@ -13,8 +13,8 @@ N > 1, Adam.  Headline workload at N = 1: BASELINE.json configs[1] = "Replica ro
 N > 1: weak scaling (4096 rays per GPU) is the headline line; one all-reduce of the flat gradient buffer per step.
 
 Extra measurements ride on the same JSON line (key "extra"): the other BASELINE configs (c3: K = 21; c5shard: a 1024-ray shard of
-8192 x 192 with K = 64; c1: 512 x 64, K = 2), a "trained" variant of c2 (beta = 5e-3: the sampler runs 4-5 refinement rounds
-instead of 1), the fp32-grade mode (3xTF32), the reference's torch op sequence on the same GPU with the reference's own hash-grid
+8192 x 192 with K = 64; c1: 512 x 64, K = 2), a "trained" variant of c2 (beta = 1e-3: the sampler runs up to its 5-round limit
+instead of 1 round), the fp32-grade mode (3xTF32), the reference's torch op sequence on the same GPU with the reference's own hash-grid
 CUDA kernels (key "reference_gpu"), and, for N > 1, strong scaling at 4096 and 8192 global rays.
 
 --impl reference times the reference path's CPU restatement (oracle/, the only other place that may
@@ -47,8 +47,8 @@ WORKLOADS = {
     "c5shard": dict(name="gibson_stage1_K64_8192x192_shard_of_1024_rays", R=1024, K=64, N_samples=158, beta=0.1, **_SAMPLER),
     # configs[0]: 1 object + background, 512 x 64 (the reference's CPU-runnable case)
     "c1": dict(name="replica_room_0_stage1_K2_512x64", R=512, K=2, N_samples=30, beta=0.1, **_SAMPLER),
-    # c2 with a sharp density (a trained scene has beta -> 1e-3): the error-bound sampler runs 4-5 rounds instead of 1
-    "trained": dict(name="replica_room_0_stage1_full_conf_4096x128_beta5e-3", R=4096, K=32, N_samples=94, beta=5e-3, **_SAMPLER),
+    # c2 with a sharp density (a trained scene has beta -> 1e-3): the error-bound sampler runs up to its 5-round limit instead of 1
+    "trained": dict(name="replica_room_0_stage1_full_conf_4096x128_beta1e-3", R=4096, K=32, N_samples=94, beta=1e-3, **_SAMPLER),
 }
 WORKLOAD = WORKLOADS["c2"]
 METRIC = "rendered samples/sec (rays x samples) per Stage-1 SDF train step"

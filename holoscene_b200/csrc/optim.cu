@@ -9,11 +9,12 @@
 
 namespace hsb {
 
-// one warp per output row n:  We[n, 0:cols] = g[n] * v[n,:] / ||v[n,:]||,  We[n, cols:ldw] = 0,
-// and the transposed copy WeT[k, n] (ldt >= rows; rows of WeT beyond `cols` are zeroed by the caller's memset).
+// one warp per output row n:  We[n, (k + rot) % cols] = g[n] * v[n,k] / ||v[n,:]||,  We[n, cols:ldw] = 0,
+// and the transposed copy WeT[(k + rot) % cols, n] (ldt >= rows; rows of WeT beyond `cols` are zeroed by the caller's memset).
+// rot != 0 stores the effective weight with its input columns rotated (the render net's input row keeps the feature block first).
 __global__ void __launch_bounds__(256) wn_forward_kernel(const float* __restrict__ v, const float* __restrict__ g, int rows,
                                                          int cols, float* __restrict__ We, int ldw, float* __restrict__ WeT,
-                                                         int ldt, int rtf) {
+                                                         int ldt, int rtf, int rot) {
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n >= rows) return;
@@ -23,29 +24,36 @@ __global__ void __launch_bounds__(256) wn_forward_kernel(const float* __restrict
     ss = warp_sum(ss);
     const float sc = g[n] / sqrtf(ss);
     for (int k = lane; k < ldw; k += 32) {
-        const float w = k < cols ? rtf32(sc * vr[k], rtf) : 0.0f;
-        We[(long long)n * ldw + k] = w;
-        if (WeT && k < cols) WeT[(long long)k * ldt + n] = w;
+        if (k < cols) {
+            const float w = rtf32(sc * vr[k], rtf);
+            int ke = k + rot;
+            if (ke >= cols) ke -= cols;
+            We[(long long)n * ldw + ke] = w;
+            if (WeT) WeT[(long long)ke * ldt + n] = w;
+        } else {
+            We[(long long)n * ldw + k] = 0.0f;
+        }
     }
 }
 
 // dv[n,:] += (g/||v||) (dW[n,:] - (dW[n,:].vhat) vhat),  dg[n] += dW[n,:].vhat
 __global__ void __launch_bounds__(256) wn_backward_kernel(const float* __restrict__ dWe, int ldw, const float* __restrict__ v,
                                                           const float* __restrict__ g, int rows, int cols,
-                                                          float* __restrict__ dv, float* __restrict__ dg) {
+                                                          float* __restrict__ dv, float* __restrict__ dg, int rot) {
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n >= rows) return;
     const float* vr = v + (long long)n * cols;
     const float* dw = dWe + (long long)n * ldw;
     float ss = 0.0f, dot = 0.0f;
-    for (int k = lane; k < cols; k += 32) { ss += vr[k] * vr[k]; dot += dw[k] * vr[k]; }
+    auto eff = [&](int k) { const int ke = k + rot; return ke >= cols ? ke - cols : ke; };     // effective column of reference column k
+    for (int k = lane; k < cols; k += 32) { ss += vr[k] * vr[k]; dot += dw[eff(k)] * vr[k]; }
     ss = warp_sum(ss);
     dot = warp_sum(dot);
     const float inv = rsqrtf(ss);
     const float dotn = dot * inv;               // dW . vhat
     const float sc = g[n] * inv;
-    for (int k = lane; k < cols; k += 32) dv[(long long)n * cols + k] += sc * (dw[k] - dotn * vr[k] * inv);
+    for (int k = lane; k < cols; k += 32) dv[(long long)n * cols + k] += sc * (dw[eff(k)] - dotn * vr[k] * inv);
     if (lane == 0) dg[n] += dotn;
 }
 
@@ -121,13 +129,13 @@ int launch_add_into(const float* src, float* dst, int n, cudaStream_t st) {
 }
 
 int launch_wn_forward(const float* v, const float* g, int rows, int cols, float* We, int ldw, float* WeT, int ldt, int rtf,
-                      cudaStream_t st) {
-    wn_forward_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(v, g, rows, cols, We, ldw, WeT, ldt, rtf);
+                      cudaStream_t st, int rot) {
+    wn_forward_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(v, g, rows, cols, We, ldw, WeT, ldt, rtf, rot);
     return check_launch("wn_forward");
 }
 int launch_wn_backward(const float* dWe, int ldw, const float* v, const float* g, int rows, int cols, float* dv, float* dg,
-                       cudaStream_t st) {
-    wn_backward_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(dWe, ldw, v, g, rows, cols, dv, dg);
+                       cudaStream_t st, int rot) {
+    wn_backward_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(dWe, ldw, v, g, rows, cols, dv, dg, rot);
     return check_launch("wn_backward");
 }
 int launch_transpose(const float* W, int rows, int cols, float* WT, int ldt, float* Wcopy, int rtf, cudaStream_t st) {

@@ -23,12 +23,12 @@ __device__ __forceinline__ void pe_write(float* __restrict__ dst, float x, float
 }
 
 // points of a ray batch: x = o + z d;  H0[:, 0:39] = PE6(x), H0[:,71] = 0;
-// RIN[:, 0:27] = PE4(x), RIN[:, 27:54] = PE4(d), RIN[:, 337:344] = 0   (RIN may be null: SDF-only use)
+// RIN[:, 256:283] = PE4(x), RIN[:, 283:310] = PE4(d), RIN[:, 337:344] = 0   (RIN may be null: SDF-only use; layout: step.cuh)
 // A CTA owns 128 points.  Phase 1: thread = point, 18 (+12) sincosf into a shared tile (PE4(x) is the first 27 columns of
 // PE6(x)).  Phase 2: thread = (point, 16-byte slot); consecutive threads write consecutive float4s of a row, so every store
 // instruction covers whole sectors (a per-point scalar walk writes 4 bytes into 32 different rows per instruction).
-// Slots: 0..9 = H0 columns 0..39, 10 = H0 columns 68..71, 11..24 = RIN columns 0..55, 25..26 = RIN columns 336..343.  Columns
-// zero-filled inside those slots but not owned here (H0 39, 68..70: hash features; RIN 54, 55: PE4(g); RIN 336: feature) are
+// Slots: 0..9 = H0 columns 0..39, 10 = H0 columns 68..71, 11..24 = RIN columns 256..311, 25..26 = RIN columns 336..343.  Columns
+// zero-filled inside those slots but not owned here (H0 39, 68..70: hash features; RIN 310, 311, 336: PE4(g)) are
 // written by later kernels of the same pass.
 constexpr int RP_PTS = 128;
 __global__ void __launch_bounds__(RP_PTS) ray_points_kernel(const float* __restrict__ o, const float* __restrict__ d,
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(RP_PTS) ray_points_kernel(const float* __restr
                 e[k] = c < 27 ? sx[lp][c] : (c < 54 ? sd[lp][c - 27] : 0.0f);
             }
             v = make_float4(e[0], e[1], e[2], e[3]);
-            dst = RIN + p * LD_RIN + j;
+            dst = RIN + p * LD_RIN + RIN_PE + j;
         } else {
             dst = RIN + p * LD_RIN + 336 + 4 * (slot - 25);
         }
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) points_pe_kernel(const float* __restrict_
 // min over the K object channels, first index on ties (== -maxpool1d(-s)); channel >= 0 selects one channel.
 // Rows are Kp = 8 n floats, 16-byte aligned: read as float4.
 __global__ void __launch_bounds__(256) sdf_min_kernel(const float* __restrict__ SR, long long N, int K, int Kp, int channel,
-                                                      float* __restrict__ sdf, int* __restrict__ kstar) {
+                                                      float* __restrict__ sdf, int* __restrict__ kstar, unsigned long long mask) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     const float* s = SR + p * Kp;
@@ -105,12 +105,13 @@ __global__ void __launch_bounds__(256) sdf_min_kernel(const float* __restrict__ 
     if (channel >= 0) { best = channel; v = s[channel]; }
     else {
         v = 3.0e38f;
+        bool have = false;                                   // the min runs over the channels of `mask` (Stage-2 object subsets)
         for (int k4 = 0; k4 < Kp; k4 += 4) {
             const float4 q = __ldg(reinterpret_cast<const float4*>(s + k4));
             const float e[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (k4 + u < K && (e[u] < v || (k4 + u) == 0)) { v = e[u]; best = k4 + u; }
+                if (k4 + u < K && ((mask >> (k4 + u)) & 1ull) && (e[u] < v || !have)) { v = e[u]; best = k4 + u; have = true; }
         }
     }
     sdf[p] = v;
@@ -182,7 +183,7 @@ __device__ __forceinline__ void chain_end_col(const ChainCol& c, int j, const fl
         g[0] += __ldg(dy + c.dyoff) * hq; g[1] += __ldg(dy + c.dyoff + 2) * hq; g[2] += __ldg(dy + c.dyoff + 4) * hq;
     }
 }
-// end of the chain: G[m] = (dh0/dx)^T Q0[m];  rows m = s*N + p.  Optionally PE4(g) -> RIN[p, 54:81].
+// end of the chain: G[m] = (dh0/dx)^T Q0[m];  rows m = s*N + p.  Optionally PE4(g) -> RIN[p, 310:337].
 __global__ void __launch_bounds__(32 * CE_WARPS) chain_end_kernel(const float* __restrict__ Q0, const float* __restrict__ H0,
                                                                   const float* __restrict__ DY, long long N, long long rows,
                                                                   float* __restrict__ G, float* __restrict__ RIN, int rtf) {
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(32 * CE_WARPS) chain_end_kernel(const float* _
         if (lane < 8) chain_end_col(c2, lane + 64, q, h, dy, g);
         g[0] = warp_sum(g[0]); g[1] = warp_sum(g[1]); g[2] = warp_sum(g[2]);
         if (lane < 3) G[m * 3 + lane] = lane == 0 ? g[0] : (lane == 1 ? g[1] : g[2]);
-        if (RIN && lane < 27) RIN[p * LD_RIN + 54 + lane] = rtf32(pe4_slot(lane, g), rtf);
+        if (RIN && lane < 27) RIN[p * LD_RIN + RIN_PEG + lane] = rtf32(pe4_slot(lane, g), rtf);
     }
 }
 
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(32 * CE_WARPS) chain_end_kernel(const float* _
 // 4096 x 128: the row's reductions put three shuffle trees on every row's critical path, while here a thread streams its whole
 // row through L1 with 16-byte loads and needs no cross-lane traffic at all.)
 // backward of chain_end: dQ0 = (dh0/dx) dG, where for the main pass
-//   dG = dGn (normal-map term) + PE4(g)^T dRIN[:, 54:81]        (RIN holds sin/cos of g)
+//   dG = dGn (normal-map term) + PE4(g)^T dRIN[:, 310:337]      (RIN holds sin/cos of g)
 // The total dG is written back to dGn (it feeds the second-order hash scatter).
 __global__ void __launch_bounds__(128) chain_end_bwd_kernel(float* __restrict__ dG, const float* __restrict__ dRIN,
                                                             const float* __restrict__ RIN, const float* __restrict__ H0,
@@ -221,8 +222,8 @@ __global__ void __launch_bounds__(128) chain_end_bwd_kernel(float* __restrict__ 
     const long long p = m % N;
     float dg[3] = {dG[m * 3 + 0], dG[m * 3 + 1], dG[m * 3 + 2]};
     if (dRIN) {
-        const float* dr = dRIN + p * LD_RIN + 54;          // 216 B into the row: only 8-byte aligned
-        const float* r = RIN + p * LD_RIN + 54;
+        const float* dr = dRIN + p * LD_RIN + RIN_PEG;     // 1240 B into the row: only 8-byte aligned
+        const float* r = RIN + p * LD_RIN + RIN_PEG;
         float f = 1.0f;
 #pragma unroll
         for (int d = 0; d < 3; ++d) dg[d] += dr[d];
@@ -574,9 +575,9 @@ int launch_points_pe(const float* X, long long N, float* H0, int rtf, cudaStream
     points_pe_kernel<<<cdiv(N, 256), 256, 0, st>>>(X, N, H0, rtf);
     return check_launch("points_pe");
 }
-int launch_sdf_min(const float* SR, long long N, int K, int Kp, int channel, float* sdf, int* kstar, cudaStream_t st) {
+int launch_sdf_min(const float* SR, long long N, int K, int Kp, int channel, float* sdf, int* kstar, cudaStream_t st, unsigned long long mask) {
     if (N == 0) return HSB_OK;
-    sdf_min_kernel<<<cdiv(N, 256), 256, 0, st>>>(SR, N, K, Kp, channel, sdf, kstar);
+    sdf_min_kernel<<<cdiv(N, 256), 256, 0, st>>>(SR, N, K, Kp, channel, sdf, kstar, mask);
     return check_launch("sdf_min");
 }
 int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long long N, int K, int nseed, float* P2, int rtf,

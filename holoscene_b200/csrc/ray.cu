@@ -58,6 +58,9 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int nr
 //   mode 0 (scene): weights from the scene (min) SDF; colour / semantics / opacity composites.
 //   mode 1 (bg patch, network.py:947-968): weights from SR[:, 0] for depth / normals; the scene-SDF
 //          weights are used only for the semantic arg-max (bg_mask).
+//   mode 2 (Stage-2 object subsets, network.py:1235-1306): `weights` from SDF = min over the subset channels (semantics of the
+//          subset channels, one opacity per ray = sum of weights), `bg_weights` from SDFB = min over the object channels
+//          (colour, depth, normal composites).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * CMP_WARPS) composite_fwd_kernel(CompositeArgs a) {
     extern __shared__ float cmp_smem[];
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_fwd_kernel(Composite
 
     float carry = 0.0f, carry2 = 0.0f;
     float acc_rgb[3] = {0.f, 0.f, 0.f}, acc_n[3] = {0.f, 0.f, 0.f};
-    float acc_wz = 0.f, acc_w = 0.f;
+    float acc_wz = 0.f, acc_w = 0.f, acc_w2 = 0.f;
     float acc_op[HSB_MAX_K / 32] = {0.f, 0.f}, acc_sem[HSB_MAX_K / 32] = {0.f, 0.f};   // lane k%32 owns channel k
     for (int base = 0; base < S; base += 32) {
         const int i = base + lane;
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_fwd_kernel(Composite
             s_scene = a.SDF[p0 + i];
         }
         __syncwarp();
-        if (ok) s_w = (a.mode == 1) ? tile[lane * ldt] : s_scene;
+        if (ok) s_w = (a.mode == 1) ? tile[lane * ldt] : (a.mode == 2 ? a.SDFB[p0 + i] : s_scene);
         const float E = ok ? delta * laplace_density(s_w, beta) : 0.0f;
         const float incl = warp_scan_incl(E, lane);
         // exclusive prefix through a shuffle, NOT incl - E: the last interval is 1e10 long, so E ~ 1e11 there and
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_fwd_kernel(Composite
         const float w = ok ? (1.0f - expf(-E)) * T : 0.0f;
         carry += __shfl_sync(0xffffffffu, incl, 31);
         float w2 = w;
-        if (a.mode == 1) {        // scene weights for the semantic composite
+        if (a.mode != 0) {        // scene / subset weights for the semantic composite
             const float E2 = ok ? delta * laplace_density(s_scene, beta) : 0.0f;
             const float incl2 = warp_scan_incl(E2, lane);
             float excl2 = __shfl_up_sync(0xffffffffu, incl2, 1);
@@ -112,14 +115,15 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_fwd_kernel(Composite
         }
         sD[lane] = delta; sT[lane] = T; sW2[lane] = w2;
         if (ok) {
-            a.W[p0 + i] = w;
+            if (a.mode == 2) { a.W[p0 + i] = w2; a.WB[p0 + i] = w; acc_w2 += w2; }
+            else a.W[p0 + i] = w;
             a.T[p0 + i] = T;
             acc_w += w;
             acc_wz += w * zi;
             const float* g = a.G + (p0 + i) * 3;
             const float nrm = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]) + 1e-6f;
             acc_n[0] += w * g[0] / nrm; acc_n[1] += w * g[1] / nrm; acc_n[2] += w * g[2] / nrm;
-            if (a.mode == 0) {
+            if (a.mode != 1) {
                 const float4 c = __ldg(reinterpret_cast<const float4*>(a.RGB) + p0 + i);
                 acc_rgb[0] += w * c.x; acc_rgb[1] += w * c.y; acc_rgb[2] += w * c.z;
             }
@@ -141,15 +145,23 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_fwd_kernel(Composite
         }
         __syncwarp();                                        // the tile is re-staged by the next chunk
     }
-    for (int k = lane; k < K; k += 32) {
-        if (a.opacity) a.opacity[(long long)r * K + k] = acc_op[k >> 5];
-        a.semantic[(long long)r * K + k] = acc_sem[k >> 5];
+    if (a.mode == 2) {                                       // semantics of the subset channels, packed in ascending channel order
+        const int nsub = __popcll(a.mask);
+        for (int k = lane; k < K; k += 32)
+            if ((a.mask >> k) & 1ull) a.semantic[(long long)r * nsub + __popcll(a.mask & ((1ull << k) - 1ull))] = acc_sem[k >> 5];
+        acc_w2 = warp_sum(acc_w2);
+        if (lane == 0 && a.opacity) a.opacity[r] = acc_w2;  // sum_i (1 - exp(-delta sigma(sdf_i))) T_i = sum of the subset weights
+    } else {
+        for (int k = lane; k < K; k += 32) {
+            if (a.opacity) a.opacity[(long long)r * K + k] = acc_op[k >> 5];
+            a.semantic[(long long)r * K + k] = acc_sem[k >> 5];
+        }
     }
     acc_w = warp_sum(acc_w); acc_wz = warp_sum(acc_wz);
 #pragma unroll
     for (int c = 0; c < 3; ++c) { acc_rgb[c] = warp_sum(acc_rgb[c]); acc_n[c] = warp_sum(acc_n[c]); }
     if (lane == 0) {
-        if (a.mode == 0) {
+        if (a.mode != 1) {
             a.rgb_values[r * 3 + 0] = acc_rgb[0]; a.rgb_values[r * 3 + 1] = acc_rgb[1]; a.rgb_values[r * 3 + 2] = acc_rgb[2];
         }
         a.depth_values[r] = a.depth_scale[r] * (acc_wz / (acc_w + 1e-8f));
@@ -228,7 +240,7 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_bwd_kernel(Composite
             const float den = rn + 1e-6f;
             const float gv = gg[0] * dn[0] + gg[1] * dn[1] + gg[2] * dn[2];
             ai = ddepth * (zi * Wt - Nz) / (Wt * Wt) + gv / den;
-            if (a.mode == 0) {
+            if (a.mode != 1) {
                 const float4 c = __ldg(reinterpret_cast<const float4*>(a.RGB) + p0 + i);
                 ai += drgb[0] * c.x + drgb[1] * c.y + drgb[2] * c.z;
                 float4 o;

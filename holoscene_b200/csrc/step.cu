@@ -58,6 +58,7 @@ struct Slot {
     float *X, *H0, *DY, *H1, *H2, *SR, *SDF, *P2, *P1, *Q0, *G;
     int* KS;
     float *EC, *C1, *RIN, *U1, *U2, *RGB, *W, *T, *WSUM, *WZSUM, *ZV, *DSCALE, *ROT;
+    float *SDFB, *WB;   // Stage-2 subset pass: min over the object channels, bg_weights
     // backward temporaries
     float *dO, *dS, *dG, *dQ0, *dQ1, *dA1x, *dQ2, *dA2x, *dA2, *dA1, *dH0E, *dU2, *dU1, *dRIN, *dFEAT, *dC1, *dEC;
     // forward-mode (tangent) buffers of the eikonal slot, rows m = d*N + p (d = 0..2)
@@ -74,7 +75,7 @@ struct Ctx {
     char* ws; size_t ws_bytes; size_t ws_used;
     std::vector<NamedBuf> names;
     // derived weights
-    float *W0e, *W0eT, *W1e, *W1eT, *W2e, *W2eT, *C0e, *C0T, *C1e, *C1T, *R0e, *R0eT, *R1e, *R1eT, *R2e;
+    float *W0e, *W0eT, *W1e, *W1eT, *W2e, *W2eT, *C0e, *C0T, *C1e, *C1T, *R0e, *R0eT, *R1e, *R1eT, *R2e, *R2r;
     int rtf() const { return cfg.precise ? 0 : 1; }   // TF32 storage discipline of the tcgen05 fast mode
     // effective-weight gradient accumulators (zeroed by hsb_prepare)
     float *dW0e, *dW1e, *dW2e, *dB2e, *dR0e, *dR1e, *dR2e, *dRB2e;
@@ -83,6 +84,7 @@ struct Ctx {
     Slot scratch;   // X, H0, H1, H2, SR only: hsb_sdf_values between a slot's forward and its backward
     long long block_tiles = 0;   // L2 blocking of the ray passes: 128-row tiles per block of rays (0 = one block)
     bool dual_bwd = true;        // fast mode: chain + SDF-net backward through the dual-accumulator layer kernel (csrc/dual_tc.cu)
+    bool fused_fwd = true;       // fast mode: scene-pass forward through the fused trunk kernels (csrc/render_tc.cu)
     float* P(int seg) const { return params + off[seg]; }
     float* Gp(int seg) const { return grads + off[seg]; }
 };
@@ -121,6 +123,7 @@ static void carve_slot(Ctx* c, int idx, const char* pre, long long points, int m
         s.W = carve(c, nm("W"), N, 1, dry);    s.T = carve(c, nm("T"), N, 1, dry);        s.ZV = carve(c, nm("ZV"), N, 1, dry);
         s.WSUM = carve(c, nm("WSUM"), rays, 1, dry); s.WZSUM = carve(c, nm("WZSUM"), rays, 1, dry);
         s.DSCALE = carve(c, nm("DSCALE"), rays, 1, dry); s.ROT = carve(c, nm("ROT"), 16, 1, dry);
+        s.SDFB = carve(c, nm("SDFB"), N, 1, dry);  s.WB = carve(c, nm("WB"), N, 1, dry);
     }
     if (color) {
         s.EC = carve(c, nm("EC"), N, 32, dry);     s.C1 = carve(c, nm("C1"), N, 256, dry);   s.RIN = carve(c, nm("RIN"), N, LD_RIN, dry);
@@ -150,6 +153,7 @@ static void carve_all(Ctx* c, bool dry) {
     c->R0e = carve(c, "R0e", 256, LD_RIN, dry);  c->R0eT = carve(c, "R0eT", LD_RIN, 256, dry);
     c->R1e = carve(c, "R1e", 256, 256, dry);     c->R1eT = carve(c, "R1eT", 256, 256, dry);
     c->R2e = carve(c, "R2e", 4, 256, dry);
+    c->R2r = carve(c, "R2r", 16, 256, dry);      // TF32-rounded, zero-padded to one MMA N tile (fused render trunk)
     size_t begin = c->ws_used;
     c->dW0e = carve(c, "dW0e", 256, LD_H0, dry); c->dW1e = carve(c, "dW1e", 256, 256, dry);
     c->dW2e = carve(c, "dW2e", Kp, 256, dry);    c->dB2e = carve(c, "dB2e", Kp, 1, dry);
@@ -185,7 +189,7 @@ static Slot slot_block(const Slot& s, long long p0, long long r0, int Kp) {
     if (b.KS) b.KS += p0;
     adv(b.P2, 256); adv(b.P1, 256); adv(b.Q0, LD_H0); adv(b.G, 3);
     adv(b.EC, 32); adv(b.C1, 256); adv(b.RIN, LD_RIN); adv(b.U1, 256); adv(b.U2, 256); adv(b.RGB, 4);
-    adv(b.W, 1); adv(b.T, 1); adv(b.ZV, 1);
+    adv(b.W, 1); adv(b.T, 1); adv(b.ZV, 1); adv(b.SDFB, 1); adv(b.WB, 1);
     if (b.WSUM) b.WSUM += r0;
     if (b.WZSUM) b.WZSUM += r0;
     if (b.DSCALE) b.DSCALE += r0;
@@ -363,20 +367,33 @@ static CompositeArgs composite_args(Ctx* c, Slot& s, int mode) {
 }
 
 // per-point part of the ray pass forward on one block of rays
-static int render_forward_block(Ctx* c, Slot& s, bool scene, const float* o, const float* d, const float* z, cudaStream_t st) {
+static int render_forward_block(Ctx* c, Slot& s, bool scene, const float* o, const float* d, const float* z, cudaStream_t st,
+                                unsigned long long mask = ~0ull) {
     const hsb_step_cfg& f = c->cfg;
     const int P = f.precise;
     const int rt = c->rtf();
     const long long N = s.N;
     TRY(launch_ray_points(o, d, z, s.R, s.S, s.X, s.H0, scene ? s.RIN : nullptr, rt, st));
-    TRY(sdf_forward(c, s, N, true, st));
-    TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, -1, s.SDF, s.KS, st));
-    TRY(chain_forward(c, s, N, 1, st));
+    if (P == 0 && c->fused_fwd && sdf_chain_tc_eligible(c->K)) {
+        // hash gather, then ONE kernel for the three SDF layers, the min over objects and the reverse chain down to d sdf / d h0
+        // (csrc/sdfchain_tc.cu); the hidden activations the backward needs are written once and never re-read here
+        TRY(hash_forward_ex(s.X, c->P(SEG_EMB), c->hoffs, s.H0 + 39, 2, LD_H0, s.DY, 96, (uint32_t)N, f.L, f.S, f.H, 1, rt, st));
+        TRY(sdf_chain_tc(s.H0, N, c->W0e, c->W1e, c->W2e, c->W1eT, c->W0eT, c->P(SEG_L0B), c->P(SEG_L1B), c->P(SEG_L2B), c->K, c->Kp,
+                         s.H1, s.H2, s.SR, s.SDF, s.KS, s.P2, s.P1, s.Q0, st, mask));
+        TRY(launch_chain_end(s.Q0, s.H0, s.DY, N, 1, s.G, s.with_color ? s.RIN : nullptr, rt, st));
+    } else {
+        TRY(sdf_forward(c, s, N, true, st));
+        TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, -1, s.SDF, s.KS, st, mask));
+        TRY(chain_forward(c, s, N, 1, st));
+    }
     if (scene) {
         TRY(hash_forward_ex(s.X, c->P(SEG_CEMB), c->hoffs, s.EC, 2, 32, nullptr, 0, (uint32_t)N, f.L, f.S, f.H, 1, rt, st));
+        if (P == 0 && c->fused_fwd && render_trunk_tc_eligible())       // colour MLP + render net + sigmoid in ONE kernel (csrc/render_tc.cu)
+            return render_trunk_tc(s.EC, s.RIN, N, c->C0e, c->C1e, c->R0e, c->R1e, c->R2r, c->P(SEG_C0B), c->P(SEG_C1B), c->P(SEG_R0B),
+                                   c->P(SEG_R1B), c->P(SEG_R2B), s.C1, s.U1, s.U2, s.RGB, st);
         Epi e = epi(EPI_BIAS_RELU, s.C1, 256, rt); e.bias = c->P(SEG_C0B);
         TRY(gemm_tn(s.EC, 32, c->C0e, 32, N, 256, 32, e, P, st));
-        e = epi(EPI_BIAS, s.RIN + 81, LD_RIN, rt); e.bias = c->P(SEG_C1B);
+        e = epi(EPI_BIAS, s.RIN, LD_RIN, rt); e.bias = c->P(SEG_C1B);       // colour feature = columns [0,256) of the render-net input row
         TRY(gemm_tn(s.C1, 256, c->C1e, 256, N, 256, 256, e, P, st));
         e = epi(EPI_BIAS_RELU, s.U1, 256, rt); e.bias = c->P(SEG_R0B);
         TRY(gemm_tn(s.RIN, LD_RIN, c->R0e, LD_RIN, N, 256, LD_RIN, e, P, st));
@@ -403,10 +420,10 @@ static int render_backward_block(Ctx* c, Slot& s, bool scene, cudaStream_t st) {
         Epi e = epi(EPI_BWD_RELU, s.dU1, 256, rt); e.aux = s.U1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_R0B) : nullptr;
         TRY(gemm_tn(s.dU2, 256, c->R1eT, 256, N, 256, 256, e, P, st));
         TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, fold ? nullptr : c->Gp(SEG_R1B), P, st));
-        e = epi(EPI_NONE, s.dRIN + 54, LD_RIN);
-        TRY(gemm_tn(s.dU1, 256, c->R0eT + 54 * 256, 256, N, 27, 256, e, P, st));     // d PE4(grad)
+        e = epi(EPI_NONE, s.dRIN + RIN_PEG, LD_RIN);
+        TRY(gemm_tn(s.dU1, 256, c->R0eT + RIN_PEG * 256, 256, N, 27, 256, e, P, st)); // d PE4(grad)
         e = epi(EPI_NONE, s.dFEAT, 256, rt); e.colsum = fold ? c->Gp(SEG_C1B) : nullptr;
-        TRY(gemm_tn(s.dU1, 256, c->R0eT + 81 * 256, 256, N, 256, 256, e, P, st));    // d feature
+        TRY(gemm_tn(s.dU1, 256, c->R0eT, 256, N, 256, 256, e, P, st));               // d feature (effective columns [0,256))
         TRY(gemm_wgrad(s.dU1, 256, 256, s.RIN, LD_RIN, LD_RIN, N, c->dR0e, LD_RIN, fold ? nullptr : c->Gp(SEG_R0B), P, st));
         // colour-feature MLP + colour hash grid
         TRY(gemm_wgrad(s.dFEAT, 256, 256, s.C1, 256, 256, N, c->Gp(SEG_C1W), 256, fold ? nullptr : c->Gp(SEG_C1B), P, st));
@@ -476,6 +493,8 @@ extern "C" int hsb_ctx_create(const hsb_step_cfg* cfg, float* params, float* gra
     c->block_tiles = bt ? atoll(bt) : 0;                        // off by default: see the note at slot_block
     const char* du = getenv("HSB_DUAL_BWD");
     c->dual_bwd = du ? atoi(du) != 0 : true;
+    const char* ff = getenv("HSB_FUSED_FWD");
+    c->fused_fwd = ff ? atoi(ff) != 0 : true;
     *out = reinterpret_cast<hsb_ctx*>(c);
     return HSB_OK;
 }
@@ -487,6 +506,7 @@ extern "C" int hsb_ctx_set_option(hsb_ctx* h, const char* name, int64_t value) {
     CTX_OR_FAIL(c, "hsb_ctx_set_option");
     if (c && name && !strcmp(name, "block_tiles") && value >= 0) { c->block_tiles = value; return HSB_OK; }
     if (c && name && !strcmp(name, "dual_bwd")) { c->dual_bwd = value != 0; return HSB_OK; }
+    if (c && name && !strcmp(name, "fused_fwd")) { c->fused_fwd = value != 0; return HSB_OK; }
     set_error("hsb_ctx_set_option: unknown option or bad value");
     return HSB_ERR_ARG;
 }
@@ -514,9 +534,13 @@ extern "C" int hsb_prepare(hsb_ctx* h, cudaStream_t st) {
     TRY(launch_wn_forward(c->P(SEG_L0V), c->P(SEG_L0G), 256, 71, c->W0e, LD_H0, c->W0eT, 256, rt, st));
     TRY(launch_wn_forward(c->P(SEG_L1V), c->P(SEG_L1G), 256, 256, c->W1e, 256, c->W1eT, 256, rt, st));
     TRY(launch_wn_forward(c->P(SEG_L2V), c->P(SEG_L2G), c->K, 256, c->W2e, 256, c->W2eT, c->Kp, rt, st));
-    TRY(launch_wn_forward(c->P(SEG_R0V), c->P(SEG_R0G), 256, 337, c->R0e, LD_RIN, c->R0eT, 256, rt, st));
+    TRY(launch_wn_forward(c->P(SEG_R0V), c->P(SEG_R0G), 256, 337, c->R0e, LD_RIN, c->R0eT, 256, rt, st, R0_ROT));
     TRY(launch_wn_forward(c->P(SEG_R1V), c->P(SEG_R1G), 256, 256, c->R1e, 256, c->R1eT, 256, rt, st));
     TRY(launch_wn_forward(c->P(SEG_R2V), c->P(SEG_R2G), 3, 256, c->R2e, 256, nullptr, 0, 0, st));
+    if (rt) {
+        TRYCUDA(cudaMemsetAsync(c->R2r, 0, (size_t)16 * 256 * sizeof(float), st));
+        TRY(launch_wn_forward(c->P(SEG_R2V), c->P(SEG_R2G), 3, 256, c->R2r, 256, nullptr, 0, 1, st));
+    }
     TRY(launch_transpose(c->P(SEG_C0W), 256, 32, c->C0T, 256, c->C0e, rt, st));
     TRY(launch_transpose(c->P(SEG_C1W), 256, 256, c->C1T, 256, c->C1e, rt, st));
     return HSB_OK;
@@ -529,7 +553,7 @@ extern "C" int hsb_finish(hsb_ctx* h, cudaStream_t st) {
     TRY(launch_wn_backward(c->dW0e, LD_H0, c->P(SEG_L0V), c->P(SEG_L0G), 256, 71, c->Gp(SEG_L0V), c->Gp(SEG_L0G), st));
     TRY(launch_wn_backward(c->dW1e, 256, c->P(SEG_L1V), c->P(SEG_L1G), 256, 256, c->Gp(SEG_L1V), c->Gp(SEG_L1G), st));
     TRY(launch_wn_backward(c->dW2e, 256, c->P(SEG_L2V), c->P(SEG_L2G), c->K, 256, c->Gp(SEG_L2V), c->Gp(SEG_L2G), st));
-    TRY(launch_wn_backward(c->dR0e, LD_RIN, c->P(SEG_R0V), c->P(SEG_R0G), 256, 337, c->Gp(SEG_R0V), c->Gp(SEG_R0G), st));
+    TRY(launch_wn_backward(c->dR0e, LD_RIN, c->P(SEG_R0V), c->P(SEG_R0G), 256, 337, c->Gp(SEG_R0V), c->Gp(SEG_R0G), st, R0_ROT));
     TRY(launch_wn_backward(c->dR1e, 256, c->P(SEG_R1V), c->P(SEG_R1G), 256, 256, c->Gp(SEG_R1V), c->Gp(SEG_R1G), st));
     TRY(launch_wn_backward(c->dR2e, 256, c->P(SEG_R2V), c->P(SEG_R2G), 3, 256, c->Gp(SEG_R2V), c->Gp(SEG_R2G), st));
     // padded bias accumulators -> exact-size bias gradients
@@ -553,10 +577,25 @@ extern "C" int hsb_eik_points(const float* uniform, const float* o, const float*
 // SDF values (min over K, or one channel) at the points o + z d of a ray batch -- the sampler's no-grad queries
 // (model/ray_sampler.py:150-156).  Runs in its own scratch buffers ("samp.*"): the background-patch sampler is
 // called between the main pass forward and its backward and must not touch the saved activations.
+static int sdf_values_impl(Ctx* c, const float* o, const float* d, const float* z, int32_t R, int32_t S, int32_t channel,
+                           unsigned long long mask, float* sdf_out, cudaStream_t st);
 extern "C" int hsb_sdf_values(hsb_ctx* h, const float* o, const float* d, const float* z, int32_t R, int32_t S, int32_t channel,
                               float* sdf_out, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     CTX_OR_FAIL(c, "hsb_sdf_values");
+    return sdf_values_impl(c, o, d, z, R, S, channel, ~0ull, sdf_out, st);
+}
+// Stage-2 object subsets (model/network.py:320-326 get_multi_object_sdf_vals): min over the channels of `mask`
+extern "C" int hsb_sdf_values_subset(hsb_ctx* h, const float* o, const float* d, const float* z, int32_t R, int32_t S, uint64_t mask,
+                                     float* sdf_out, cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_sdf_values_subset");
+    if (c->K < 64 && (mask >> c->K)) { set_error("hsb_sdf_values_subset: mask names a channel >= K"); return HSB_ERR_ARG; }
+    if (!mask) { set_error("hsb_sdf_values_subset: empty channel mask"); return HSB_ERR_ARG; }
+    return sdf_values_impl(c, o, d, z, R, S, -1, mask, sdf_out, st);
+}
+static int sdf_values_impl(Ctx* c, const float* o, const float* d, const float* z, int32_t R, int32_t S, int32_t channel,
+                           unsigned long long mask, float* sdf_out, cudaStream_t st) {
     Slot& s = c->scratch;
     const long long N = (long long)R * S;
     if (N > s.cap_points || channel >= c->K) { set_error("hsb_sdf_values: batch exceeds max_points / bad channel"); return HSB_ERR_ARG; }
@@ -566,10 +605,10 @@ extern "C" int hsb_sdf_values(hsb_ctx* h, const float* o, const float* d, const 
         const hsb_step_cfg& f = c->cfg;
         TRY(hash_forward_ex(s.X, c->P(SEG_EMB), c->hoffs, s.H0 + 39, 2, LD_H0, nullptr, 96, (uint32_t)N, f.L, f.S, f.H, 1, 1, st));
         return sdf_trunk_tc(s.H0, N, c->W0e, c->W1e, c->W2e, c->P(SEG_L0B), c->P(SEG_L1B), c->P(SEG_L2B), c->K, c->Kp, channel, sdf_out,
-                            s.SR, st);
+                            s.SR, st, mask);
     }
     TRY(sdf_forward(c, s, N, false, st));
-    TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, channel, sdf_out, nullptr, st));
+    TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, channel, sdf_out, nullptr, st, mask));
     return HSB_OK;
 }
 
@@ -600,6 +639,41 @@ extern "C" int hsb_render_forward(hsb_ctx* h, int32_t slot_id, const float* o, c
         a.semantic = semantic + (long long)r0 * c->K;
         TRY(launch_composite_fwd(a, st));
     }
+    return HSB_OK;
+}
+
+// Stage-2 consumer of the same operator (model/network.py:1235-1306 forward_multi_obj_rays_subset_all_sdf): the scene
+// pass with the min / arg-min / gradient taken over the SUBSET channels (mask_subset) and a second, "background" set of weights
+// from the min over the object channels (mask_obj) that composites colour, depth and normals.  Forward only: the MAIN slot's
+// recorded forward is invalidated (hsb_render_backward refuses until the next hsb_render_forward).
+extern "C" int hsb_render_forward_subset(hsb_ctx* h, const float* o, const float* d, const float* z, int32_t R, int32_t S,
+                                         const float* depth_scale, const float* rot, uint64_t mask_subset, uint64_t mask_obj,
+                                         float* rgb_values, float* depth_values, float* normal_map, float* opacity, float* semantic,
+                                         cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_render_forward_subset");
+    Slot& s = c->slot[HSB_SLOT_MAIN];
+    const long long N = (long long)R * S;
+    if (N > s.cap_points || R > s.cap_rays) { set_error("hsb_render_forward_subset: batch exceeds slot capacity"); return HSB_ERR_ARG; }
+    if (!mask_subset || !mask_obj || (c->K < 64 && ((mask_subset | mask_obj) >> c->K))) {
+        set_error("hsb_render_forward_subset: empty channel mask or channel >= K");
+        return HSB_ERR_ARG;
+    }
+    if (!rgb_values || !depth_values || !normal_map || !opacity || !semantic || !o || !d || !z || !depth_scale || !rot) {
+        set_error("hsb_render_forward_subset: null pointer");
+        return HSB_ERR_ARG;
+    }
+    s.N = N; s.R = R; s.S = S; s.nseed = 1; s.mode = 2;
+    TRYCUDA(cudaMemcpyAsync(s.ZV, z, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRYCUDA(cudaMemcpyAsync(s.DSCALE, depth_scale, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRYCUDA(cudaMemcpyAsync(s.ROT, rot, 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRY(render_forward_block(c, s, true, o, d, z, st, mask_subset));
+    TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, -1, s.SDFB, nullptr, st, mask_obj));
+    CompositeArgs a = composite_args(c, s, 2);
+    a.SDFB = s.SDFB; a.WB = s.WB; a.mask = mask_subset;
+    a.rgb_values = rgb_values; a.depth_values = depth_values; a.normal_map = normal_map; a.opacity = opacity; a.semantic = semantic;
+    TRY(launch_composite_fwd(a, st));
+    s.N = 0;                                        // forward only
     return HSB_OK;
 }
 

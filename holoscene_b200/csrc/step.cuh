@@ -8,7 +8,14 @@
 namespace hsb {
 
 constexpr int LD_H0 = 72;    // SDF-net input row: PE6(x) [0,39) | hash features [39,71) | pad
-constexpr int LD_RIN = 344;  // render-net input row: PE4(x) [0,27) | PE4(view) [27,54) | PE4(grad) [54,81) | feature [81,337) | pad
+// render-net input row: feature [0,256) | PE4(x) [256,283) | PE4(view) [283,310) | PE4(grad) [310,337) | pad.  The reference
+// concatenates [PE4(x), PE4(view), PE4(grad), feature] (model/network.py:596-603); here the 256-wide feature block comes FIRST so that
+// the colour-MLP epilogue writes it 16-byte aligned (and a fused kernel can keep it as k-blocks 0..7 of the next contraction); the
+// effective lin0 weight is stored with its columns rotated accordingly (R0_ROT, see wn_forward / wn_backward).
+constexpr int LD_RIN = 344;
+constexpr int RIN_PE = 256;     // first PE column
+constexpr int RIN_PEG = 310;    // first column of PE4(grad)
+constexpr int R0_ROT = 256;     // effective column of reference column k of rendering_network.lin0: (k + R0_ROT) % 337
 constexpr int HID = 256;
 
 struct CompositeArgs {
@@ -26,6 +33,10 @@ struct CompositeArgs {
     float* W; float* T;    // [P]
     float* rgb_values; float* depth_values; float* normal_map; float* opacity; float* semantic;
     float* wsum; float* wzsum;   // [R]
+    // mode 2 (Stage-2 object subsets, forward only): SDF = min over the subset channels `mask` (weights / opacity / semantics),
+    // SDFB = min over the object channels (bg_weights: colour / depth / normal composites); WB [P] receives bg_weights,
+    // opacity [R] one value per ray, semantic [R, popcount(mask)] in ascending channel order
+    const float* SDFB; float* WB; unsigned long long mask;
 };
 struct CompositeGrads {
     const float* d_rgb_values; const float* d_depth_values; const float* d_normal_map; const float* d_opacity;
@@ -35,7 +46,7 @@ struct CompositeGrads {
 
 int launch_ray_points(const float* o, const float* d, const float* z, int R, int S, float* X, float* H0, float* RIN, int rtf, cudaStream_t st);
 int launch_points_pe(const float* X, long long N, float* H0, int rtf, cudaStream_t st);
-int launch_sdf_min(const float* SR, long long N, int K, int Kp, int channel, float* sdf, int* kstar, cudaStream_t st);
+int launch_sdf_min(const float* SR, long long N, int K, int Kp, int channel, float* sdf, int* kstar, cudaStream_t st, unsigned long long mask = ~0ull);
 int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long long N, int K, int nseed, float* P2, int rtf, cudaStream_t st);
 int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN, int rtf, cudaStream_t st);
 int launch_chain_end_bwd(float* dG, const float* dRIN, const float* RIN, const float* H0, const float* DY, long long N, int nseed, float* dQ0, int rtf, cudaStream_t st);
@@ -57,15 +68,27 @@ int launch_composite_bwd(const CompositeArgs& a, const CompositeGrads& g, cudaSt
 // trunk_tc.cu: fused no-grad SDF trunk (three layers + min over objects in one tcgen05 kernel, activations in tensor memory)
 bool sdf_trunk_tc_eligible(int K);
 int sdf_trunk_tc(const float* H0, long long N, const float* W0e, const float* W1e, const float* W2e, const float* b0, const float* b1,
-                 const float* b2, int K, int Kp, int channel, float* sdf, float* sr, cudaStream_t stream);
+                 const float* b2, int K, int Kp, int channel, float* sdf, float* sr, cudaStream_t stream, unsigned long long mask = ~0ull);
 
 // optim.cu
-int launch_wn_forward(const float* v, const float* g, int rows, int cols, float* We, int ldw, float* WeT, int ldt, int rtf, cudaStream_t st);
-int launch_wn_backward(const float* dWe, int ldw, const float* v, const float* g, int rows, int cols, float* dv, float* dg, cudaStream_t st);
+int launch_wn_forward(const float* v, const float* g, int rows, int cols, float* We, int ldw, float* WeT, int ldt, int rtf, cudaStream_t st, int rot = 0);
+int launch_wn_backward(const float* dWe, int ldw, const float* v, const float* g, int rows, int cols, float* dv, float* dg, cudaStream_t st, int rot = 0);
 int launch_add_into(const float* src, float* dst, int n, cudaStream_t st);
 int launch_transpose(const float* W, int rows, int cols, float* WT, int ldt, float* Wcopy, int rtf, cudaStream_t st);
 int hash_forward_ex(const float* x, const float* emb, const int32_t* offs, float* out, long long ls, long long ps, float* dy, long long dps,
                     uint32_t B, uint32_t L, float S, uint32_t H, int map01, int rtf, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float* gnorm2, float gscale, cudaStream_t st);
+
+// render_tc.cu: fused colour + render trunk of the scene pass forward (fast mode)
+bool render_trunk_tc_eligible();
+int render_trunk_tc(const float* EC, float* RIN, long long N, const float* C0e, const float* C1e, const float* R0e, const float* R1e,
+                    const float* R2r, const float* c0b, const float* c1b, const float* r0b, const float* r1b, const float* r2b, float* C1,
+                    float* U1, float* U2, float* RGB, cudaStream_t stream);
+
+// sdfchain_tc.cu: fused SDF trunk + d sdf / d x chain of the scene pass forward (fast mode)
+bool sdf_chain_tc_eligible(int K);
+int sdf_chain_tc(const float* H0, long long N, const float* W0e, const float* W1e, const float* W2e, const float* W1eT, const float* W0eT,
+                 const float* b0, const float* b1, const float* b2, int K, int Kp, float* H1, float* H2, float* SR, float* SDF, int* KS,
+                 float* P2, float* P1, float* Q0, cudaStream_t stream, unsigned long long mask = ~0ull);
 
 }  // namespace hsb

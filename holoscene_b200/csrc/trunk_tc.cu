@@ -35,6 +35,7 @@ struct TrunkArgs {
     long long N;            // points
     int K, Kp, n2;          // object channels, padded row width of SR, MMA N of the last layer (Kp rounded up to 16)
     int channel;            // >= 0: return that channel instead of the min
+    unsigned long long mask; // channels the min runs over (bit k = channel k); all ones = every channel
     const float *b0, *b1, *b2;
     float* sdf;             // [N] (may be null)
     float* sr;              // [N, Kp] raw per-object values (may be null)
@@ -199,6 +200,7 @@ sdf_trunk_tc_kernel(const __grid_constant__ CUtensorMap mapH0, const __grid_cons
                 const long long row = (long long)tile * TC_BM + q * 32 + lane;
                 float best = 3.0e38f;
                 float pick = 0.0f;
+                bool have = false;
                 const int nchunk = (a.Kp + 31) / 32;
                 for (int c = 0; c < nchunk; ++c) {
                     float v[32];
@@ -208,7 +210,7 @@ sdf_trunk_tc_kernel(const __grid_constant__ CUtensorMap mapH0, const __grid_cons
                         v[i] += sbias[512 + c * 32 + i];
                         const int k = c * 32 + i;
                         if (k < a.K) {
-                            if (v[i] < best || k == 0) best = v[i];      // == -maxpool(-s): first index wins ties
+                            if (((a.mask >> k) & 1ull) && (v[i] < best || !have)) { best = v[i]; have = true; }   // == -maxpool(-s): first index wins ties
                             if (k == a.channel) pick = v[i];
                         }
                     }
@@ -246,7 +248,7 @@ bool sdf_trunk_tc_eligible(int K) {
 
 // H0 [N, LD_H0] (PE | hash features, TF32-rounded), W0e [256, LD_H0], W1e [256, 256], W2e [Kp, 256] (effective weights, rows >= K zero)
 int sdf_trunk_tc(const float* H0, long long N, const float* W0e, const float* W1e, const float* W2e, const float* b0, const float* b1,
-                 const float* b2, int K, int Kp, int channel, float* sdf, float* sr, cudaStream_t stream) {
+                 const float* b2, int K, int Kp, int channel, float* sdf, float* sr, cudaStream_t stream, unsigned long long mask) {
     if (N <= 0) return HSB_OK;
     if (N > 0x7fffffffLL - TC_BM) { set_error("sdf_trunk: batch too large"); return HSB_ERR_ARG; }
     const int n2 = (Kp + 15) / 16 * 16;
@@ -261,7 +263,7 @@ int sdf_trunk_tc(const float* H0, long long N, const float* W0e, const float* W1
     const uint32_t idesc256 = common | ((uint32_t)(256 >> 3) << 17);
     const uint32_t idesc2 = common | ((uint32_t)(n2 >> 3) << 17);
     TrunkArgs a{};
-    a.N = N; a.K = K; a.Kp = Kp; a.n2 = n2; a.channel = channel; a.b0 = b0; a.b1 = b1; a.b2 = b2; a.sdf = sdf; a.sr = sr;
+    a.N = N; a.K = K; a.Kp = Kp; a.n2 = n2; a.channel = channel; a.mask = mask; a.b0 = b0; a.b1 = b1; a.b2 = b2; a.sdf = sdf; a.sr = sr;
     a.num_tiles = (int)((N + TC_BM - 1) / TC_BM);
     const unsigned grid = (unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms());
     sdf_trunk_tc_kernel<<<grid, TR_THREADS, TR_SMEM_BYTES, stream>>>(mH0, mW0, mW1, mW2, a, idesc256, idesc2);

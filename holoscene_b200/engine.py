@@ -50,6 +50,9 @@ _finish = declare("hsb_finish", [_vp, c_stream])
 _sdf_values = declare("hsb_sdf_values", [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, c_stream])
 _render_fwd = declare("hsb_render_forward", [_vp, ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp,
                                              _vp, _vp, _vp, _vp, _vp, c_stream])
+_sdf_values_subset = declare("hsb_sdf_values_subset", [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, _vp, c_stream])
+_render_fwd_subset = declare("hsb_render_forward_subset", [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp, ctypes.c_uint64,
+                                                           ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, c_stream])
 _render_bwd = declare("hsb_render_backward", [_vp, ctypes.c_int32, _vp, _vp, _vp, _vp, c_stream])
 _eik_fwd = declare("hsb_eikonal_forward", [_vp, _vp, ctypes.c_int64, _vp, _vp, _vp, c_stream])
 _eik_bwd = declare("hsb_eikonal_backward", [_vp, _vp, _vp, c_stream])
@@ -123,6 +126,19 @@ def eik_points(uniform, o, d, z_eik, noise):
     check(_eik_points(ptr(uniform.contiguous()), ptr(o), ptr(d), ptr(z_eik.reshape(n).contiguous()), ptr(noise.contiguous()), n,
                       ptr(out), stream()))
     return out
+
+
+def channel_mask(idxs, K: int) -> int:
+    """Bit mask of a set of object channels (bit k = channel k), as the *_subset entry points take it."""
+    m = 0
+    for k in idxs:
+        k = int(k)
+        if not 0 <= k < K:
+            raise _lib.HsbError(f"object channel {k} outside [0, {K})")
+        m |= 1 << k
+    if m == 0:
+        raise _lib.HsbError("empty object-channel set")
+    return m
 
 
 def param_layout(K: int, table_rows: int) -> list[int]:
@@ -204,11 +220,28 @@ class StepEngine:
     def finish(self):
         check(_finish(self._h, stream()))
 
-    def sdf_values(self, o, d, z, channel=-1):
+    def sdf_values(self, o, d, z, channel=-1, mask=None):
+        """No-grad SDF at o + z d: min over all channels (channel < 0), one channel, or -- mask = iterable of channel ids -- the min
+        over an object subset (hsb_sdf_values_subset)."""
         R, S = z.shape
         out = torch.empty(R, S, device=z.device)
-        check(_sdf_values(self._h, ptr(o), ptr(d), ptr(z), R, S, int(channel), ptr(out), stream()))
+        if mask is not None:
+            check(_sdf_values_subset(self._h, ptr(o), ptr(d), ptr(z), R, S, channel_mask(mask, self.K), ptr(out), stream()))
+        else:
+            check(_sdf_values(self._h, ptr(o), ptr(d), ptr(z), R, S, int(channel), ptr(out), stream()))
         return out
+
+    def render_forward_subset(self, o, d, z, depth_scale, rot, subset_idxs, obj_idxs):
+        """hsb_render_forward_subset: (rgb_values [R,3], depth_values [R,1], normal_map [R,3], opacity [R,1], semantic [R,n_subset])."""
+        R, S = z.shape
+        dev = z.device
+        msub, mobj = channel_mask(subset_idxs, self.K), channel_mask(obj_idxs, self.K)
+        rgbv, depth, nmap = torch.empty(R, 3, device=dev), torch.empty(R, 1, device=dev), torch.empty(R, 3, device=dev)
+        opac = torch.empty(R, 1, device=dev)
+        sem = torch.empty(R, bin(msub).count("1"), device=dev)
+        check(_render_fwd_subset(self._h, ptr(o), ptr(d), ptr(z), R, S, ptr(depth_scale), ptr(rot), msub, mobj, ptr(rgbv), ptr(depth),
+                                 ptr(nmap), ptr(opac), ptr(sem), stream()))
+        return rgbv, depth, nmap, opac, sem
 
     def render_forward(self, slot, o, d, z, depth_scale, rot):
         R, S = z.shape

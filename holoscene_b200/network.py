@@ -364,8 +364,11 @@ class HoloSceneNetwork(nn.Module):
                     ssdf if ssdf is not None else torch.empty(0, device=dev),
                     bg[0] if bg is not None else torch.empty(0, device=dev),
                     bg[1] if bg is not None else torch.empty(0, device=dev)]
-            rgbv, depth, nmap, opac, gt_, ssdf_, bgd, bgn = _StepFn.apply(self.density.beta, self, outs, gt is not None,
-                                                                          bg is not None)
+            # The anchor only makes the outputs require grad (the backward accumulates into the flat gradient buffer itself).  It is a
+            # fresh leaf per forward: a Parameter's gradient accumulator node remembers the stream it was created on, and one kept
+            # alive by an earlier step's outputs would tie a CUDA-graph capture of this step to the default stream.
+            anchor = torch.empty(0, device=dev, requires_grad=True)
+            rgbv, depth, nmap, opac, gt_, ssdf_, bgd, bgn = _StepFn.apply(anchor, self, outs, gt is not None, bg is not None)
             if gt is not None:
                 gt, ssdf = gt_, ssdf_
             if bg is not None:
@@ -379,6 +382,62 @@ class HoloSceneNetwork(nn.Module):
         if bg is not None:
             output["bg_depth_values"], output["bg_normal_map"] = bg
         return output
+
+    # ---- Stage-2 consumers of the same operator --------------------------------------------------------------
+    @torch.no_grad()
+    def forward_multi_obj_rays_subset_all_sdf(self, ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs, iter_step=-1,
+                                              near_far=None):
+        """Reference model/network.py:1235-1306: render explicit rays with the scene restricted to an object subset.  The sampler
+        and the `bg_weights` (colour / depth / normal composites) use the min over `obj_idxs`, the sdf / gradient / `weights` /
+        semantics / opacity the min over `subset_obj_idxs`.  Same output keys as the reference.  Forward only in this
+        implementation (the reference's version is differentiable; Stage 2 calls it for visibility / rendering queries)."""
+        dev = self.density.beta.device
+        o = ray_origins.reshape(-1, 3).to(dev, torch.float32).contiguous()
+        d = torch.nn.functional.normalize(ray_dirs.reshape(-1, 3).to(dev, torch.float32), dim=-1).contiguous()
+        rot = pose.to(dev)[..., :3, :3].reshape(3, 3).permute(1, 0).contiguous()
+        depth_scale = (rot @ d.permute(1, 0)).permute(1, 0)[:, 2:].contiguous()
+        eng = self.engine()
+        if o.shape[0] > eng.max_rays:
+            raise RuntimeError(f"{o.shape[0]} rays exceed hsb_max_rays={eng.max_rays} (set model.hsb_max_rays in the conf)")
+        eng.prepare()
+        draws = self.draws if self.draws is not None else LiveDraws(dev)
+        self.draws = draws
+        try:
+            obj, sub = [int(k) for k in obj_idxs], [int(k) for k in subset_obj_idxs]
+            z_vals, _ = self.ray_sampler.get_z_vals(d, o, self, idx=obj, near_far=near_far)
+            z_vals = z_vals.contiguous()
+            R, S = z_vals.shape
+            rgbv, depth, nmap, opac, sem = eng.render_forward_subset(o, d, z_vals, depth_scale, rot, sub, obj)
+            P = R * S
+            if len(set(sub)) != len(sub) or sorted(sub) != sub:
+                # the kernel packs the subset's semantics in ascending channel order; restore the caller's order / duplicates
+                order = sorted(set(sub))
+                sem = sem[:, [order.index(k) for k in sub]]
+            return {"rgb": eng.buffer("main.RGB")[:P].view(R, S, 4)[..., :3].clone(), "semantic_values": sem, "opacity": opac,
+                    "rgb_values": rgbv, "depth_values": depth, "z_vals": z_vals, "depth_vals": z_vals * depth_scale,
+                    "sdf": eng.buffer("main.SDF")[:P].view(R, S).clone(), "weights": eng.buffer("main.W")[:P].view(R, S).clone(),
+                    "bg_weights": eng.buffer("main.WB")[:P].view(R, S).clone(), "normal_map": nmap,
+                    **({"_depth_scale": depth_scale} if near_far is not None else {})}
+        finally:
+            if isinstance(draws, LiveDraws):
+                self.draws = None
+
+    def forward_multi_obj_rays_subset_all_sdf_near_far(self, ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs, near, far,
+                                                       iter_step=-1):
+        """Reference model/network.py:1307-1383: the same with the sampler started on an explicit [near, far] interval
+        (ray_sampler.get_z_vals_near_far).  This variant differs from the other in two outputs, reproduced: the depth is NOT
+        normalised by the accumulated weight (depth_scale * sum bg_w z, :1347) and `opacity` is the accumulated bg_weights, shape [R]
+        (:1353)."""
+        out = self.forward_multi_obj_rays_subset_all_sdf(ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs, iter_step,
+                                                         near_far=(float(near), float(far)))
+        eng = self.engine()
+        R = out["z_vals"].shape[0]
+        wsum = eng.buffer("main.WSUM")[:R].clone()
+        wzsum = eng.buffer("main.WZSUM")[:R].clone()
+        out["opacity"] = wsum.reshape(-1)
+        out["depth_values"] = out["_depth_scale"] * wzsum
+        del out["_depth_scale"]
+        return out
 
     def get_parameters(self):
         return list(self.parameters())

@@ -39,7 +39,12 @@ class ErrorBoundSampler:
         self.spec_hits = self.spec_misses = 0
 
     @torch.no_grad()
-    def get_z_vals(self, ray_dirs, cam_loc, model, idx=None, speculate=False):
+    def get_z_vals_near_far(self, ray_dirs, cam_loc, model, near, far, idx=None):
+        """Reference model/ray_sampler.py:290-447 (+ UniformSampler.get_z_vals_near_far, :85-104): the same algorithm started from a
+        uniform sampling of the given [near, far] instead of the cube exit, with near / far themselves appended at the end."""
+        return self.get_z_vals(ray_dirs, cam_loc, model, idx=idx, near_far=(float(near), float(far)))
+
+    def get_z_vals(self, ray_dirs, cam_loc, model, idx=None, speculate=False, near_far=None):
         """Same contract as the reference (ray_sampler.py:130-287).  Every refinement round is: fused SDF query of the new
         samples (hsb_sdf_values) -> hsb_sampler_bound (merge, d*, beta bisection, global flag) -> the reference's global
         convergence test `beta.max() > beta0` (:204) -> hsb_sampler_resample.  No torch ops in between.
@@ -54,8 +59,13 @@ class ErrorBoundSampler:
         dev = ray_dirs.device
         R = ray_dirs.shape[0]
         eng = model.engine()
-        channel = -1 if idx is None else int(idx)
-        key = channel
+        # idx: None = scene (min over all K channels), int = that channel, list = min over that object subset (Stage 2:
+        # get_multi_object_sdf_vals, reference network.py:320-326)
+        subset = sorted({int(k) for k in idx}) if isinstance(idx, (list, tuple)) else None
+        channel = -1 if (idx is None or subset is not None) else int(idx)
+        key = channel if subset is None else ("subset",) + tuple(subset)
+        if near_far is not None:
+            key = (key, near_far)
         capture = speculate == "capture"          # under CUDA-graph capture: no events, the caller ships the flags to the host
         guess = self._rounds_guess.get(key) if speculate else None
         if capture and guess is None:
@@ -67,14 +77,17 @@ class ErrorBoundSampler:
         t_rand = model.draws.rand("t_rand", (R, Ne)).contiguous() if model.training else None
         samples = torch.empty(R, Ne, device=dev)
         beta = torch.empty(R, device=dev)
-        _lib.check(E.sampler_init(p(o), p(d), R, Ne, float(self.near), float(self.far), float(self.scene_bounding_sphere),
-                                  p(t_rand), float(self.eps), p(samples), p(beta), st()))
+        if near_far is None:
+            near, far, bound = float(self.near), float(self.far), float(self.scene_bounding_sphere)
+        else:
+            near, far, bound = near_far[0], near_far[1], 1.0e9     # no cube clipping: uniform in the given [near, far]
+        _lib.check(E.sampler_init(p(o), p(d), R, Ne, near, far, bound, p(t_rand), float(self.eps), p(samples), p(beta), st()))
         beta_param = model.density.beta
         flags = torch.zeros(max(self.max_total_iters, 1), dtype=torch.int32, device=dev)
         z_all = sdf_all = None
         n_old, total_iters, not_converge = 0, 0, True
         while not_converge and total_iters < self.max_total_iters:
-            s_new = eng.sdf_values(o, d, samples, channel)
+            s_new = eng.sdf_values(o, d, samples, channel, mask=subset)
             n_new = samples.shape[1]
             n = n_old + n_new
             z_out = torch.empty(R, n, device=dev)
@@ -121,8 +134,8 @@ class ErrorBoundSampler:
         eidx = model.draws.randint("eik_idx", S, (R,)).to(dev, torch.int32).contiguous()
         z_vals = torch.empty(R, S, device=dev)
         z_eik = torch.empty(R, 1, device=dev)
-        _lib.check(E.sampler_finalize(p(z_all), n, p(samples), self.N_samples, p(extra), self.N_samples_extra, float(self.near),
-                                      float(self.far), p(eidx), R, p(z_vals), p(z_eik), st()))
+        _lib.check(E.sampler_finalize(p(z_all), n, p(samples), self.N_samples, p(extra), self.N_samples_extra, near, far, p(eidx), R,
+                                      p(z_vals), p(z_eik), st()))
         return z_vals, z_eik
 
     def _pinned_flags(self):

@@ -187,6 +187,18 @@ int hsb_sampler_finalize(const float* z, int32_t n, const float* samples, int32_
 int hsb_render_forward(hsb_ctx* ctx, int32_t slot, const float* o, const float* d, const float* z, int32_t R, int32_t S,
                        const float* depth_scale, const float* rot, float* rgb_values, float* depth_values, float* normal_map,
                        float* opacity, float* semantic, hsb_stream_t stream);
+/* Stage-2 consumers of the same operator (model/network.py:1235-1383 forward_multi_obj_rays_subset_all_sdf[_near_far],
+ * model/network.py:320-326 get_multi_object_sdf_vals, model/ray_sampler.py:290-447): channel sets are bit masks (bit k = channel k).
+ *   hsb_sdf_values_subset:     no-grad min over the channels of `mask` at o + z d (the sampler's queries with idx = list);
+ *   hsb_render_forward_subset: scene pass whose sdf / arg-min / gradient run over mask_subset (`weights`, semantics of the subset
+ *       channels in ascending order -> semantic [R, popcount(mask_subset)], opacity [R] = sum of weights) while colour, depth and
+ *       normals are composited with `bg_weights` from the min over mask_obj.  Per-sample state: "main.SDF", "main.W" (weights),
+ *       "main.WB" (bg_weights), "main.RGB".  Forward only (no backward is recorded). */
+int hsb_sdf_values_subset(hsb_ctx* ctx, const float* o, const float* d, const float* z, int32_t R, int32_t S, uint64_t mask,
+                          float* sdf_out, hsb_stream_t stream);
+int hsb_render_forward_subset(hsb_ctx* ctx, const float* o, const float* d, const float* z, int32_t R, int32_t S,
+                              const float* depth_scale, const float* rot, uint64_t mask_subset, uint64_t mask_obj, float* rgb_values,
+                              float* depth_values, float* normal_map, float* opacity, float* semantic, hsb_stream_t stream);
 /* Ray pass backward from d(loss)/d(per-ray outputs) (NULL = zero). */
 int hsb_render_backward(hsb_ctx* ctx, int32_t slot, const float* d_rgb_values, const float* d_depth_values,
                         const float* d_normal_map, const float* d_opacity, hsb_stream_t stream);

@@ -29,7 +29,7 @@ if os.path.exists(path):
     ref = torch.load(path)
     for n in names + ["grads"]:
         a, b = cur[n], ref[n]
-        if n == "dRIN": a, b = a[:, 54:81], b[:, 54:81]
+        if n == "dRIN": a, b = a[:, 310:337], b[:, 310:337]
         if n == "SR": a, b = a[:, :cfg.d_out], b[:, :cfg.d_out]
         print("%-6s rel %.3e   max|ref| %.3e" % (n, common.rel_err(a, b), float(b.abs().max())))
 else:

@@ -1,0 +1,68 @@
+"""Generates tests/golden/stage2_*.npz: the reference's Stage-2 consumers of the Stage-1 operator,
+run through the REFERENCE's own Python (model/network.py:1235-1383, model/ray_sampler.py:85-104,290-447, imported from
+/root/reference through oracle/ref_shims.py) on CPU in eval mode (deterministic sampler).
+
+    forward_multi_obj_rays_subset_all_sdf(ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs)
+    forward_multi_obj_rays_subset_all_sdf_near_far(..., near, far)
+
+Run in the build container only:   python tests/golden/make_golden_stage2.py
+Weights are reproduced from torch.manual_seed(42) + holoscene_b200.synthetic.perturb_state_dict (a checksum is stored).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+from holoscene_b200 import synthetic  # noqa: E402
+from make_golden import LOGMAP, make_conf  # noqa: E402
+from oracle import model as om  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+
+CASES = {
+    # name: (K, R, sampler, obj_idxs, subset_obj_idxs, (near, far) or None)
+    "stage2_subset": (4, 40, (16, 32, 8), [1, 2], [0, 1, 2], None),
+    "stage2_subset_same": (5, 40, (16, 32, 8), [2, 4], [2, 4], None),
+    "stage2_single_bg": (4, 40, (16, 32, 8), [0], [0], None),
+    "stage2_near_far": (4, 40, (16, 32, 8), [1, 3], [1, 3], (0.15, 2.2)),
+}
+
+
+def main():
+    net, _, _ = ref_shims.reference_modules()
+    for name, (K, R, sampler, obj, sub, nf) in CASES.items():
+        cfg = om.StepConfig(d_out=K, logmap=LOGMAP, N_samples=sampler[0], N_samples_eval=sampler[1], N_samples_extra=sampler[2])
+        torch.manual_seed(42)
+        model = net.HoloSceneNetwork(make_conf(K, sampler))
+        torch.manual_seed(42)
+        sd = synthetic.perturb_state_dict(om.init_state_dict(cfg))
+        model.load_state_dict(sd)
+        model.eval()
+        Kmat, pose = synthetic.camera()
+        gen = torch.Generator().manual_seed(5)
+        pose = pose.clone()
+        pose[0, :3, :3] = torch.linalg.qr(torch.randn(3, 3, generator=gen))[0]          # a real rotation: depth scale / normal frame matter
+        uv, _ = synthetic.rays_and_gt(R, K)
+        dirs, cam, _ = om.camera_rays(uv, pose, Kmat)
+        dirs = dirs * (1.0 + torch.rand(R, 1, generator=gen))                            # un-normalised on purpose: the method normalises
+        if nf is None:
+            out = model.forward_multi_obj_rays_subset_all_sdf(cam.clone(), dirs.clone(), pose, obj, sub)
+        else:
+            out = model.forward_multi_obj_rays_subset_all_sdf_near_far(cam.clone(), dirs.clone(), pose, obj, sub, nf[0], nf[1])
+        blob = {"meta_K": K, "meta_R": R, "meta_sampler": np.array(sampler), "meta_logmap": LOGMAP, "meta_obj_idxs": np.array(obj),
+                "meta_subset_idxs": np.array(sub), "meta_near_far": np.array(nf if nf else (-1.0, -1.0)),
+                "in_ray_origins": cam.numpy(), "in_ray_dirs": dirs.numpy(), "in_pose": pose.numpy()}
+        for k, v in out.items():
+            blob["out_" + k] = v.detach().numpy()
+        blob["check_param_sum"] = np.float64(sum(float(v.double().abs().sum()) for v in sd.values() if v.dtype.is_floating_point))
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".npz")
+        np.savez_compressed(path, **blob)
+        print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024), {k: tuple(v.shape) for k, v in out.items() if k in ("opacity", "semantic_values")})
+
+
+if __name__ == "__main__":
+    main()
