@@ -48,6 +48,7 @@ class TrainStep:
         self._tag = 0
         self._tag_host = self._tag_dev = self._flags_host = None
         self._eager_steps = 0
+        self._cooldown = 0                      # kernel-by-kernel steps left after a wrong round-count guess (an unstable count makes replays a loss)
         self._graph_kernels = 0                 # libhsb200 kernels executed through graph replays so far
         self.stats = {"captures": 0, "replays": 0, "misses": 0, "eager": 0}
 
@@ -106,6 +107,9 @@ class TrainStep:
         if getattr(self.loss_fn, "end_step", -1) > 0:
             return False                        # loss weights decay with the step count: they would be baked into the graph
         if self._eager_steps < self.graph_after:
+            return False
+        if self._cooldown > 0:
+            self._cooldown -= 1
             return False
         return m.ray_sampler._rounds_guess.get(-1) is not None
 
@@ -169,6 +173,7 @@ class TrainStep:
         if not m.ray_sampler.judge(-1, rec.rounds, self._flags_host.tolist()):
             # wrong round count: this step's gradients are not the reference's -- discard them and repeat the step kernel by kernel
             self.stats["misses"] += 1
+            self._cooldown = min(64, 4 * self.stats["misses"])      # back off: every miss costs a whole wasted step
             m.ray_sampler._rounds_guess.pop(-1, None)
             return self._eager_step(model_input, ground_truth, indices)
         self.stats["replays"] += 1
