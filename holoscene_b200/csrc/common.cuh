@@ -27,12 +27,8 @@ __device__ __forceinline__ float softplus100(float a) {
 __device__ __forceinline__ float sp_sigma(float h) { return 1.0f - __expf(-100.0f * h); }
 
 // Laplace density, reference model/density.py:21-26.
-// expm1 well below -1 is taken as exp(x) - 1 with ONE fp32 rounding: CUDA's expm1f may return -1 + 2^-24 where the correctly rounded
-// value is -1 (torch on the CPU returns -1), and the last compositing interval (1e10 long) turns that one ulp -- a density of 3e-7
-// instead of exactly 0 far outside the surface -- into a full weight.
 __device__ __forceinline__ float laplace_density(float s, float beta) {
-    const float x = -fabsf(s) / beta;
-    float e = (x < -1.0f) ? (expf(x) - 1.0f) : expm1f(x);
+    float e = expm1f(-fabsf(s) / beta);
     float sg = (s > 0.0f) ? 1.0f : ((s < 0.0f) ? -1.0f : 0.0f);
     return (1.0f / beta) * (0.5f + 0.5f * sg * e);
 }

@@ -21,6 +21,10 @@ namespace hsb {
 
 // accumulator slots (double)
 enum { A_RGB = 0, A_NL1, A_NCOS, A_SEM, A_EIK, A_SMOOTH, A_DD, A_D, A_DG, A_G, A_COUNT };
+// second-phase sums of the depth term (sum phi, sum phi' d, sum phi'): their own range, so that a data-parallel run can all-reduce the
+// two phases separately (hsb_loss_phase)
+enum { A_P0 = 16, A_P1, A_P2 };
+constexpr int A_BADSEG = 15;
 
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(256) loss_ray_kernel(hsb_loss_cfg f, const flo
         const bool m = pos && neg && (mask_gt[r] > 0.5f);
         // opacity BCE over the K channels
         const int seg = (int)segs[r];
-        if (lane == 0 && (seg < 0 || seg >= f.K)) acc[HSB_LOSS_SCRATCH_DOUBLES - 1] = 1.0;     // class id outside [0, K): flagged, see loss_final_kernel
+        if (lane == 0 && (seg < 0 || seg >= f.K)) acc[A_BADSEG] = 1.0;     // class id outside [0, K): flagged, see loss_final_kernel
         const float gk = f.w_sem / ((float)f.R * (float)f.K);
         float bce = 0.0f;
         for (int k = lane; k < f.K; k += 32) {
@@ -165,17 +169,23 @@ __global__ void __launch_bounds__(256) loss_eik_kernel(hsb_loss_cfg f, const flo
 }
 
 // ---- depth term (needs the global sums) + the scalar outputs: one CTA ---------------------------------------------
+// do_sums: add this batch's (sum phi, sum phi' d, sum phi') to acc[A_P0..]; do_final: gradients + scalar outputs from acc.  One GPU:
+// both in one launch.  Data parallel over ray shards (union-batch semantics): the caller all-reduces acc[0:16] before the do_sums
+// launch and acc[16:19] before the do_final launch; n_total = rays of the union batch, half_total = its eikonal rows / 2, grad_mult =
+// world size (the shard gradients are later SUM-all-reduced and divided by the world size).
 __global__ void __launch_bounds__(1024) loss_final_kernel(hsb_loss_cfg f, const float* __restrict__ depth, const float* __restrict__ depth_gt,
-                                                          long long half, float* __restrict__ d_depth, const double* __restrict__ acc,
-                                                          float* __restrict__ losses) {
+                                                          long long half, float* __restrict__ d_depth, double* __restrict__ acc,
+                                                          float* __restrict__ losses, int do_sums, int do_final, double n_total,
+                                                          double grad_mult) {
     __shared__ double red[3][32];
     __shared__ double tot[3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double N = (double)f.R;
+    const double N = n_total;
     const double sdd = acc[A_DD], sd = acc[A_D], sdg = acc[A_DG], sg = acc[A_G];
     const double det = sdd * N - sd * sd;
     const double w = (N * sdg - sd * sg) / det, q = (sdd * sg - sd * sdg) / det;
     double p[3] = {0, 0, 0};   // sum phi, sum phi' d, sum phi'
+    if (do_sums)
     for (int r = threadIdx.x; r < f.R; r += blockDim.x) {
         const double d = (double)depth[r];
         const double e = w * d + q - (double)depth_gt[r];
@@ -195,13 +205,15 @@ __global__ void __launch_bounds__(1024) loss_final_kernel(hsb_loss_cfg f, const 
         for (int i = 0; i < 3; ++i) {
             double s = lane < (int)((blockDim.x + 31) >> 5) ? red[i][lane] : 0.0;
             s = warp_sum_d(s);
-            if (lane == 0) tot[i] = s;
+            if (lane == 0) tot[i] = do_sums ? acc[A_P0 + i] + s : acc[A_P0 + i];
         }
     }
     __syncthreads();
+    if (do_sums && threadIdx.x < 3) acc[A_P0 + threadIdx.x] = tot[threadIdx.x];
+    if (!do_final) return;
     // u = A^-1 [sum phi' d, sum phi']  (A symmetric)
     const double u0 = (N * tot[1] - sd * tot[2]) / det, u1 = (sdd * tot[2] - sd * tot[1]) / det;
-    const double k = (double)f.w_depth / N;
+    const double k = (double)f.w_depth * grad_mult / N;
     // a zero depth weight must not leak the NaN of a singular scale/shift system (R == 1, constant depth) into the backward: 0 * NaN = NaN
     const bool depth_off = f.w_depth == 0.0f;
     for (int r = threadIdx.x; r < f.R; r += blockDim.x) {
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(1024) loss_final_kernel(hsb_loss_cfg f, const 
                             f.w_sem * sem);
         // a class id outside [0, K) makes the reference's F.one_hot raise (model/loss.py:487-492); here (no host sync on the hot
         // path) the step's loss becomes NaN, which the trainer's logging shows at once
-        if (acc[HSB_LOSS_SCRATCH_DOUBLES - 1] != 0.0) losses[0] = __int_as_float(0x7fc00000);
+        if (acc[A_BADSEG] != 0.0) losses[0] = __int_as_float(0x7fc00000);
     }
 }
 
@@ -229,27 +241,48 @@ __global__ void __launch_bounds__(1024) loss_final_kernel(hsb_loss_cfg f, const 
 
 using namespace hsb;
 
-extern "C" int hsb_loss(const hsb_loss_cfg* cfg, const float* rgb_values, const float* depth_values, const float* normal_map,
-                        const float* opacity, const float* sdf, const float* grad_theta_all, const float* rgb_gt, const float* depth_gt,
-                        const float* normal_gt, const float* mask_gt, const int64_t* segs, float* d_rgb, float* d_depth, float* d_normal,
-                        float* d_opacity, float* d_grad_theta_all, double* scratch, float* losses, cudaStream_t st) {
+// phase: 0 = the whole loss (one GPU);  data parallel with union-batch semantics: 1 = per-ray / eikonal terms into scratch[0:16],
+// 2 = depth second-phase sums into scratch[16:19] (scratch[0:16] all-reduced by the caller), 3 = gradients of the depth term + the
+// scalar outputs (scratch[16:19] all-reduced).  rays_total / grad_rows_total describe the union batch, grad_mult = world size.
+extern "C" int hsb_loss_phase(const hsb_loss_cfg* cfg, int32_t phase, int64_t rays_total, int64_t grad_rows_total, float grad_mult,
+                              const float* rgb_values, const float* depth_values, const float* normal_map, const float* opacity,
+                              const float* sdf, const float* grad_theta_all, const float* rgb_gt, const float* depth_gt,
+                              const float* normal_gt, const float* mask_gt, const int64_t* segs, float* d_rgb, float* d_depth,
+                              float* d_normal, float* d_opacity, float* d_grad_theta_all, double* scratch, float* losses, cudaStream_t st) {
     if (!cfg || cfg->R < 1 || cfg->S < 1 || cfg->K < 1 || cfg->n_grad_rows < 0 || (cfg->n_grad_rows & 1) || !rgb_values || !depth_values ||
         !normal_map || !opacity || !sdf || !rgb_gt || !depth_gt || !normal_gt || !mask_gt || !segs || !d_rgb || !d_depth || !d_normal ||
-        !d_opacity || !scratch || !losses || (cfg->n_grad_rows > 0 && (!grad_theta_all || !d_grad_theta_all))) {
+        !d_opacity || !scratch || !losses || (cfg->n_grad_rows > 0 && (!grad_theta_all || !d_grad_theta_all)) || phase < 0 || phase > 3 ||
+        rays_total < cfg->R || grad_rows_total < cfg->n_grad_rows) {
         set_error("hsb_loss: bad argument");
         return HSB_ERR_ARG;
     }
     const hsb_loss_cfg f = *cfg;
-    cudaMemsetAsync(scratch, 0, HSB_LOSS_SCRATCH_DOUBLES * sizeof(double), st);
-    loss_ray_kernel<<<cdiv((long long)f.R * 32, 256), 256, 0, st>>>(f, rgb_values, depth_values, normal_map, opacity, sdf, rgb_gt, depth_gt,
-                                                                   normal_gt, mask_gt, reinterpret_cast<const long long*>(segs), d_rgb,
-                                                                   d_normal, d_opacity, scratch);
     const long long half = f.n_grad_rows / 2;
-    if (half > 0) {
-        loss_eik_kernel<<<cdiv(half, 256), 256, 0, st>>>(f, grad_theta_all, half, d_grad_theta_all, scratch);
+    if (phase <= 1) {
+        if (cudaMemsetAsync(scratch, 0, HSB_LOSS_SCRATCH_DOUBLES * sizeof(double), st) != cudaSuccess) { set_error("hsb_loss: memset failed"); return HSB_ERR_CUDA; }
+        loss_ray_kernel<<<cdiv((long long)f.R * 32, 256), 256, 0, st>>>(f, rgb_values, depth_values, normal_map, opacity, sdf, rgb_gt,
+                                                                       depth_gt, normal_gt, mask_gt, reinterpret_cast<const long long*>(segs),
+                                                                       d_rgb, d_normal, d_opacity, scratch);
+        count_launch(1);
+        if (half > 0) {
+            loss_eik_kernel<<<cdiv(half, 256), 256, 0, st>>>(f, grad_theta_all, half, d_grad_theta_all, scratch);
+            count_launch(1);
+        }
+    }
+    if (phase != 1) {
+        const int do_sums = phase == 0 || phase == 2, do_final = phase == 0 || phase == 3;
+        loss_final_kernel<<<1, 1024, 0, st>>>(f, depth_values, depth_gt, phase == 0 ? half : grad_rows_total / 2, d_depth, scratch, losses,
+                                              do_sums, do_final, (double)(phase == 0 ? f.R : rays_total), phase == 0 ? 1.0 : (double)grad_mult);
         count_launch(1);
     }
-    loss_final_kernel<<<1, 1024, 0, st>>>(f, depth_values, depth_gt, half, d_depth, scratch, losses);
-    count_launch(1);
-    return check_launch("hsb_loss");
+    return check_cuda("hsb_loss");
+}
+
+extern "C" int hsb_loss(const hsb_loss_cfg* cfg, const float* rgb_values, const float* depth_values, const float* normal_map,
+                        const float* opacity, const float* sdf, const float* grad_theta_all, const float* rgb_gt, const float* depth_gt,
+                        const float* normal_gt, const float* mask_gt, const int64_t* segs, float* d_rgb, float* d_depth, float* d_normal,
+                        float* d_opacity, float* d_grad_theta_all, double* scratch, float* losses, cudaStream_t st) {
+    return hsb_loss_phase(cfg, 0, cfg ? cfg->R : 0, cfg ? cfg->n_grad_rows : 0, 1.0f, rgb_values, depth_values, normal_map, opacity, sdf,
+                          grad_theta_all, rgb_gt, depth_gt, normal_gt, mask_gt, segs, d_rgb, d_depth, d_normal, d_opacity, d_grad_theta_all,
+                          scratch, losses, st);
 }

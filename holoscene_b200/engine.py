@@ -80,12 +80,13 @@ class LossCfg(ctypes.Structure):
                 ("w_sem", c_f32)]
 
 
-LOSS_SCRATCH_DOUBLES = 16
+LOSS_SCRATCH_DOUBLES = 32
 _loss = declare("hsb_loss", [ctypes.POINTER(LossCfg)] + [_vp] * 18 + [c_stream])
+_loss_phase = declare("hsb_loss_phase", [ctypes.POINTER(LossCfg), ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, c_f32] + [_vp] * 18 + [c_stream])
 
 
 def fused_loss(cfg: LossCfg, rgb_values, depth_values, normal_map, opacity, sdf, grad_all, rgb_gt, depth_gt, normal_gt, mask_gt,
-               segs):
+               segs, union_world=1):
     """hsb_loss: returns (losses[8], d_rgb, d_depth, d_normal, d_opacity, d_grad_all) -- see include/hsb200.h."""
     dev = rgb_values.device
     d_rgb = torch.empty_like(rgb_values)
@@ -95,9 +96,20 @@ def fused_loss(cfg: LossCfg, rgb_values, depth_values, normal_map, opacity, sdf,
     d_grad = torch.empty_like(grad_all) if grad_all is not None else None
     scratch = torch.empty(LOSS_SCRATCH_DOUBLES, dtype=torch.float64, device=dev)
     losses = torch.empty(8, device=dev)
-    check(_loss(ctypes.byref(cfg), ptr(rgb_values), ptr(depth_values), ptr(normal_map), ptr(opacity), ptr(sdf), ptr(grad_all),
-                ptr(rgb_gt), ptr(depth_gt), ptr(normal_gt), ptr(mask_gt), ptr(segs), ptr(d_rgb), ptr(d_depth), ptr(d_normal),
-                ptr(d_opacity), ptr(d_grad), ptr(scratch), ptr(losses), stream()))
+    args = (ptr(rgb_values), ptr(depth_values), ptr(normal_map), ptr(opacity), ptr(sdf), ptr(grad_all), ptr(rgb_gt), ptr(depth_gt),
+            ptr(normal_gt), ptr(mask_gt), ptr(segs), ptr(d_rgb), ptr(d_depth), ptr(d_normal), ptr(d_opacity), ptr(d_grad), ptr(scratch),
+            ptr(losses), stream())
+    if union_world <= 1:
+        check(_loss(ctypes.byref(cfg), *args))
+    else:
+        # ray shards with union-batch semantics: the depth term's least-squares fit and the reported means run over ALL ranks' rays
+        import torch.distributed as dist
+        R_total, rows_total = cfg.R * union_world, cfg.n_grad_rows * union_world
+        check(_loss_phase(ctypes.byref(cfg), 1, R_total, rows_total, float(union_world), *args))
+        dist.all_reduce(scratch[:16])
+        check(_loss_phase(ctypes.byref(cfg), 2, R_total, rows_total, float(union_world), *args))
+        dist.all_reduce(scratch[16:19])
+        check(_loss_phase(ctypes.byref(cfg), 3, R_total, rows_total, float(union_world), *args))
     return losses, d_rgb, d_depth, d_normal, d_opacity, d_grad
 
 

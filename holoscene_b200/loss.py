@@ -46,11 +46,11 @@ class _FusedLossFn(torch.autograd.Function):
     the per-term values are returned detached."""
 
     @staticmethod
-    def forward(ctx, cfg, sdf, gts, rgb_values, depth_values, normal_map, opacity, grad_all):
+    def forward(ctx, cfg, sdf, gts, rgb_values, depth_values, normal_map, opacity, grad_all, union_world=1):
         from . import engine as _engine
         losses, d_rgb, d_depth, d_normal, d_opacity, d_grad = _engine.fused_loss(
             cfg, rgb_values.contiguous(), depth_values.contiguous(), normal_map.contiguous(), opacity.contiguous(), sdf,
-            None if grad_all is None else grad_all.contiguous(), *gts)
+            None if grad_all is None else grad_all.contiguous(), *gts, union_world=union_world)
         ctx.grads = (d_rgb, d_depth, d_normal, d_opacity, d_grad)
         ctx.mark_non_differentiable(losses)
         return losses[0].clone(), losses
@@ -61,7 +61,7 @@ class _FusedLossFn(torch.autograd.Function):
         ctx.grads = None
         # g_total is 1 for loss.backward(); kept general (one tiny launch per tensor only when it is not the constant one)
         sc = (lambda t: t) if g_total is None else (lambda t: None if t is None else t * g_total)
-        return None, None, None, sc(d_rgb), sc(d_depth), sc(d_normal), sc(d_opacity), sc(d_grad)
+        return None, None, None, sc(d_rgb), sc(d_depth), sc(d_normal), sc(d_opacity), sc(d_grad), None
 
 
 class HoloSceneLoss(MonoSDFLoss):
@@ -77,6 +77,9 @@ class HoloSceneLoss(MonoSDFLoss):
         self.use_obj_opacity = use_obj_opacity
         if not use_obj_opacity:
             raise NotImplementedError("Stage-1 confs use use_obj_opacity = True (ObjectSDF++ opacity loss)")
+        # > 1: this process holds one of `union_world` equal ray shards and the loss is that of the UNION batch (the depth term's
+        # scale/shift fit and the reported means are all-reduced inside hsb_loss_phase; set by TrainStep(union_batch=True))
+        self.union_world = 1
 
     def object_distinct_loss(self, sdf_value, min_sdf):
         _, min_indice = torch.min(sdf_value, dim=1, keepdim=True)
@@ -138,7 +141,7 @@ class HoloSceneLoss(MonoSDFLoss):
         gts = (f32(gt["rgb"], 3), f32(gt["depth"], 1), f32(gt["normal"], 3), f32(gt["mask"], 1),
                gt["segs"].to(dev, non_blocking=True).long().reshape(R).contiguous())
         total, terms = _FusedLossFn.apply(cfg, sdf, gts, mo["rgb_values"], mo["depth_values"], mo["normal_map"],
-                                          mo["object_opacity"], grad_all)
+                                          mo["object_opacity"], grad_all, self.union_world)
         zero = torch.zeros((), device=dev)
         out = {"rgb_loss": terms[1], "eikonal_loss": terms[2], "smooth_loss": terms[3], "depth_loss": terms[4],
                "normal_l1": terms[5], "normal_cos": terms[6], "semantic_loss": terms[7]}

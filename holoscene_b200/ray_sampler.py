@@ -35,6 +35,7 @@ class ErrorBoundSampler:
         self._rounds_guess = {}     # channel (-1 = scene) -> rounds the last call needed (speculative convergence test)
         self._pending = []          # speculative calls awaiting verify()
         self.capture_flags = None   # (kind, rounds, device flags) of the last call made under CUDA-graph capture
+        self.union_world = 1        # > 1: the convergence test is the reference's GLOBAL one over all ranks' rays (exact mode only)
         self._flag_bufs = []
         self.spec_hits = self.spec_misses = 0
 
@@ -98,6 +99,9 @@ class ErrorBoundSampler:
             z_all, sdf_all, n_old = z_out, sdf_out, n
             total_iters += 1
             if guess is None:
+                if self.union_world > 1:                               # `beta.max() > beta0` over the union batch: any rank, any ray
+                    import torch.distributed as dist
+                    dist.all_reduce(flags[total_iters - 1: total_iters], op=dist.ReduceOp.MAX)
                 not_converge = bool(flags[total_iters - 1].item())     # the reference's per-round host sync (:204)
             else:
                 not_converge = total_iters < guess                     # verified later against the device flags

@@ -35,7 +35,7 @@ class _Captured:
 
 class TrainStep:
     def __init__(self, model, loss_fn, optimizer: StageOneAdam, add_objectvio_iter=25000, world_size=1, use_graph=False,
-                 graph_after=2):
+                 graph_after=2, union_batch=False):
         self.model, self.loss_fn, self.opt = model, loss_fn, optimizer
         self.add_objectvio_iter = add_objectvio_iter
         self.world_size = world_size
@@ -51,6 +51,16 @@ class TrainStep:
         self._cooldown = 0                      # kernel-by-kernel steps left after a wrong round-count guess (an unstable count makes replays a loss)
         self._graph_kernels = 0                 # libhsb200 kernels executed through graph replays so far
         self.stats = {"captures": 0, "replays": 0, "misses": 0, "eager": 0}
+        # union_batch: the ranks' equal ray shards reproduce the single-process step on the union batch -- the two places where rays
+        # couple are exchanged: the depth term's least-squares sums (two 16-double all-reduces inside the loss) and the sampler's global
+        # convergence test (one 4-byte MAX all-reduce per refinement round, host-synchronous like the reference's own .item()).
+        # It is the parity mode of the data-parallel path (kernel by kernel, exact sampler); the default lets both act per shard.
+        self.union_batch = bool(union_batch) and world_size > 1
+        if self.union_batch:
+            self.use_graph = False
+            model.speculative_sampler = False
+            model.ray_sampler.union_world = world_size
+            loss_fn.union_world = world_size
 
     # ---- bookkeeping ----------------------------------------------------------------------------------------------------
     def kernel_launches(self) -> int:

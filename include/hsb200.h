@@ -218,7 +218,7 @@ int hsb_eikonal_backward(hsb_ctx* ctx, const float* d_grad_theta, const float* d
  * the depth/normal decay already applied.  Outputs: d_* = weight * d(term)/d(output), ready for hsb_render_backward /
  * hsb_eikonal_backward; losses[8] = {weighted total of these terms, rgb, eikonal, smooth, depth, normal_l1, normal_cos, semantic}.
  * scratch: HSB_LOSS_SCRATCH_DOUBLES device doubles. */
-#define HSB_LOSS_SCRATCH_DOUBLES 16
+#define HSB_LOSS_SCRATCH_DOUBLES 32
 typedef struct hsb_loss_cfg {
     int32_t R, S, K;
     int64_t n_grad_rows;
@@ -228,6 +228,18 @@ int hsb_loss(const hsb_loss_cfg* cfg, const float* rgb_values, const float* dept
              const float* opacity, const float* sdf, const float* grad_theta_all, const float* rgb_gt, const float* depth_gt,
              const float* normal_gt, const float* mask_gt, const int64_t* segs, float* d_rgb, float* d_depth, float* d_normal,
              float* d_opacity, float* d_grad_theta_all, double* scratch, float* losses, hsb_stream_t stream);
+
+/* The same loss in phases, for ray-sharded data parallelism with UNION-BATCH semantics (every rank holds a shard of the rays; the
+ * depth term's scale/shift least squares (model/loss.py:181-193) couples all rays): phase 1 = per-ray + eikonal terms and their
+ * gradients, partial sums into scratch[0:16]; [caller: all-reduce(sum) scratch[0:16]]; phase 2 = second-phase sums of the depth term
+ * into scratch[16:19]; [caller: all-reduce(sum) scratch[16:19]]; phase 3 = d_depth and the scalar outputs.  rays_total /
+ * grad_rows_total are the union batch's sizes, grad_mult = world size (the shard gradients are SUM-all-reduced and scaled by
+ * 1/world afterwards, so d_depth is pre-multiplied).  phase 0 = hsb_loss. */
+int hsb_loss_phase(const hsb_loss_cfg* cfg, int32_t phase, int64_t rays_total, int64_t grad_rows_total, float grad_mult,
+                   const float* rgb_values, const float* depth_values, const float* normal_map, const float* opacity, const float* sdf,
+                   const float* grad_theta_all, const float* rgb_gt, const float* depth_gt, const float* normal_gt, const float* mask_gt,
+                   const int64_t* segs, float* d_rgb, float* d_depth, float* d_normal, float* d_opacity, float* d_grad_theta_all,
+                   double* scratch, float* losses, hsb_stream_t stream);
 
 /* torch.optim.Adam semantics over one flat segment (holoscene_train.py:156-164); grad_norm_sq (may be NULL)
  * accumulates sum(g^2) in the same pass (the trainer's total_norm statistic, :367-372). */

@@ -28,7 +28,10 @@ CASES = {
     "stage2_subset": (4, 40, (16, 32, 8), [1, 2], [0, 1, 2], None),
     "stage2_subset_same": (5, 40, (16, 32, 8), [2, 4], [2, 4], None),
     "stage2_single_bg": (4, 40, (16, 32, 8), [0], [0], None),
-    "stage2_near_far": (4, 40, (16, 32, 8), [1, 3], [1, 3], (0.15, 2.2)),
+    # far = 3.0: at the last sample exp(-sdf / beta) is far below 2^-25, where the fp32 density 0.5 + 0.5 expm1(.) is exactly 0 (the
+    # last compositing interval is 1e10 long: with a far plane around 2.2 some rays sit ON that rounding edge and an sdf difference of
+    # 1e-5 flips their whole residual weight between 0 and T -- an artefact of the reference arithmetic, not a parity target)
+    "stage2_near_far": (4, 40, (16, 32, 8), [1, 3], [1, 3], (0.15, 3.0)),
 }
 
 
