@@ -93,6 +93,54 @@ __global__ void __launch_bounds__(256) points_pe_kernel(const float* __restrict_
     h[71] = 0.0f;
 }
 
+// Regular-grid points for mesh extraction (utils/general.py:3223-3231, utils/plots.py get_grid_uniform): linear index i = first + t
+// in np.meshgrid(indexing="ij") ravel order -> (ix, iy, iz) = (i / (ny nz), (i / nz) % ny, i % nz), coordinate lo + idx * step
+// (np.linspace: lo + idx * (hi - lo) / (n - 1), the last point pinned to hi).  Writes X and the PE columns of H0 in one pass: no
+// coordinate tensor ever exists on the host or crosses PCIe.
+__global__ void __launch_bounds__(256) grid_points_kernel(float lox, float loy, float loz, float hix, float hiy, float hiz, int nx, int ny,
+                                                          int nz, long long first, long long N, float* __restrict__ X,
+                                                          float* __restrict__ H0, int rtf) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const long long i = first + t;
+    const int iz = (int)(i % nz), iy = (int)((i / nz) % ny), ix = (int)(i / ((long long)nz * ny));
+    // float64 like np.linspace, then one rounding to float32 (the reference builds the grid in numpy and casts)
+    auto lin = [](float lo, float hi, int n, int k) {
+        if (n == 1) return lo;
+        if (k == n - 1) return hi;
+        return (float)((double)lo + (double)k * (((double)hi - (double)lo) / (double)(n - 1)));
+    };
+    const float x = lin(lox, hix, nx, ix), y = lin(loy, hiy, ny, iy), z = lin(loz, hiz, nz, iz);
+    X[t * 3 + 0] = x; X[t * 3 + 1] = y; X[t * 3 + 2] = z;
+    float* h = H0 + t * LD_H0;
+    pe_write(h, x, y, z, 6, rtf);
+    h[71] = 0.0f;
+}
+
+// get_shift_sdf_raw (model/network.py:460-479) on rows of per-object values: where the scene SDF (min) is negative every other
+// object's value is raised to at least -min; the arg-min channel keeps the min.  channel >= 0: only that column leaves ([N]),
+// else the K columns ([N, K], dense).
+__global__ void __launch_bounds__(256) grid_select_kernel(const float* __restrict__ SR, long long N, int K, int Kp, int channel, int shift,
+                                                          float* __restrict__ out) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const float* s = SR + p * Kp;
+    float mn = s[0];
+    int best = 0;
+    if (shift || channel < -1)
+        for (int k = 1; k < K; ++k)
+            if (s[k] < mn) { mn = s[k]; best = k; }
+    auto value = [&](int k) {
+        float v = s[k];
+        if (shift && mn < 0.0f && k != best) v = fmaxf(v, -mn);
+        return v;
+    };
+    if (channel >= 0) out[p] = value(channel);
+    else if (channel == -2) out[p] = mn;                      // scene SDF (get_sdf_vals)
+    else
+        for (int k = 0; k < K; ++k) out[p * K + k] = value(k);
+}
+
 // min over the K object channels, first index on ties (== -maxpool1d(-s)); channel >= 0 selects one channel.
 // Rows are Kp = 8 n floats, 16-byte aligned: read as float4.
 __global__ void __launch_bounds__(256) sdf_min_kernel(const float* __restrict__ SR, long long N, int K, int Kp, int channel,
@@ -574,6 +622,17 @@ int launch_points_pe(const float* X, long long N, float* H0, int rtf, cudaStream
     if (N == 0) return HSB_OK;
     points_pe_kernel<<<cdiv(N, 256), 256, 0, st>>>(X, N, H0, rtf);
     return check_launch("points_pe");
+}
+int launch_grid_points(const float* lo, const float* hi, const int* res, long long first, long long N, float* X, float* H0, int rtf,
+                       cudaStream_t st) {
+    if (N == 0) return HSB_OK;
+    grid_points_kernel<<<cdiv(N, 256), 256, 0, st>>>(lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], res[0], res[1], res[2], first, N, X, H0, rtf);
+    return check_launch("grid_points");
+}
+int launch_grid_select(const float* SR, long long N, int K, int Kp, int channel, int shift, float* out, cudaStream_t st) {
+    if (N == 0) return HSB_OK;
+    grid_select_kernel<<<cdiv(N, 256), 256, 0, st>>>(SR, N, K, Kp, channel, shift, out);
+    return check_launch("grid_select");
 }
 int launch_sdf_min(const float* SR, long long N, int K, int Kp, int channel, float* sdf, int* kstar, cudaStream_t st, unsigned long long mask) {
     if (N == 0) return HSB_OK;

@@ -642,6 +642,33 @@ extern "C" int hsb_render_forward(hsb_ctx* h, int32_t slot_id, const float* o, c
     return HSB_OK;
 }
 
+// Dense-grid SDF inference for mesh extraction (utils/general.py:3223-3252 marching_cubes_from_sdf, utils/plots.py:
+// 181-200: get_sdf_raw / get_shift_sdf_raw / get_sdf_vals over a regular grid in chunks).  One call evaluates `n` consecutive grid
+// points starting at linear index `first` (np.meshgrid(indexing="ij") ravel order): grid coordinates and PE in one kernel, hash
+// gather, the fused SDF trunk, then the column selection / shift rule -- the chunk's coordinates never exist on the host.
+extern "C" int hsb_sdf_grid(hsb_ctx* h, const float* lo_host, const float* hi_host, const int32_t* res_host, int64_t first, int64_t n,
+                            int32_t channel, int32_t shift, float* out, cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_sdf_grid");
+    Slot& s = c->scratch;
+    if (!lo_host || !hi_host || !res_host || !out || n < 0 || first < 0 || channel < -2 || channel >= c->K || res_host[0] < 1 || res_host[1] < 1 ||
+        res_host[2] < 1 || first + n > (long long)res_host[0] * res_host[1] * res_host[2]) {
+        set_error("hsb_sdf_grid: bad argument");
+        return HSB_ERR_ARG;
+    }
+    if (n > s.cap_points) { set_error("hsb_sdf_grid: chunk exceeds max_points"); return HSB_ERR_ARG; }
+    const hsb_step_cfg& f = c->cfg;
+    const int rt = c->rtf();
+    TRY(launch_grid_points(lo_host, hi_host, res_host, first, n, s.X, s.H0, rt, st));
+    if (!f.precise && sdf_trunk_tc_eligible(c->K)) {
+        TRY(hash_forward_ex(s.X, c->P(SEG_EMB), c->hoffs, s.H0 + 39, 2, LD_H0, nullptr, 96, (uint32_t)n, f.L, f.S, f.H, 1, 1, st));
+        TRY(sdf_trunk_tc(s.H0, n, c->W0e, c->W1e, c->W2e, c->P(SEG_L0B), c->P(SEG_L1B), c->P(SEG_L2B), c->K, c->Kp, -1, nullptr, s.SR, st));
+    } else {
+        TRY(sdf_forward(c, s, n, false, st));
+    }
+    return launch_grid_select(s.SR, n, c->K, c->Kp, channel, shift, out, st);
+}
+
 // Stage-2 consumer of the same operator (model/network.py:1235-1306 forward_multi_obj_rays_subset_all_sdf): the scene
 // pass with the min / arg-min / gradient taken over the SUBSET channels (mask_subset) and a second, "background" set of weights
 // from the min over the object channels (mask_obj) that composites colour, depth and normals.  Forward only: the MAIN slot's

@@ -46,6 +46,8 @@ struct CompositeGrads {
 
 int launch_ray_points(const float* o, const float* d, const float* z, int R, int S, float* X, float* H0, float* RIN, int rtf, cudaStream_t st);
 int launch_points_pe(const float* X, long long N, float* H0, int rtf, cudaStream_t st);
+int launch_grid_points(const float* lo, const float* hi, const int* res, long long first, long long N, float* X, float* H0, int rtf, cudaStream_t st);
+int launch_grid_select(const float* SR, long long N, int K, int Kp, int channel, int shift, float* out, cudaStream_t st);
 int launch_sdf_min(const float* SR, long long N, int K, int Kp, int channel, float* sdf, int* kstar, cudaStream_t st, unsigned long long mask = ~0ull);
 int launch_chain_seed(const float* W2e, const float* H2, const int* kstar, long long N, int K, int nseed, float* P2, int rtf, cudaStream_t st);
 int launch_chain_end(const float* Q0, const float* H0, const float* DY, long long N, int nseed, float* G, float* RIN, int rtf, cudaStream_t st);

@@ -53,6 +53,8 @@ _render_fwd = declare("hsb_render_forward", [_vp, ctypes.c_int32, _vp, _vp, _vp,
 _sdf_values_subset = declare("hsb_sdf_values_subset", [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, _vp, c_stream])
 _render_fwd_subset = declare("hsb_render_forward_subset", [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp, ctypes.c_uint64,
                                                            ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, c_stream])
+_sdf_grid = declare("hsb_sdf_grid", [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32),
+                                     ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _vp, c_stream])
 _render_bwd = declare("hsb_render_backward", [_vp, ctypes.c_int32, _vp, _vp, _vp, _vp, c_stream])
 _eik_fwd = declare("hsb_eikonal_forward", [_vp, _vp, ctypes.c_int64, _vp, _vp, _vp, c_stream])
 _eik_bwd = declare("hsb_eikonal_backward", [_vp, _vp, _vp, c_stream])
@@ -242,6 +244,12 @@ class StepEngine:
         else:
             check(_sdf_values(self._h, ptr(o), ptr(d), ptr(z), R, S, int(channel), ptr(out), stream()))
         return out
+
+    def sdf_grid(self, lo, hi, res, first, n, channel, shift, out):
+        """hsb_sdf_grid: n consecutive points of the regular grid (ravel index first..first+n) -> out (device), see include/hsb200.h."""
+        f3 = (ctypes.c_float * 3)
+        check(_sdf_grid(self._h, f3(*[float(v) for v in lo]), f3(*[float(v) for v in hi]), (ctypes.c_int32 * 3)(*[int(v) for v in res]),
+                        int(first), int(n), int(channel), int(bool(shift)), ptr(out), stream()))
 
     def render_forward_subset(self, o, d, z, depth_scale, rot, subset_idxs, obj_idxs):
         """hsb_render_forward_subset: (rgb_values [R,3], depth_values [R,1], normal_map [R,3], opacity [R,1], semantic [R,n_subset])."""

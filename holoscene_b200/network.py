@@ -127,6 +127,28 @@ class ObjectImplicitNetworkGrid(nn.Module):
         return shift
 
 
+    @torch.no_grad()
+    def get_outputs_and_indices(self, x):
+        """network.py:481-504 as used by plotting: (sdf, feature_vectors, gradients, semantic, sdf_raw, indices) at points x.
+        Runs the scene-pass forward kernels on the points (forward only: the returned tensors carry no autograd graph)."""
+        model = self._owner[0]
+        eng = model.engine()
+        eng.prepare()
+        x = x.reshape(-1, 3).contiguous().float()
+        outs = []
+        step = eng.max_rays
+        eye = torch.eye(3, device=x.device)
+        for i in range(0, x.shape[0], step):
+            xb = x[i:i + step].contiguous()
+            n = xb.shape[0]
+            zeros = torch.zeros(n, 3, device=x.device)
+            eng.render_forward(_engine.SLOT_MAIN, xb, zeros, torch.zeros(n, 1, device=x.device), torch.ones(n, 1, device=x.device), eye)
+            raw = eng.buffer("main.SR")[:n, : self.d_out].clone()
+            outs.append((eng.buffer("main.SDF")[:n].clone(), eng.buffer("main.RIN")[:n, :256].clone(), eng.buffer("main.G")[:n].clone(),
+                         self.sigmoid * torch.sigmoid(-self.sigmoid * raw), raw, eng.buffer("main.KS", torch.int32)[:n].long().clone()))
+        return tuple(torch.cat([o[j] for o in outs], 0) for j in range(6))
+
+
 class RenderingNetwork(nn.Module):
     """Parameter container with the reference's names (network.py:535-583)."""
 

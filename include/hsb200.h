@@ -187,6 +187,14 @@ int hsb_sampler_finalize(const float* z, int32_t n, const float* samples, int32_
 int hsb_render_forward(hsb_ctx* ctx, int32_t slot, const float* o, const float* d, const float* z, int32_t R, int32_t S,
                        const float* depth_scale, const float* rot, float* rgb_values, float* depth_values, float* normal_map,
                        float* opacity, float* semantic, hsb_stream_t stream);
+/* Dense-grid SDF inference for mesh extraction (utils/general.py:3223-3252, utils/plots.py:181-200): per-object values at `n`
+ * consecutive points of the regular grid lo..hi (res points per axis, np.linspace / np.meshgrid(indexing="ij") ravel order) starting
+ * at linear index `first`; n <= max_points.  channel >= 0: that object's column -> out [n]; -1: all K columns -> out [n,K]; -2: the
+ * scene SDF (min over K) -> out [n].  shift != 0 applies get_shift_sdf_raw (model/network.py:460-479).  lo / hi / res are HOST arrays
+ * of 3; grid coordinates are generated on the device. */
+int hsb_sdf_grid(hsb_ctx* ctx, const float* lo_host, const float* hi_host, const int32_t* res_host, int64_t first, int64_t n,
+                 int32_t channel, int32_t shift, float* out, hsb_stream_t stream);
+
 /* Stage-2 consumers of the same operator (model/network.py:1235-1383 forward_multi_obj_rays_subset_all_sdf[_near_far],
  * model/network.py:320-326 get_multi_object_sdf_vals, model/ray_sampler.py:290-447): channel sets are bit masks (bit k = channel k).
  *   hsb_sdf_values_subset:     no-grad min over the channels of `mask` at o + z d (the sampler's queries with idx = list);

@@ -674,3 +674,53 @@ def test_stage2_subset_forward_matches_reference_golden(name, precise):
     report(f"{name} precise={precise}", rows)
     bad = [r for r in rows if not (r[1] <= r[2])]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("precise", [True, False])
+def test_dense_sdf_grid_matches_oracle_on_the_reference_grid(precise):
+    """N2: dense-grid SDF inference for mesh extraction.  holoscene_b200.grid_query.dense_sdf_grid (grid coordinates generated on the
+    device, fused trunk, chunked with a ragged last chunk, double-buffered D2H) against the oracle evaluated on the grid the
+    reference builds with numpy (utils/general.py:3223-3231: np.linspace / np.meshgrid(indexing="ij"), chunks of get_sdf_raw), for one
+    object channel, all channels, the scene SDF and the shift rule (model/network.py:460-479); plus get_outputs_and_indices."""
+    from holoscene_b200 import grid_query
+    from oracle import model as om
+    g = common.load_golden("step_train_k3")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    m = build_model(cfg, sd, precise).eval()
+    res, lo, hi = (7, 5, 9), (-0.9, -0.8, -1.0), (0.7, 1.0, 0.95)
+    axes = [np.linspace(lo[a], hi[a], res[a]) for a in range(3)]
+    xx, yy, zz = np.meshgrid(*axes, indexing="ij")
+    pts = torch.tensor(np.vstack([xx.ravel(), yy.ravel(), zz.ravel()]).T, dtype=torch.float)
+    raw, _ = om.implicit_forward(sd, cfg, pts, with_color=False)
+    raw = raw.detach()
+    mn, idx = raw.min(dim=1, keepdim=True)
+    shifted = torch.where((mn < 0).expand_as(raw), torch.max(raw, (-mn).expand_as(raw)), raw)
+    shifted[torch.arange(raw.shape[0]), idx.squeeze(1)] = mn.squeeze(1)
+    tol = 2e-4 if precise else 5e-3
+    got = grid_query.dense_sdf_grid(m, res, (lo, hi), chunk_points=100)
+    assert got.shape == (7 * 5 * 9, cfg.d_out) and float(np.abs(got - raw.numpy()).max()) < tol
+    got = grid_query.dense_sdf_grid(m, res, (lo, hi), obj_id=1, chunk_points=64)
+    assert got.shape == res and float(np.abs(got.reshape(-1) - raw[:, 1].numpy()).max()) < tol
+    got = grid_query.dense_sdf_grid(m, res, (lo, hi), scene=True)
+    assert float(np.abs(got.reshape(-1) - mn[:, 0].numpy()).max()) < tol
+    got = grid_query.dense_sdf_grid(m, res, (lo, hi), shift=True, chunk_points=77)
+    assert float(np.abs(got - shifted.numpy()).max()) < tol and int((mn < 0).sum()) > 5
+    ax = grid_query.grid_axes(res, (lo, hi))
+    assert all(np.allclose(a, b) for a, b in zip(ax, axes))
+    # uniform cube, the form marching_cubes_from_sdf uses
+    cube = grid_query.dense_sdf_grid(m, 6, (-1.0, 1.0), obj_id=0)
+    x = np.linspace(-1, 1, 6)
+    cx, cy, cz = np.meshgrid(x, x, x, indexing="ij")
+    cpts = torch.tensor(np.vstack([cx.ravel(), cy.ravel(), cz.ravel()]).T, dtype=torch.float)
+    craw, _ = om.implicit_forward(sd, cfg, cpts, with_color=False)
+    assert cube.shape == (6, 6, 6) and float(np.abs(cube.reshape(-1) - craw[:, 0].detach().numpy()).max()) < tol
+    # get_outputs_and_indices (reference network.py:481-504, used by utils/plots.py)
+    sub = pts[:150]
+    sdf, feat, grads, sem, sdf_raw = om.get_outputs(sd, cfg, sub.clone())
+    o_sdf, o_feat, o_grad, o_sem, o_raw, o_idx = m.implicit_network.get_outputs_and_indices(sub.cuda())
+    assert float((o_raw.cpu() - sdf_raw.detach()).abs().max()) < tol and float((o_sdf.cpu() - sdf.detach()).abs().max()) < tol
+    assert common.rel_err(o_grad.cpu(), grads.detach()) < (2e-3 if precise else 2e-2)
+    assert common.rel_err(o_feat.cpu(), feat.detach()) < (1e-4 if precise else 5e-3)
+    assert float((o_sem.cpu() - sem.detach()).abs().max()) < 50 * tol
+    assert o_idx.shape == (150, 1) and float((o_idx.cpu().squeeze(1) != sdf_raw.argmin(1)).float().mean()) < 0.02
