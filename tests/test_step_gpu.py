@@ -724,3 +724,49 @@ def test_dense_sdf_grid_matches_oracle_on_the_reference_grid(precise):
     assert common.rel_err(o_feat.cpu(), feat.detach()) < (1e-4 if precise else 5e-3)
     assert float((o_sem.cpu() - sem.detach()).abs().max()) < 50 * tol
     assert o_idx.shape == (150, 1) and float((o_idx.cpu().squeeze(1) != sdf_raw.argmin(1)).float().mean()) < 0.02
+
+
+def test_device_input_pipeline_feeds_the_train_step():
+    """N4: the per-step batch (frame choice, class-balanced + uniform pixel selection, uv / ground-truth gathers; reference
+    datasets/ns_dataset.py:380-455) produced on the device by DeviceFrames and consumed by TrainStep without touching the host."""
+    from holoscene_b200 import synthetic
+    from holoscene_b200.device_dataset import DeviceFrames
+    from holoscene_b200.optim import StageOneAdam
+    from holoscene_b200.train_step import TrainStep
+    g = common.load_golden("step_train")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    K = cfg.d_out
+    H = W = 48
+    gen = torch.Generator().manual_seed(3)
+    F = 3
+    segs = torch.randint(0, K, (F, H * W, 1), generator=gen)
+    segs[1][segs[1] == 2] = 0                                             # frame 1 has no pixel of class 2
+    classes = [sorted(int(c) for c in segs[f].unique()) for f in range(F)]
+    Kmat, pose = synthetic.camera(fx=40.0, cx=24.0)
+    frames = DeviceFrames(rgb=torch.rand(F, H * W, 3, generator=gen), depth=torch.rand(F, H * W, 1, generator=gen) + 0.5,
+                          normal=torch.nn.functional.normalize(torch.randn(F, H * W, 3, generator=gen), dim=-1),
+                          mask=torch.ones(F, H * W, 1), segs=segs, intrinsics=Kmat.repeat(F, 1, 1), pose=pose.repeat(F, 1, 1),
+                          img_res=(H, W), classes_per_frame=classes, num_pixels=64)
+    idx, mi, gt = frames.sample(1)
+    R = mi["uv"].shape[1]
+    assert mi["uv"].is_cuda and gt["rgb"].is_cuda and mi["uv"].shape == (1, R, 2) and gt["rgb"].shape == (1, R, 3) and R == 64
+    sidx = mi["sampling_idx"].reshape(-1)
+    assert torch.equal(gt["segs"][0], frames.segs[1][sidx]) and torch.equal(gt["rgb"][0], frames.rgb[1][sidx])
+    assert torch.equal(mi["uv"][0], frames.uv[sidx])
+    # class-balanced half: per class exactly min(count, quota) picks, in the reference's block order
+    bg, per, n_uni = (32 - (32 // len(classes[1])) * (len(classes[1]) - 1)), 32 // len(classes[1]), 32
+    first_half = gt["segs"][0, : R - n_uni, 0].cpu()
+    want = sum(([c] * (bg if i == 0 else per) for i, c in enumerate(classes[1])), [])
+    assert first_half.tolist() == want
+    assert float(mi["uv"][0, :, 0].max()) < W and float(mi["uv"][0, :, 1].max()) < H
+    m = build_model(cfg, sd, False, max_rays=64).train()
+    step = TrainStep(m, make_loss(), StageOneAdam(m), use_graph=True)
+    step.iter_step = 1
+    losses = []
+    for it in range(8):
+        idx, mi, gt = frames.sample(0 if it < 6 else None)               # one frame first: a stable sampler round count -> graph replays
+        out, lo = step({k: mi[k] for k in ("uv", "intrinsics", "pose")}, gt, idx)
+        losses.append(float(lo["loss"].detach()))
+    st = step.graph_stats()
+    assert all(np.isfinite(losses)) and st["captures"] >= 1 and st["replays"] + st["misses"] >= 2, st
