@@ -493,7 +493,7 @@ def main():
     # ---- extra measurements (same JSON line, key "extra") ----
     extra = {}
     if not args.no_extras:
-        short = dict(steps=max(5, args.steps // 2), warmup=4)
+        short = dict(steps=max(5, args.steps // 2), warmup=12)      # the warm-up covers a background-patch step in both sampler modes
         if world == 1:
             for name in ("c3", "c5shard", "c1", "trained"):
                 if name == args.workload:
