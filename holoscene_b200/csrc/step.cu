@@ -84,7 +84,8 @@ struct Ctx {
     Slot scratch;   // X, H0, H1, H2, SR only: hsb_sdf_values between a slot's forward and its backward
     long long block_tiles = 0;   // L2 blocking of the ray passes: 128-row tiles per block of rays (0 = one block)
     bool dual_bwd = true;        // fast mode: chain + SDF-net backward through the dual-accumulator layer kernel (csrc/dual_tc.cu)
-    bool fused_fwd = true;       // fast mode: scene-pass forward through the fused trunk kernels (csrc/render_tc.cu)
+    bool fused_fwd = true;       // fast mode: scene-pass forward through the fused trunk kernels (csrc/sdfchain_tc.cu, render_tc.cu)
+    bool fused_bwd = true;       // fast mode: render / colour data-gradient chain of the backward as one kernel (csrc/render_bwd_tc.cu)
     float* P(int seg) const { return params + off[seg]; }
     float* Gp(int seg) const { return grads + off[seg]; }
 };
@@ -410,7 +411,17 @@ static int render_backward_block(Ctx* c, Slot& s, bool scene, cudaStream_t st) {
     const int P = f.precise;
     const int rt = c->rtf();
     const long long N = s.N;
-    if (scene) {
+    if (scene && P == 0 && c->fused_bwd && render_bwd_tc_eligible()) {
+        // data gradients of render net + colour MLP in ONE kernel (csrc/render_bwd_tc.cu), incl. the four bias gradients, d R2 and
+        // d b2; then the weight-gradient contractions over the tensors it stored, and the colour-table scatter
+        TRY(render_bwd_tc(s.dO, s.U2, s.U1, s.C1, N, c->R2e, c->R1eT, c->R0eT, c->C1T, c->C0T, s.dU2, s.dU1, s.dRIN, s.dFEAT, s.dC1, s.dEC,
+                          c->Gp(SEG_R1B), c->Gp(SEG_R0B), c->Gp(SEG_C1B), c->Gp(SEG_C0B), c->dR2e, c->dRB2e, st));
+        TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, nullptr, 0, st));
+        TRY(gemm_wgrad(s.dU1, 256, 256, s.RIN, LD_RIN, LD_RIN, N, c->dR0e, LD_RIN, nullptr, 0, st));
+        TRY(gemm_wgrad(s.dFEAT, 256, 256, s.C1, 256, 256, N, c->Gp(SEG_C1W), 256, nullptr, 0, st));
+        TRY(gemm_wgrad(s.dC1, 256, 256, s.EC, 32, 32, N, c->Gp(SEG_C0W), 32, nullptr, 0, st));
+        TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dEC, 32, nullptr, 0, nullptr, 1, c->Gp(SEG_CEMB), (uint32_t)N, f.L, f.S, f.H, st));
+    } else if (scene) {
         // render net
         const bool fold = (P == 0) && gemm_tc_available();
         // fast mode: lin1 bias gradient, lin2 weight and bias gradients are taken inside rgb_head_bwd (no extra pass over U2 / dU2)
@@ -495,6 +506,8 @@ extern "C" int hsb_ctx_create(const hsb_step_cfg* cfg, float* params, float* gra
     c->dual_bwd = du ? atoi(du) != 0 : true;
     const char* ff = getenv("HSB_FUSED_FWD");
     c->fused_fwd = ff ? atoi(ff) != 0 : true;
+    const char* fb = getenv("HSB_FUSED_BWD");
+    c->fused_bwd = fb ? atoi(fb) != 0 : true;
     *out = reinterpret_cast<hsb_ctx*>(c);
     return HSB_OK;
 }
@@ -507,6 +520,7 @@ extern "C" int hsb_ctx_set_option(hsb_ctx* h, const char* name, int64_t value) {
     if (c && name && !strcmp(name, "block_tiles") && value >= 0) { c->block_tiles = value; return HSB_OK; }
     if (c && name && !strcmp(name, "dual_bwd")) { c->dual_bwd = value != 0; return HSB_OK; }
     if (c && name && !strcmp(name, "fused_fwd")) { c->fused_fwd = value != 0; return HSB_OK; }
+    if (c && name && !strcmp(name, "fused_bwd")) { c->fused_bwd = value != 0; return HSB_OK; }
     set_error("hsb_ctx_set_option: unknown option or bad value");
     return HSB_ERR_ARG;
 }

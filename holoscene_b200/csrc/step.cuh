@@ -93,4 +93,10 @@ int sdf_chain_tc(const float* H0, long long N, const float* W0e, const float* W1
                  const float* b0, const float* b1, const float* b2, int K, int Kp, float* H1, float* H2, float* SR, float* SDF, int* KS,
                  float* P2, float* P1, float* Q0, cudaStream_t stream, unsigned long long mask = ~0ull);
 
+// render_bwd_tc.cu: fused colour + render trunk of the scene pass backward (data-gradient chain, fast mode)
+bool render_bwd_tc_eligible();
+int render_bwd_tc(const float* dO, const float* U2, const float* U1, const float* C1, long long N, const float* R2e, const float* R1eT,
+                  const float* R0eT, const float* C1T, const float* C0T, float* dU2, float* dU1, float* dRIN, float* dFEAT, float* dC1,
+                  float* dEC, float* g_r1b, float* g_r0b, float* g_c1b, float* g_c0b, float* dR2e, float* dRB2e, cudaStream_t stream);
+
 }  // namespace hsb

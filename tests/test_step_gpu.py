@@ -770,3 +770,51 @@ def test_device_input_pipeline_feeds_the_train_step():
         losses.append(float(lo["loss"].detach()))
     st = step.graph_stats()
     assert all(np.isfinite(losses)) and st["captures"] >= 1 and st["replays"] + st["misses"] >= 2, st
+
+
+@pytest.mark.parametrize("K,R,S", [(3, 50, 33), (32, 300, 128), (21, 1024, 128)])
+def test_fused_render_backward_matches_layer_by_layer_path(K, R, S):
+    """Scene-pass backward, fast mode (option "fused_bwd"): the render-net / colour-MLP data-gradient chain
+    dO -> dU2 -> dU1 -> {dPE, dFEAT} -> dC1 -> dEC as ONE tcgen05 kernel (csrc/render_bwd_tc.cu, gradients handed from layer to layer
+    through tensor memory, ReLU masks from the stored activations, bias gradients / d R2 / d b2 accumulated in shared memory) against
+    the layer-by-layer launches.  Same operands, same accumulation order: every stored gradient tensor must agree bit for bit; the
+    parameter gradients agree up to the summation order of the atomics."""
+    from bench import model_conf
+    from holoscene_b200 import engine as E, synthetic
+    from holoscene_b200.network import HoloSceneNetwork
+    w = dict(name="t", R=R, K=K, N_samples=max(S - 34, 1), N_samples_eval=S, N_samples_extra=32, logmap=15)
+    gen = torch.Generator().manual_seed(R * S + K)
+    o = (torch.rand(R, 3, generator=gen) * 0.6 - 0.3).cuda()
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=gen), dim=1).cuda()
+    z = (torch.rand(R, S, generator=gen) * 2.0).sort(dim=1)[0].cuda().contiguous()
+    ds, rot = torch.ones(R, 1).cuda(), torch.eye(3).cuda()
+    cot = [torch.randn(R, 3, generator=gen).cuda(), torch.randn(R, 1, generator=gen).cuda(), torch.randn(R, 3, generator=gen).cuda(),
+           torch.randn(R, K, generator=gen).cuda()]
+    P = R * S
+    names = ("dU2", "dU1", "dRIN", "dFEAT", "dC1", "dEC")
+    res = {}
+    for fused in (0, 1):
+        torch.manual_seed(42)
+        m = HoloSceneNetwork(model_conf(w, precise=False, max_rays=max(R, 1024)))
+        m.load_state_dict(synthetic.perturb_state_dict(m.state_dict()))
+        m = m.cuda().train()
+        eng = m.engine()
+        eng.set_option("fused_bwd", fused)
+        m._attach_grads()
+        eng.prepare()
+        eng.render_forward(E.SLOT_MAIN, o, d, z, ds, rot)
+        for n in names:
+            eng.buffer("main." + n).fill_(float("nan"))
+        eng.render_backward(E.SLOT_MAIN, *cot)
+        eng.finish()
+        torch.cuda.synchronize()
+        bufs = {n: eng.buffer("main." + n)[:P].clone() for n in names}
+        bufs["dRIN"] = bufs["dRIN"][:, 310:337].clone()
+        res[fused] = (bufs, {n: p.grad.detach().clone() for n, p in m.named_parameters()})
+    for n in names:
+        a, b = res[1][0][n], res[0][0][n]
+        assert bool(torch.isfinite(a).all()), n
+        assert torch.equal(a, b), (n, float((a - b).abs().max()))
+    for n in res[0][1]:
+        e = common.rel_err(res[1][1][n].cpu(), res[0][1][n].cpu())
+        assert e < 2e-4, (n, e)
