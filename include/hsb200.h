@@ -136,7 +136,10 @@ void hsb_ctx_destroy(hsb_ctx* ctx);
 /* Tuning options.  "block_tiles": the ray passes run in blocks of whole rays of about this many 128-row tiles, so that a kernel finds
  * the tensor its predecessor wrote in L2 (0 = the whole batch as one block, the default: kernel-by-kernel launches make the blocked
  * step launch-bound, see csrc/step.cu; env HSB_BLOCK_TILES sets the initial value).  "dual_bwd": 1 (default in the fast mode) = chain +
- * SDF-net backward through the dual-accumulator layer kernel (csrc/dual_tc.cu), 0 = EPI_BWD_CHAIN + EPI_BWD_SP launches; env HSB_DUAL_BWD. */
+ * SDF-net backward through the dual-accumulator layer kernel (csrc/dual_tc.cu), 0 = EPI_BWD_CHAIN + EPI_BWD_SP launches; env HSB_DUAL_BWD.
+ * "fused_fwd": 1 (default in the fast mode) = scene-pass forward through the two TMEM-chained kernels (csrc/sdfchain_tc.cu,
+ * csrc/render_tc.cu), 0 = one launch per layer; env HSB_FUSED_FWD.  "fused_bwd": 1 = render / colour data-gradient chain of the backward
+ * as one kernel (csrc/render_bwd_tc.cu), default 0 (measured slower than the launches it replaces); env HSB_FUSED_BWD. */
 int hsb_ctx_set_option(hsb_ctx* ctx, const char* name, int64_t value);
 /* Introspection for tests: byte offset / rows / row stride (floats) of a named workspace buffer, e.g. "main.H1". */
 int hsb_ctx_buffer(hsb_ctx* ctx, const char* name, int64_t* offset_bytes, int64_t* rows, int64_t* ld);
