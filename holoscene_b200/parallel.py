@@ -17,9 +17,15 @@ def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def shard_batch(model_input: dict, ground_truth: dict, rank: int, world: int):
-    """Slice uv [1,R,2] and every ground-truth tensor [1,R,*] to this rank's rays; intrinsics / pose are shared."""
+def shard_batch(model_input: dict, ground_truth: dict, rank: int, world: int, allow_uneven: bool = False):
+    """Slice uv [1,R,2] and every ground-truth tensor [1,R,*] to this rank's rays; intrinsics / pose are shared.
+
+    The data-parallel step averages the ranks' gradients with equal weights (SUM all-reduce, 1/world in the fused Adam), which is the
+    gradient of the mean over all rays only for EQUAL shards: R must be divisible by the world size unless allow_uneven is set (the
+    caller then accepts a 1/shard-size re-weighting of the last rays)."""
     R = model_input["uv"].shape[1]
+    if R % world != 0 and not allow_uneven:
+        raise ValueError(f"{R} rays do not split into {world} equal shards: equal-weight gradient averaging needs equal shard sizes")
     lo, hi = shard_bounds(R, rank, world)
     mi = dict(model_input, uv=model_input["uv"][:, lo:hi].contiguous())
     gt = {k: (v[:, lo:hi].contiguous() if v.dim() >= 2 and v.shape[1] == R else v) for k, v in ground_truth.items()}
