@@ -26,6 +26,8 @@ struct Epi {
     int atomic2;                                           // out2[m % aux_rows] += (atomic) instead of store
     int round_out;                                         // store `out` rounded to TF32 (it is a later tcgen05 operand)
     float* colsum;                                         // optional [N]: += column sums of `out` (bias gradient), tcgen05 path only
+    const uint32_t* aux_bits;                              // EPI_BWD_RELU, tcgen05 path, N == 256: bit (n % 32) of word [m * 8 + n / 32] = [aux[m,n] > 0]
+                                                           // (written by the fused forward kernel); replaces the read of the [M,256] fp32 aux tensor
 };
 
 // ---- epilogue math -----------------------------------------------------------------------------------

@@ -100,7 +100,12 @@ __device__ __forceinline__ void tc_epilogue_chunk(const Epi& e, uint32_t taddr, 
             if (FULL || (col_ok && r < rows)) {
                 long long ma = ma0 + r;
                 while (ma >= wrap) ma -= wrap;
-                ax[i] = __ldg(reinterpret_cast<const float4*>(e.aux + ma * e.lda + n));
+                if (KIND == EPI_BWD_RELU && e.aux_bits) {      // ReLU mask as bits: 4 bytes per (row, 32 columns) instead of 128
+                    const uint32_t b = __ldg(e.aux_bits + ma * 8 + c) >> cl;
+                    ax[i] = make_float4((float)(b & 1u), (float)((b >> 1) & 1u), (float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
+                } else {
+                    ax[i] = __ldg(reinterpret_cast<const float4*>(e.aux + ma * e.lda + n));
+                }
             }
         }
     }

@@ -48,13 +48,14 @@ struct RenderTrunkArgs {
     int num_tiles;
     const float *c0b, *c1b, *r0b, *r1b, *r2b;
     float *C1, *RIN, *U1, *U2, *RGB;
+    uint32_t *MC1, *MU1;    // optional ReLU masks of C1 / U1 as bits: word [row * 8 + chunk], bit i = [value(row, 32 chunk + i) > 0]
 };
 
 // one 32-column chunk of a hidden layer: accumulator -> act(acc + bias), rounded to TF32, back into tensor memory (the next
 // layer's A operand), published on `ready`, then stored to HBM through the warp's transpose pad
 template <bool RELU>
 __device__ __forceinline__ void rt_hidden_chunk(uint32_t taddr, uint32_t sbias, uint64_t* ready, uint32_t pad, float* __restrict__ gout,
-                                                long long ld, long long row0, int rows, int col0, int lane) {
+                                                long long ld, long long row0, int rows, int col0, int lane, uint32_t* __restrict__ mask) {
     float v[32];
     tmem_ld32(taddr, v);
 #pragma unroll
@@ -71,6 +72,12 @@ __device__ __forceinline__ void rt_hidden_chunk(uint32_t taddr, uint32_t sbias, 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(ready);
+    if (RELU && mask && lane < rows) {                                  // the backward's ReLU' as one word per (row, chunk)
+        uint32_t w = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) w |= (v[i] > 0.0f ? 1u : 0u) << i;
+        mask[(row0 + lane) * 8 + (col0 >> 5)] = w;
+    }
     // HBM copy for the backward: lane = row in registers -> pad -> lane = (row quad, 4 columns): 128-byte row segments per store
 #pragma unroll
     for (int j = 0; j < 8; ++j) sts128(pad + (uint32_t)(lane * 36 + 4 * j) * 4u, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -246,8 +253,9 @@ render_trunk_tc_kernel(const __grid_constant__ CUtensorMap mapEC, const __grid_c
                 for (int j = 0; j < 2; ++j) {
                     const int c = g + 4 * j;
                     const uint32_t bias = sb + (uint32_t)(layer * 256 + c * 32) * 4u;
-                    if (layer == 1) rt_hidden_chunk<false>(base + (uint32_t)(c * 32), bias, chunk_ready + c, pad, gout, ld, row0, rows, c * 32, lane);
-                    else rt_hidden_chunk<true>(base + (uint32_t)(c * 32), bias, chunk_ready + c, pad, gout, ld, row0, rows, c * 32, lane);
+                    if (layer == 1) rt_hidden_chunk<false>(base + (uint32_t)(c * 32), bias, chunk_ready + c, pad, gout, ld, row0, rows, c * 32, lane, nullptr);
+                    else rt_hidden_chunk<true>(base + (uint32_t)(c * 32), bias, chunk_ready + c, pad, gout, ld, row0, rows, c * 32, lane,
+                                               layer == 0 ? a.MC1 : (layer == 2 ? a.MU1 : nullptr));
                 }
             }
             mbar_wait(acc_full, u & 1); ++u;     // colour head
@@ -290,7 +298,7 @@ bool render_trunk_tc_eligible() {
 // weights rounded to TF32.  Writes C1, RIN[:, 0:256] (the colour feature), U1, U2 (all TF32-rounded) and RGB [N,4].
 int render_trunk_tc(const float* EC, float* RIN, long long N, const float* C0e, const float* C1e, const float* R0e, const float* R1e,
                     const float* R2r, const float* c0b, const float* c1b, const float* r0b, const float* r1b, const float* r2b, float* C1,
-                    float* U1, float* U2, float* RGB, cudaStream_t stream) {
+                    float* U1, float* U2, float* RGB, cudaStream_t stream, uint32_t* MC1, uint32_t* MU1) {
     if (N <= 0) return HSB_OK;
     if (N > 0x7fffffffLL - TC_BM) { set_error("render_trunk: batch too large"); return HSB_ERR_ARG; }
     CUtensorMap mEC, mC0, mC1w, mR0f, mPE, mR0p, mR1, mR2;
@@ -309,7 +317,7 @@ int render_trunk_tc(const float* EC, float* RIN, long long N, const float* C0e, 
     RenderTrunkArgs a{};
     a.N = N; a.num_tiles = (int)((N + TC_BM - 1) / TC_BM);
     a.c0b = c0b; a.c1b = c1b; a.r0b = r0b; a.r1b = r1b; a.r2b = r2b;
-    a.C1 = C1; a.RIN = RIN; a.U1 = U1; a.U2 = U2; a.RGB = RGB;
+    a.C1 = C1; a.RIN = RIN; a.U1 = U1; a.U2 = U2; a.RGB = RGB; a.MC1 = MC1; a.MU1 = MU1;
     const unsigned grid = (unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms());
     render_trunk_tc_kernel<<<grid, RT_THREADS, RT_SMEM_BYTES, stream>>>(mEC, mC0, mC1w, mR0f, mPE, mR0p, mR1, mR2, a, idesc256, idesc16);
     return check_launch("render_trunk");

@@ -59,6 +59,8 @@ struct Slot {
     int* KS;
     float *EC, *C1, *RIN, *U1, *U2, *RGB, *W, *T, *WSUM, *WZSUM, *ZV, *DSCALE, *ROT;
     float *SDFB, *WB;   // Stage-2 subset pass: min over the object channels, bg_weights
+    uint32_t *MC1, *MU1;   // ReLU masks of C1 / U1 as bits (written by the fused render trunk; [points, 8] words)
+    bool masks_valid = false;
     // backward temporaries
     float *dO, *dS, *dG, *dQ0, *dQ1, *dA1x, *dQ2, *dA2x, *dA2, *dA1, *dH0E, *dU2, *dU1, *dRIN, *dFEAT, *dC1, *dEC;
     // forward-mode (tangent) buffers of the eikonal slot, rows m = d*N + p (d = 0..2)
@@ -134,6 +136,7 @@ static void carve_slot(Ctx* c, int idx, const char* pre, long long points, int m
         s.dO = carve(c, nm("dO"), N, 4, dry);      s.dU2 = carve(c, nm("dU2"), N, 256, dry); s.dU1 = carve(c, nm("dU1"), N, 256, dry);
         s.dRIN = carve(c, nm("dRIN"), N, LD_RIN, dry); s.dFEAT = carve(c, nm("dFEAT"), N, 256, dry);
         s.dC1 = carve(c, nm("dC1"), N, 256, dry);  s.dEC = carve(c, nm("dEC"), N, 32, dry);
+        s.MC1 = (uint32_t*)carve(c, nm("MC1"), N, 8, dry); s.MU1 = (uint32_t*)carve(c, nm("MU1"), N, 8, dry);
     }
 }
 
@@ -199,6 +202,8 @@ static Slot slot_block(const Slot& s, long long p0, long long r0, int Kp) {
     adv(b.dO, 4); adv(b.dS, Kp); adv(b.dG, 3); adv(b.dQ0, LD_H0); adv(b.dQ1, 256); adv(b.dA1x, 256); adv(b.dQ2, 256);
     adv(b.dA2x, 256); adv(b.dA2, 256); adv(b.dA1, 256); adv(b.dH0E, 32); adv(b.dU2, 256); adv(b.dU1, 256); adv(b.dRIN, LD_RIN);
     adv(b.dFEAT, 256); adv(b.dC1, 256); adv(b.dEC, 32);
+    if (b.MC1) b.MC1 += p0 * 8;
+    if (b.MU1) b.MU1 += p0 * 8;
     return b;
 }
 // rays per block (whole rays); block_tiles = 0 disables blocking
@@ -393,7 +398,7 @@ static int render_forward_block(Ctx* c, Slot& s, bool scene, const float* o, con
         TRY(hash_forward_ex(s.X, c->P(SEG_CEMB), c->hoffs, s.EC, 2, 32, nullptr, 0, (uint32_t)N, f.L, f.S, f.H, 1, rt, st));
         if (P == 0 && c->fused_fwd && render_trunk_tc_eligible())       // colour MLP + render net + sigmoid in ONE kernel (csrc/render_tc.cu)
             return render_trunk_tc(s.EC, s.RIN, N, c->C0e, c->C1e, c->R0e, c->R1e, c->R2r, c->P(SEG_C0B), c->P(SEG_C1B), c->P(SEG_R0B),
-                                   c->P(SEG_R1B), c->P(SEG_R2B), s.C1, s.U1, s.U2, s.RGB, st);
+                                   c->P(SEG_R1B), c->P(SEG_R2B), s.C1, s.U1, s.U2, s.RGB, st, s.MC1, s.MU1);
         Epi e = epi(EPI_BIAS_RELU, s.C1, 256, rt); e.bias = c->P(SEG_C0B);
         TRY(gemm_tn(s.EC, 32, c->C0e, 32, N, 256, 32, e, P, st));
         e = epi(EPI_BIAS, s.RIN, LD_RIN, rt); e.bias = c->P(SEG_C1B);       // colour feature = columns [0,256) of the render-net input row
@@ -431,6 +436,7 @@ static int render_backward_block(Ctx* c, Slot& s, bool scene, cudaStream_t st) {
                                 fold ? c->dRB2e : nullptr, st));
         if (!fold) TRY(gemm_wgrad(s.dO, 4, 4, s.U2, 256, 256, N, c->dR2e, 256, c->dRB2e, P, st));
         Epi e = epi(EPI_BWD_RELU, s.dU1, 256, rt); e.aux = s.U1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_R0B) : nullptr;
+        e.aux_bits = s.masks_valid ? s.MU1 : nullptr;     // ReLU' from the bit mask the fused forward wrote: 16 MB instead of 537 MB
         TRY(gemm_tn(s.dU2, 256, c->R1eT, 256, N, 256, 256, e, P, st));
         TRY(gemm_wgrad(s.dU2, 256, 256, s.U1, 256, 256, N, c->dR1e, 256, fold ? nullptr : c->Gp(SEG_R1B), P, st));
         e = epi(EPI_NONE, s.dRIN + RIN_PEG, LD_RIN);
@@ -441,6 +447,7 @@ static int render_backward_block(Ctx* c, Slot& s, bool scene, cudaStream_t st) {
         // colour-feature MLP + colour hash grid
         TRY(gemm_wgrad(s.dFEAT, 256, 256, s.C1, 256, 256, N, c->Gp(SEG_C1W), 256, fold ? nullptr : c->Gp(SEG_C1B), P, st));
         e = epi(EPI_BWD_RELU, s.dC1, 256, rt); e.aux = s.C1; e.lda = 256; e.colsum = fold ? c->Gp(SEG_C0B) : nullptr;
+        e.aux_bits = s.masks_valid ? s.MC1 : nullptr;
         TRY(gemm_tn(s.dFEAT, 256, c->C1T, 256, N, 256, 256, e, P, st));
         TRY(gemm_wgrad(s.dC1, 256, 256, s.EC, 32, 32, N, c->Gp(SEG_C0W), 32, fold ? nullptr : c->Gp(SEG_C0B), P, st));
         e = epi(EPI_NONE, s.dEC, 32);
@@ -639,6 +646,7 @@ extern "C" int hsb_render_forward(hsb_ctx* h, int32_t slot_id, const float* o, c
     if (N > s.cap_points || R > s.cap_rays) { set_error("hsb_render_forward: batch exceeds slot capacity"); return HSB_ERR_ARG; }
     const bool scene = slot_id == HSB_SLOT_MAIN;
     s.N = N; s.R = R; s.S = S; s.nseed = 1; s.mode = scene ? 0 : 1;
+    s.masks_valid = scene && !c->cfg.precise && c->fused_fwd && render_trunk_tc_eligible();
     TRYCUDA(cudaMemcpyAsync(s.ZV, z, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TRYCUDA(cudaMemcpyAsync(s.DSCALE, depth_scale, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TRYCUDA(cudaMemcpyAsync(s.ROT, rot, 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));

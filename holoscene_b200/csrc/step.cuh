@@ -85,7 +85,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, long long n, float
 bool render_trunk_tc_eligible();
 int render_trunk_tc(const float* EC, float* RIN, long long N, const float* C0e, const float* C1e, const float* R0e, const float* R1e,
                     const float* R2r, const float* c0b, const float* c1b, const float* r0b, const float* r1b, const float* r2b, float* C1,
-                    float* U1, float* U2, float* RGB, cudaStream_t stream);
+                    float* U1, float* U2, float* RGB, cudaStream_t stream, uint32_t* MC1 = nullptr, uint32_t* MU1 = nullptr);
 
 // sdfchain_tc.cu: fused SDF trunk + d sdf / d x chain of the scene pass forward (fast mode)
 bool sdf_chain_tc_eligible(int K);
