@@ -464,7 +464,9 @@ extern "C" int hsb_hash_backward_fused(const float* x_world, const int32_t* offs
                                        cudaStream_t stream) {
     if (B == 0) return HSB_OK;
     if (!x_world || !offsets || !grad_embeddings || L == 0 || L > 32 || (q0E && !dg && nseed != 3)) { set_error("hsb_hash_backward_fused: bad argument"); return HSB_ERR_ARG; }
-    hash_bwd_fused_kernel<<<cdiv(B, HBF_THREADS), HBF_THREADS, 0, stream>>>(x_world, offsets, dE, e_point_stride, q0E, q_point_stride, dg, nseed,
+    // small batches (the eikonal pass: 16 k points, three seed rows each): one warp per CTA, so that every SM gets work
+    const int threads = B <= 65536u ? 32 : HBF_THREADS;
+    hash_bwd_fused_kernel<<<cdiv(B, threads), threads, 0, stream>>>(x_world, offsets, dE, e_point_stride, q0E, q_point_stride, dg, nseed,
                                                     reinterpret_cast<float2*>(grad_embeddings), B, L, S, H);
     return check_launch("hsb_hash_backward_fused");
 }

@@ -90,6 +90,8 @@ struct Ctx {
     // fast mode: render / colour data-gradient chain of the backward as one kernel (csrc/render_bwd_tc.cu).  OFF by default: bit-exact,
     // but measured 1.33 ms against 1.24 ms for the six launches it replaces (one tile in flight per SM)
     bool fused_bwd = false;
+    bool pads_zeroed = false;    // the zero padding of the derived weights has been written (first hsb_prepare)
+    bool relu_bits = true;       // fast mode: the backward takes ReLU' from the bit masks the fused render trunk wrote (else from U1 / C1)
     float* P(int seg) const { return params + off[seg]; }
     float* Gp(int seg) const { return grads + off[seg]; }
 };
@@ -530,6 +532,7 @@ extern "C" int hsb_ctx_set_option(hsb_ctx* h, const char* name, int64_t value) {
     if (c && name && !strcmp(name, "dual_bwd")) { c->dual_bwd = value != 0; return HSB_OK; }
     if (c && name && !strcmp(name, "fused_fwd")) { c->fused_fwd = value != 0; return HSB_OK; }
     if (c && name && !strcmp(name, "fused_bwd")) { c->fused_bwd = value != 0; return HSB_OK; }
+    if (c && name && !strcmp(name, "relu_bits")) { c->relu_bits = value != 0; return HSB_OK; }
     set_error("hsb_ctx_set_option: unknown option or bad value");
     return HSB_ERR_ARG;
 }
@@ -549,11 +552,16 @@ extern "C" int hsb_prepare(hsb_ctx* h, cudaStream_t st) {
     CTX_OR_FAIL(c, "hsb_prepare");
     const int rt = c->rtf();
     TRYCUDA(cudaMemsetAsync(c->dwe_begin, 0, c->dwe_bytes, st));
-    TRYCUDA(cudaMemsetAsync(c->W0eT, 0, (size_t)LD_H0 * 256 * sizeof(float), st));
-    TRYCUDA(cudaMemsetAsync(c->R0eT, 0, (size_t)LD_RIN * 256 * sizeof(float), st));
-    TRYCUDA(cudaMemsetAsync(c->W2e, 0, (size_t)c->Kp * 256 * sizeof(float), st));
-    TRYCUDA(cudaMemsetAsync(c->W2eT, 0, (size_t)c->Kp * 256 * sizeof(float), st));
-    TRYCUDA(cudaMemsetAsync(c->R2e, 0, (size_t)4 * 256 * sizeof(float), st));
+    if (!c->pads_zeroed) {
+        // zero padding of the derived weights (rows / columns beyond the real extents): written by nothing else, so once is enough
+        TRYCUDA(cudaMemsetAsync(c->W0eT, 0, (size_t)LD_H0 * 256 * sizeof(float), st));
+        TRYCUDA(cudaMemsetAsync(c->R0eT, 0, (size_t)LD_RIN * 256 * sizeof(float), st));
+        TRYCUDA(cudaMemsetAsync(c->W2e, 0, (size_t)c->Kp * 256 * sizeof(float), st));
+        TRYCUDA(cudaMemsetAsync(c->W2eT, 0, (size_t)c->Kp * 256 * sizeof(float), st));
+        TRYCUDA(cudaMemsetAsync(c->R2e, 0, (size_t)4 * 256 * sizeof(float), st));
+        TRYCUDA(cudaMemsetAsync(c->R2r, 0, (size_t)16 * 256 * sizeof(float), st));
+        c->pads_zeroed = true;
+    }
     TRY(launch_wn_forward(c->P(SEG_L0V), c->P(SEG_L0G), 256, 71, c->W0e, LD_H0, c->W0eT, 256, rt, st));
     TRY(launch_wn_forward(c->P(SEG_L1V), c->P(SEG_L1G), 256, 256, c->W1e, 256, c->W1eT, 256, rt, st));
     TRY(launch_wn_forward(c->P(SEG_L2V), c->P(SEG_L2G), c->K, 256, c->W2e, 256, c->W2eT, c->Kp, rt, st));
@@ -561,7 +569,6 @@ extern "C" int hsb_prepare(hsb_ctx* h, cudaStream_t st) {
     TRY(launch_wn_forward(c->P(SEG_R1V), c->P(SEG_R1G), 256, 256, c->R1e, 256, c->R1eT, 256, rt, st));
     TRY(launch_wn_forward(c->P(SEG_R2V), c->P(SEG_R2G), 3, 256, c->R2e, 256, nullptr, 0, 0, st));
     if (rt) {
-        TRYCUDA(cudaMemsetAsync(c->R2r, 0, (size_t)16 * 256 * sizeof(float), st));
         TRY(launch_wn_forward(c->P(SEG_R2V), c->P(SEG_R2G), 3, 256, c->R2r, 256, nullptr, 0, 1, st));
     }
     TRY(launch_transpose(c->P(SEG_C0W), 256, 32, c->C0T, 256, c->C0e, rt, st));
@@ -646,7 +653,7 @@ extern "C" int hsb_render_forward(hsb_ctx* h, int32_t slot_id, const float* o, c
     if (N > s.cap_points || R > s.cap_rays) { set_error("hsb_render_forward: batch exceeds slot capacity"); return HSB_ERR_ARG; }
     const bool scene = slot_id == HSB_SLOT_MAIN;
     s.N = N; s.R = R; s.S = S; s.nseed = 1; s.mode = scene ? 0 : 1;
-    s.masks_valid = scene && !c->cfg.precise && c->fused_fwd && render_trunk_tc_eligible();
+    s.masks_valid = scene && !c->cfg.precise && c->fused_fwd && c->relu_bits && render_trunk_tc_eligible();
     TRYCUDA(cudaMemcpyAsync(s.ZV, z, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TRYCUDA(cudaMemcpyAsync(s.DSCALE, depth_scale, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TRYCUDA(cudaMemcpyAsync(s.ROT, rot, 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -626,18 +626,6 @@ def test_fused_forward_kernels_match_layer_by_layer_path(K, R, S):
         outs = [t.clone() for t in eng.render_forward(E.SLOT_MAIN, o, d, z, ds, rot)]
         torch.cuda.synchronize()
         res[fused] = (outs, {n: eng.buffer("main." + n)[:P].clone() for n in names})
-        # the backward after the fused forward takes its ReLU masks from the bit words the forward wrote (csrc/render_tc.cu ->
-        # EPI_BWD_RELU aux_bits) instead of re-reading U1 / C1: same gradients, bit for bit
-        gen_b = torch.Generator().manual_seed(7)
-        cot = [torch.randn(R, 3, generator=gen_b).cuda(), torch.randn(R, 1, generator=gen_b).cuda(), torch.randn(R, 3, generator=gen_b).cuda(),
-               torch.randn(R, K, generator=gen_b).cuda()]
-        for n in ("dU1", "dC1", "dEC"):
-            eng.buffer("main." + n).fill_(float("nan"))
-        eng.render_backward(E.SLOT_MAIN, *cot)
-        torch.cuda.synchronize()
-        res[fused][1].update({n: eng.buffer("main." + n)[:P].clone() for n in ("dU1", "dC1", "dEC")})
-    for n in ("dU1", "dC1", "dEC"):
-        assert bool(torch.isfinite(res[1][1][n]).all()) and torch.equal(res[1][1][n], res[0][1][n]), n
     ks_a, ks_b = res[1][1]["KS"].view(torch.int32), res[0][1]["KS"].view(torch.int32)
     assert torch.equal(ks_a, ks_b) and (K == 1 or int(ks_b.unique().numel()) > 1)
     for n in names:
