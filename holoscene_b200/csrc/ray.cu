@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_fwd_kernel(Composite
             const float T2 = expf(-(carry2 + excl2));
             w2 = ok ? (1.0f - expf(-E2)) * T2 : 0.0f;
             carry2 += __shfl_sync(0xffffffffu, incl2, 31);
+            if (ok && a.mode == 2 && a.T2) a.T2[p0 + i] = T2;
         }
         sD[lane] = delta; sT[lane] = T; sW2[lane] = w2;
         if (ok) {
@@ -182,6 +183,9 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_fwd_kernel(Composite
 //                 mode 1: everything lands in channel 0)
 //   dGn  [P,3]  = dL/d(gradient) through the normal map
 //   dbeta (atomic) = dL/d beta
+// mode 2 (Stage-2 subset pass): colour / depth / normals / the raw sums hang on the bg_weights (SDFB, T, WB; their sdf gradient lands
+// in the arg-min channel KSB of the object set), the per-ray opacity on the subset weights (SDF, T2, W; channel KS): two reverse scans.
+// The semantic composite is not differentiated (no Stage-2 loss reads it, training/holoscene_train_post.py:558-631).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32 * CMP_WARPS) composite_bwd_kernel(CompositeArgs a, CompositeGrads g) {
     extern __shared__ float cmp_smem[];
@@ -197,10 +201,15 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_bwd_kernel(Composite
     const float* z = a.Z + (long long)r * S;
     const long long p0 = (long long)r * S;
     const bool per_object = a.mode == 0 && g.d_opacity != nullptr;
+    const bool m2 = a.mode == 2;
 
     float drgb[3] = {0.f, 0.f, 0.f}, dn[3] = {0.f, 0.f, 0.f}, ddepth = 0.f;
-    if (g.d_rgb_values && a.mode == 0) { drgb[0] = g.d_rgb_values[r * 3]; drgb[1] = g.d_rgb_values[r * 3 + 1]; drgb[2] = g.d_rgb_values[r * 3 + 2]; }
+    if (g.d_rgb_values && a.mode != 1) { drgb[0] = g.d_rgb_values[r * 3]; drgb[1] = g.d_rgb_values[r * 3 + 1]; drgb[2] = g.d_rgb_values[r * 3 + 2]; }
     if (g.d_depth_values) ddepth = g.d_depth_values[r] * a.depth_scale[r];
+    const float dws = (m2 && g.d_wsum) ? g.d_wsum[r] : 0.0f, dwz = (m2 && g.d_wzsum) ? g.d_wzsum[r] : 0.0f;
+    const float dop2 = (m2 && g.d_opacity) ? g.d_opacity[r] : 0.0f;
+    const float rgb_to_w = (m2 && g.detach_rgb) ? 0.0f : 1.0f;
+    float carry2 = 0.0f;  // mode 2: the same suffix sum for the subset weights
     if (g.d_normal_map) {   // dn = rot^T d_out
         const float* d = g.d_normal_map + r * 3;
 #pragma unroll
@@ -227,22 +236,22 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_bwd_kernel(Composite
             const float zi = z[i];
             delta = (i + 1 < S) ? z[i + 1] - zi : 1e10f;
             T = a.T[p0 + i];
-            w = a.W[p0 + i];
+            w = m2 ? a.WB[p0 + i] : a.W[p0 + i];
         }
         sD[lane] = delta; sT[lane] = T;
         __syncwarp();
         if (ok) {
             const float zi = z[i];
-            s_w = (a.mode == 1) ? tile[lane * ldt] : a.SDF[p0 + i];
+            s_w = (a.mode == 1) ? tile[lane * ldt] : (m2 ? a.SDFB[p0 + i] : a.SDF[p0 + i]);
             E = delta * laplace_density(s_w, beta);
             const float* gg = a.G + (p0 + i) * 3;
             const float rn = sqrtf(gg[0] * gg[0] + gg[1] * gg[1] + gg[2] * gg[2]);
             const float den = rn + 1e-6f;
             const float gv = gg[0] * dn[0] + gg[1] * dn[1] + gg[2] * dn[2];
-            ai = ddepth * (zi * Wt - Nz) / (Wt * Wt) + gv / den;
+            ai = ddepth * (zi * Wt - Nz) / (Wt * Wt) + gv / den + dws + dwz * zi;
             if (a.mode != 1) {
                 const float4 c = __ldg(reinterpret_cast<const float4*>(a.RGB) + p0 + i);
-                ai += drgb[0] * c.x + drgb[1] * c.y + drgb[2] * c.z;
+                ai += rgb_to_w * (drgb[0] * c.x + drgb[1] * c.y + drgb[2] * c.z);
                 float4 o;
                 o.x = w * drgb[0] * c.x * (1.0f - c.x);
                 o.y = w * drgb[1] * c.y * (1.0f - c.y);
@@ -300,8 +309,28 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_bwd_kernel(Composite
             const float dsig = dE * delta;                         // dL/d sigma(scene)
             const float dsdf = (dsig != 0.0f) ? dsig * dsg : 0.0f;
             dbeta += (dsig != 0.0f) ? dsig * dbt : 0.0f;
-            const int kk = (a.mode == 1) ? 0 : a.KS[p0 + i];
+            const int kk = (a.mode == 1) ? 0 : (m2 ? a.KSB[p0 + i] : a.KS[p0 + i]);
             tile[lane * ldt + kk] = rtf32(tile[lane * ldt + kk] + dsdf, g.rtf);
+        }
+        if (dop2 != 0.0f) {                                          // warp-uniform: one value per ray
+            const float w2 = ok ? a.W[p0 + i] : 0.0f;
+            const float sfx2 = warp_scan_incl_rev(dop2 * w2, lane);
+            float after2 = __shfl_down_sync(0xffffffffu, sfx2, 1);
+            if (lane == 31) after2 = 0.0f;
+            after2 += carry2;
+            carry2 += __shfl_sync(0xffffffffu, sfx2, 0);
+            if (ok) {
+                const float s2 = a.SDF[p0 + i];
+                const float E2 = delta * laplace_density(s2, beta);
+                const float dE2 = dop2 * a.T2[p0 + i] * expf(-E2) - after2;
+                float dsg, dbt;
+                laplace_grads(s2, beta, dsg, dbt);
+                const float dsig = dE2 * delta;
+                const float dsdf = (dsig != 0.0f) ? dsig * dsg : 0.0f;
+                dbeta += (dsig != 0.0f) ? dsig * dbt : 0.0f;
+                const int k2 = a.KS[p0 + i];
+                tile[lane * ldt + k2] = rtf32(tile[lane * ldt + k2] + dsdf, g.rtf);
+            }
         }
         __syncwarp();
         {   // the chunk's dS rows leave as one contiguous run of 16-byte stores

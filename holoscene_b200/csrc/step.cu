@@ -58,7 +58,9 @@ struct Slot {
     float *X, *H0, *DY, *H1, *H2, *SR, *SDF, *P2, *P1, *Q0, *G;
     int* KS;
     float *EC, *C1, *RIN, *U1, *U2, *RGB, *W, *T, *WSUM, *WZSUM, *ZV, *DSCALE, *ROT;
-    float *SDFB, *WB;   // Stage-2 subset pass: min over the object channels, bg_weights
+    float *SDFB, *WB, *TS;   // Stage-2 subset pass: min over the object channels, bg_weights, transmittance of the subset weights
+    int* KSB;                // ... and the arg-min channel of the object set
+    bool detach_rgb = false; // ... colour path detached from the geometry (the *_detach_rgb_for_geometry variants)
     uint32_t *MC1, *MU1;   // ReLU masks of C1 / U1 as bits (written by the fused render trunk; [points, 8] words)
     bool masks_valid = false;
     // backward temporaries
@@ -82,7 +84,7 @@ struct Ctx {
     // effective-weight gradient accumulators (zeroed by hsb_prepare)
     float *dW0e, *dW1e, *dW2e, *dB2e, *dR0e, *dR1e, *dR2e, *dRB2e;
     char* dwe_begin; size_t dwe_bytes;
-    Slot slot[3];
+    Slot slot[HSB_NUM_SLOTS];
     Slot scratch;   // X, H0, H1, H2, SR only: hsb_sdf_values between a slot's forward and its backward
     long long block_tiles = 0;   // L2 blocking of the ray passes: 128-row tiles per block of rays (0 = one block)
     bool dual_bwd = true;        // fast mode: chain + SDF-net backward through the dual-accumulator layer kernel (csrc/dual_tc.cu)
@@ -130,7 +132,8 @@ static void carve_slot(Ctx* c, int idx, const char* pre, long long points, int m
         s.W = carve(c, nm("W"), N, 1, dry);    s.T = carve(c, nm("T"), N, 1, dry);        s.ZV = carve(c, nm("ZV"), N, 1, dry);
         s.WSUM = carve(c, nm("WSUM"), rays, 1, dry); s.WZSUM = carve(c, nm("WZSUM"), rays, 1, dry);
         s.DSCALE = carve(c, nm("DSCALE"), rays, 1, dry); s.ROT = carve(c, nm("ROT"), 16, 1, dry);
-        s.SDFB = carve(c, nm("SDFB"), N, 1, dry);  s.WB = carve(c, nm("WB"), N, 1, dry);
+        s.SDFB = carve(c, nm("SDFB"), N, 1, dry);  s.WB = carve(c, nm("WB"), N, 1, dry);  s.TS = carve(c, nm("TS"), N, 1, dry);
+        s.KSB = (int*)carve(c, nm("KSB"), N, 1, dry);
     }
     if (color) {
         s.EC = carve(c, nm("EC"), N, 32, dry);     s.C1 = carve(c, nm("C1"), N, 256, dry);   s.RIN = carve(c, nm("RIN"), N, LD_RIN, dry);
@@ -172,6 +175,11 @@ static void carve_all(Ctx* c, bool dry) {
     carve_slot(c, HSB_SLOT_MAIN, "main", c->cfg.max_points, 1, c->cfg.max_rays, true, false, dry);
     carve_slot(c, HSB_SLOT_EIK, "eik", c->cfg.max_eik_points, 3, 0, false, true, dry);
     carve_slot(c, HSB_SLOT_BG, "bg", c->cfg.max_bg_points, 1, c->cfg.max_bg_rays, false, false, dry);
+    // Stage-2 slots (capacity 0 = unused): a second scene slot, so that a subset pass can be recorded between the scene pass's forward
+    // and its backward, and two point slots for the point-constraint losses (model/network.py:973-1013)
+    carve_slot(c, HSB_SLOT_AUX, "aux", c->cfg.max_aux_points, 1, c->cfg.max_aux_rays, true, false, dry);
+    carve_slot(c, HSB_SLOT_PTS, "pts", c->cfg.max_pts_points, 3, 0, false, true, dry);
+    carve_slot(c, HSB_SLOT_PTS2, "pts2", c->cfg.max_pts_points, 3, 0, false, true, dry);
     carve_scratch(c, c->cfg.max_points, dry);
 }
 
@@ -197,7 +205,8 @@ static Slot slot_block(const Slot& s, long long p0, long long r0, int Kp) {
     if (b.KS) b.KS += p0;
     adv(b.P2, 256); adv(b.P1, 256); adv(b.Q0, LD_H0); adv(b.G, 3);
     adv(b.EC, 32); adv(b.C1, 256); adv(b.RIN, LD_RIN); adv(b.U1, 256); adv(b.U2, 256); adv(b.RGB, 4);
-    adv(b.W, 1); adv(b.T, 1); adv(b.ZV, 1); adv(b.SDFB, 1); adv(b.WB, 1);
+    adv(b.W, 1); adv(b.T, 1); adv(b.ZV, 1); adv(b.SDFB, 1); adv(b.WB, 1); adv(b.TS, 1);
+    if (b.KSB) b.KSB += p0;
     if (b.WSUM) b.WSUM += r0;
     if (b.WZSUM) b.WZSUM += r0;
     if (b.DSCALE) b.DSCALE += r0;
@@ -373,6 +382,7 @@ static CompositeArgs composite_args(Ctx* c, Slot& s, int mode) {
     a.depth_scale = s.DSCALE; a.rot = s.ROT; a.beta_param = c->P(SEG_BETA);
     a.beta_min = c->cfg.beta_min; a.sigmoid_scale = c->cfg.sigmoid_scale;
     a.W = s.W; a.T = s.T; a.wsum = s.WSUM; a.wzsum = s.WZSUM;
+    a.SDFB = s.SDFB; a.WB = s.WB; a.KSB = s.KSB; a.T2 = s.TS;
     return a;
 }
 
@@ -415,7 +425,7 @@ static int render_forward_block(Ctx* c, Slot& s, bool scene, const float* o, con
 }
 
 // per-point part of the ray pass backward on one block of rays (after its composite_bwd)
-static int render_backward_block(Ctx* c, Slot& s, bool scene, cudaStream_t st) {
+static int render_backward_block(Ctx* c, Slot& s, bool scene, cudaStream_t st, bool rin_grad = true) {
     const hsb_step_cfg& f = c->cfg;
     const int P = f.precise;
     const int rt = c->rtf();
@@ -456,8 +466,9 @@ static int render_backward_block(Ctx* c, Slot& s, bool scene, cudaStream_t st) {
         TRY(gemm_tn(s.dC1, 256, c->C0T, 256, N, 32, 256, e, P, st));
         TRY(hsb_hash_backward_fused(s.X, c->hoffs, s.dEC, 32, nullptr, 0, nullptr, 1, c->Gp(SEG_CEMB), (uint32_t)N, f.L, f.S, f.H, st));
     }
-    if (P == 0 && c->dual_bwd && gemm_dual_tc_eligible()) return chain_sdf_backward_dual(c, s, N, scene, st);
-    TRY(chain_backward(c, s, N, 1, scene, st));
+    // rin_grad = false: the render net saw a detached gradient (no d PE4(grad) term into the chain)
+    if (P == 0 && c->dual_bwd && gemm_dual_tc_eligible()) return chain_sdf_backward_dual(c, s, N, scene && rin_grad, st);
+    TRY(chain_backward(c, s, N, 1, scene && rin_grad, st));
     TRY(sdf_backward(c, s, N, true, st));
     return HSB_OK;
 }
@@ -479,7 +490,8 @@ extern "C" int hsb_param_layout(int32_t K, int64_t table_rows, int64_t* offsets_
 
 static int validate_cfg(const hsb_step_cfg* cfg) {
     if (!cfg || cfg->K < 1 || cfg->K > HSB_MAX_K || cfg->L != 16 || cfg->table_rows < 1 || cfg->max_points < 1 ||
-        cfg->max_rays < 1 || cfg->max_eik_points < 0 || cfg->max_bg_points < 0) {
+        cfg->max_rays < 1 || cfg->max_eik_points < 0 || cfg->max_bg_points < 0 || cfg->max_aux_points < 0 || cfg->max_aux_rays < 0 ||
+        cfg->max_pts_points < 0) {
         set_error("hsb_step_cfg: unsupported configuration (need 1 <= K <= 64, L == 16, positive capacities)");
         return HSB_ERR_ARG;
     }
@@ -589,6 +601,8 @@ extern "C" int hsb_finish(hsb_ctx* h, cudaStream_t st) {
     // padded bias accumulators -> exact-size bias gradients
     TRY(launch_add_into(c->dB2e, c->Gp(SEG_L2B), c->K, st));
     TRY(launch_add_into(c->dRB2e, c->Gp(SEG_R2B), 3, st));
+    // consumed: a second hsb_finish in the same step (one per autograd node that ran a backward) then adds only what came after
+    TRYCUDA(cudaMemsetAsync(c->dwe_begin, 0, c->dwe_bytes, st));
     return HSB_OK;
 }
 
@@ -704,13 +718,14 @@ extern "C" int hsb_sdf_grid(hsb_ctx* h, const float* lo_host, const float* hi_ho
 // pass with the min / arg-min / gradient taken over the SUBSET channels (mask_subset) and a second, "background" set of weights
 // from the min over the object channels (mask_obj) that composites colour, depth and normals.  Forward only: the MAIN slot's
 // recorded forward is invalidated (hsb_render_backward refuses until the next hsb_render_forward).
-extern "C" int hsb_render_forward_subset(hsb_ctx* h, const float* o, const float* d, const float* z, int32_t R, int32_t S,
+extern "C" int hsb_render_forward_subset(hsb_ctx* h, int32_t slot_id, const float* o, const float* d, const float* z, int32_t R, int32_t S,
                                          const float* depth_scale, const float* rot, uint64_t mask_subset, uint64_t mask_obj,
-                                         float* rgb_values, float* depth_values, float* normal_map, float* opacity, float* semantic,
-                                         cudaStream_t st) {
+                                         int32_t detach_rgb, float* rgb_values, float* depth_values, float* normal_map, float* opacity,
+                                         float* semantic, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     CTX_OR_FAIL(c, "hsb_render_forward_subset");
-    Slot& s = c->slot[HSB_SLOT_MAIN];
+    if (slot_id != HSB_SLOT_MAIN && slot_id != HSB_SLOT_AUX) { set_error("hsb_render_forward_subset: bad slot"); return HSB_ERR_ARG; }
+    Slot& s = c->slot[slot_id];
     const long long N = (long long)R * S;
     if (N > s.cap_points || R > s.cap_rays) { set_error("hsb_render_forward_subset: batch exceeds slot capacity"); return HSB_ERR_ARG; }
     if (!mask_subset || !mask_obj || (c->K < 64 && ((mask_subset | mask_obj) >> c->K))) {
@@ -721,17 +736,39 @@ extern "C" int hsb_render_forward_subset(hsb_ctx* h, const float* o, const float
         set_error("hsb_render_forward_subset: null pointer");
         return HSB_ERR_ARG;
     }
-    s.N = N; s.R = R; s.S = S; s.nseed = 1; s.mode = 2;
+    s.N = N; s.R = R; s.S = S; s.nseed = 1; s.mode = 2; s.detach_rgb = detach_rgb != 0;
+    s.masks_valid = !c->cfg.precise && c->fused_fwd && c->relu_bits && render_trunk_tc_eligible();
     TRYCUDA(cudaMemcpyAsync(s.ZV, z, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TRYCUDA(cudaMemcpyAsync(s.DSCALE, depth_scale, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TRYCUDA(cudaMemcpyAsync(s.ROT, rot, 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TRY(render_forward_block(c, s, true, o, d, z, st, mask_subset));
-    TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, -1, s.SDFB, nullptr, st, mask_obj));
+    TRY(launch_sdf_min(s.SR, N, c->K, c->Kp, -1, s.SDFB, s.KSB, st, mask_obj));
     CompositeArgs a = composite_args(c, s, 2);
-    a.SDFB = s.SDFB; a.WB = s.WB; a.mask = mask_subset;
+    a.mask = mask_subset;
     a.rgb_values = rgb_values; a.depth_values = depth_values; a.normal_map = normal_map; a.opacity = opacity; a.semantic = semantic;
     TRY(launch_composite_fwd(a, st));
-    s.N = 0;                                        // forward only
+    return HSB_OK;
+}
+
+// Backward of the subset pass from d(loss)/d(per-ray outputs) (NULL = zero): rgb_values [R,3], depth_values [R] (the weight-normalised
+// depth), normal_map [R,3], opacity [R] (sum of the subset weights), and the two raw sums of the near/far variant, sum bg_w [R] and
+// sum bg_w z [R] ("<slot>.WSUM" / ".WZSUM").  The semantic composite is not differentiated.
+extern "C" int hsb_render_backward_subset(hsb_ctx* h, int32_t slot_id, const float* d_rgb_values, const float* d_depth_values,
+                                          const float* d_normal_map, const float* d_opacity, const float* d_wsum, const float* d_wzsum,
+                                          cudaStream_t st) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    CTX_OR_FAIL(c, "hsb_render_backward_subset");
+    if (slot_id != HSB_SLOT_MAIN && slot_id != HSB_SLOT_AUX) { set_error("hsb_render_backward_subset: bad slot"); return HSB_ERR_ARG; }
+    Slot& s = c->slot[slot_id];
+    if (s.N == 0 || s.mode != 2) { set_error("hsb_render_backward_subset: no subset forward recorded in this slot"); return HSB_ERR_ARG; }
+    CompositeArgs a = composite_args(c, s, 2);
+    CompositeGrads g{};
+    g.d_rgb_values = d_rgb_values; g.d_depth_values = d_depth_values; g.d_normal_map = d_normal_map; g.d_opacity = d_opacity;
+    g.d_wsum = d_wsum; g.d_wzsum = d_wzsum; g.detach_rgb = s.detach_rgb ? 1 : 0;
+    g.dO = s.dO; g.dS = s.dS; g.dGn = s.dG; g.d_beta = c->Gp(SEG_BETA); g.rtf = c->rtf();
+    TRY(launch_composite_bwd(a, g, st));
+    TRY(render_backward_block(c, s, true, st, !s.detach_rgb));
+    s.N = 0;
     return HSB_OK;
 }
 
@@ -741,7 +778,7 @@ extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_r
     CTX_OR_FAIL(c, "hsb_render_backward");
     if (slot_id != HSB_SLOT_MAIN && slot_id != HSB_SLOT_BG) { set_error("hsb_render_backward: bad slot"); return HSB_ERR_ARG; }
     Slot& s = c->slot[slot_id];
-    if (s.N == 0) { set_error("hsb_render_backward: no forward recorded in this slot"); return HSB_ERR_ARG; }
+    if (s.N == 0 || s.mode == 2) { set_error("hsb_render_backward: no (scene / bg) forward recorded in this slot"); return HSB_ERR_ARG; }
     const bool scene = slot_id == HSB_SLOT_MAIN;
     const int R = s.R, S = s.S, K = c->K;
     const int rb = block_rays(c->block_tiles, R, S);
@@ -764,12 +801,20 @@ extern "C" int hsb_render_backward(hsb_ctx* h, int32_t slot_id, const float* d_r
 
 // Eikonal pass (network.py:843-866): K per-channel gradients + the min-SDF gradient at Ne points,
 // stacked [(K+1)*Ne, 3] (channel-major, min last), plus sample_sdf [Ne,K] and sample_minsdf [Ne].
+static bool point_slot(int32_t id) { return id == HSB_SLOT_EIK || id == HSB_SLOT_PTS || id == HSB_SLOT_PTS2; }
 extern "C" int hsb_eikonal_forward(hsb_ctx* h, const float* x, int64_t Ne, float* grad_theta, float* sample_sdf,
                                    float* sample_minsdf, cudaStream_t st) {
+    return hsb_points_forward(h, HSB_SLOT_EIK, x, Ne, grad_theta, sample_sdf, sample_minsdf, st);
+}
+// The same pass in a chosen point slot: EIK, or PTS / PTS2 for the Stage-2 point-constraint losses (model/network.py:973-1013:
+// get_sdf_raw(points)[:, obj_i] and gradient_obj_i(points, obj_i), both differentiable)
+extern "C" int hsb_points_forward(hsb_ctx* h, int32_t slot_id, const float* x, int64_t Ne, float* grad_theta, float* sample_sdf,
+                                  float* sample_minsdf, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
-    CTX_OR_FAIL(c, "hsb_eikonal_forward");
-    Slot& s = c->slot[HSB_SLOT_EIK];
-    if (Ne > s.cap_points || !x || !grad_theta) { set_error("hsb_eikonal_forward: batch exceeds max_eik_points / null pointer"); return HSB_ERR_ARG; }
+    CTX_OR_FAIL(c, "hsb_points_forward");
+    if (!point_slot(slot_id)) { set_error("hsb_points_forward: bad slot"); return HSB_ERR_ARG; }
+    Slot& s = c->slot[slot_id];
+    if (Ne > s.cap_points || !x || !grad_theta) { set_error("hsb_points_forward: batch exceeds the slot's capacity / null pointer"); return HSB_ERR_ARG; }
     s.N = Ne; s.nseed = 3;
     TRYCUDA(cudaMemcpyAsync(s.X, x, (size_t)Ne * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     TRY(launch_points_pe(s.X, Ne, s.H0, c->rtf(), st));
@@ -781,14 +826,18 @@ extern "C" int hsb_eikonal_forward(hsb_ctx* h, const float* x, int64_t Ne, float
         TRYCUDA(cudaMemcpy2DAsync(sample_sdf, (size_t)c->K * sizeof(float), s.SR, (size_t)c->Kp * sizeof(float), (size_t)c->K * sizeof(float),
                           (size_t)Ne, cudaMemcpyDeviceToDevice, st));
     if (sample_minsdf) TRYCUDA(cudaMemcpyAsync(sample_minsdf, s.SDF, (size_t)Ne * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    return check_cuda("hsb_eikonal_forward");
+    return check_cuda("hsb_points_forward");
 }
 
 extern "C" int hsb_eikonal_backward(hsb_ctx* h, const float* d_grad_theta, const float* d_sample_sdf, cudaStream_t st) {
+    return hsb_points_backward(h, HSB_SLOT_EIK, d_grad_theta, d_sample_sdf, st);
+}
+extern "C" int hsb_points_backward(hsb_ctx* h, int32_t slot_id, const float* d_grad_theta, const float* d_sample_sdf, cudaStream_t st) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
-    CTX_OR_FAIL(c, "hsb_eikonal_backward");
-    Slot& s = c->slot[HSB_SLOT_EIK];
-    if (s.N == 0 || !d_grad_theta) { set_error("hsb_eikonal_backward: no forward recorded / null gradient"); return HSB_ERR_ARG; }
+    CTX_OR_FAIL(c, "hsb_points_backward");
+    if (!point_slot(slot_id)) { set_error("hsb_points_backward: bad slot"); return HSB_ERR_ARG; }
+    Slot& s = c->slot[slot_id];
+    if (s.N == 0 || !d_grad_theta) { set_error("hsb_points_backward: no forward recorded / null gradient"); return HSB_ERR_ARG; }
     const long long Ne = s.N;
     TRY(launch_grad_to_jac(d_grad_theta, s.KS, Ne, c->K, c->Kp, s.dJ, c->rtf(), st));
     TRYCUDA(cudaMemsetAsync(s.dS, 0, (size_t)Ne * c->Kp * sizeof(float), st));

@@ -33,15 +33,21 @@ struct CompositeArgs {
     float* W; float* T;    // [P]
     float* rgb_values; float* depth_values; float* normal_map; float* opacity; float* semantic;
     float* wsum; float* wzsum;   // [R]
-    // mode 2 (Stage-2 object subsets, forward only): SDF = min over the subset channels `mask` (weights / opacity / semantics),
-    // SDFB = min over the object channels (bg_weights: colour / depth / normal composites); WB [P] receives bg_weights,
-    // opacity [R] one value per ray, semantic [R, popcount(mask)] in ascending channel order
+    // mode 2 (Stage-2 object subsets): SDF = min over the subset channels `mask` (weights / opacity / semantics), arg-min KS;
+    // SDFB = min over the object channels (bg_weights: colour / depth / normal composites), arg-min KSB; WB [P] receives bg_weights,
+    // T the transmittance of the bg_weights, T2 [P] that of the subset weights; opacity [R] one value per ray, semantic
+    // [R, popcount(mask)] in ascending channel order
     const float* SDFB; float* WB; unsigned long long mask;
+    const int* KSB; float* T2;
 };
 struct CompositeGrads {
     const float* d_rgb_values; const float* d_depth_values; const float* d_normal_map; const float* d_opacity;
     float* dO; float* dS; float* dGn; float* d_beta;
     int rtf;   // store dS rounded to TF32
+    // mode 2 only: d_opacity is [R] (d / d sum of the subset weights); d_wsum / d_wzsum [R] = d / d(sum bg_w), d / d(sum bg_w z), the
+    // un-normalised composites the near/far variant returns (model/network.py:1347,1353); detach_rgb: colour is composited with
+    // detached bg_weights (the *_detach_rgb_for_geometry variants, model/network.py:1422)
+    const float* d_wsum; const float* d_wzsum; int detach_rgb;
 };
 
 int launch_ray_points(const float* o, const float* d, const float* z, int R, int S, float* X, float* H0, float* RIN, int rtf, cudaStream_t st);

@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import c_f32, c_int, c_ll, c_stream, check, declare, ptr, stream
 
 NUM_SEGMENTS = 25
-SLOT_MAIN, SLOT_EIK, SLOT_BG = 0, 1, 2
+SLOT_MAIN, SLOT_EIK, SLOT_BG, SLOT_AUX, SLOT_PTS, SLOT_PTS2 = 0, 1, 2, 3, 4, 5
 
 SEGMENT_NAMES = [
     "implicit_network.encoding.embeddings", "implicit_network.color_encoding.embeddings",
@@ -33,7 +33,8 @@ class StepCfg(ctypes.Structure):
     _fields_ = [("K", ctypes.c_int32), ("L", ctypes.c_int32), ("H", ctypes.c_int32), ("S", ctypes.c_float),
                 ("table_rows", ctypes.c_int64), ("beta_min", ctypes.c_float), ("sigmoid_scale", ctypes.c_float),
                 ("max_points", ctypes.c_int64), ("max_rays", ctypes.c_int32), ("max_eik_points", ctypes.c_int64),
-                ("max_bg_points", ctypes.c_int64), ("max_bg_rays", ctypes.c_int32), ("precise", ctypes.c_int32)]
+                ("max_bg_points", ctypes.c_int64), ("max_bg_rays", ctypes.c_int32), ("precise", ctypes.c_int32),
+                ("max_aux_points", ctypes.c_int64), ("max_aux_rays", ctypes.c_int32), ("max_pts_points", ctypes.c_int64)]
 
 
 _vp = ctypes.c_void_p
@@ -51,8 +52,11 @@ _sdf_values = declare("hsb_sdf_values", [_vp, _vp, _vp, _vp, ctypes.c_int32, cty
 _render_fwd = declare("hsb_render_forward", [_vp, ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp,
                                              _vp, _vp, _vp, _vp, _vp, c_stream])
 _sdf_values_subset = declare("hsb_sdf_values_subset", [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint64, _vp, c_stream])
-_render_fwd_subset = declare("hsb_render_forward_subset", [_vp, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp, ctypes.c_uint64,
-                                                           ctypes.c_uint64, _vp, _vp, _vp, _vp, _vp, c_stream])
+_render_fwd_subset = declare("hsb_render_forward_subset", [_vp, ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp,
+                                                           ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, c_stream])
+_render_bwd_subset = declare("hsb_render_backward_subset", [_vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, c_stream])
+_pts_fwd = declare("hsb_points_forward", [_vp, ctypes.c_int32, _vp, ctypes.c_int64, _vp, _vp, _vp, c_stream])
+_pts_bwd = declare("hsb_points_backward", [_vp, ctypes.c_int32, _vp, _vp, c_stream])
 _sdf_grid = declare("hsb_sdf_grid", [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32),
                                      ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _vp, c_stream])
 _render_bwd = declare("hsb_render_backward", [_vp, ctypes.c_int32, _vp, _vp, _vp, _vp, c_stream])
@@ -166,7 +170,7 @@ class StepEngine:
 
     def __init__(self, K, table_rows, hash_offsets, S, H=16, L=16, beta_min=1e-4, sigmoid_scale=10.0, max_rays=1024,
                  max_samples=128, max_sampler_samples=128, max_bg_rays=1024, precise=False, flat_params=None,
-                 flat_grads=None):
+                 flat_grads=None, max_aux_rays=0, max_pts_points=0):
         if not torch.cuda.is_available():
             raise _lib.HsbError("StepEngine needs a CUDA device (the hot path has no CPU fallback)")
         self.K, self.L, self.H, self.S = int(K), int(L), int(H), float(S)
@@ -191,6 +195,9 @@ class StepEngine:
         cfg.max_bg_points = int(max_bg_rays) * int(max_samples)
         cfg.max_bg_rays = int(max_bg_rays)
         cfg.precise = 1 if precise else 0
+        cfg.max_aux_rays = int(max_aux_rays)                      # Stage-2 slots, 0 = not allocated (see include/hsb200.h)
+        cfg.max_aux_points = int(max_aux_rays) * int(max_samples)
+        cfg.max_pts_points = int(max_pts_points)
         self.cfg = cfg
         nbytes = ctypes.c_uint64()
         check(_ws_bytes(ctypes.byref(cfg), ctypes.byref(nbytes)))
@@ -251,7 +258,7 @@ class StepEngine:
         check(_sdf_grid(self._h, f3(*[float(v) for v in lo]), f3(*[float(v) for v in hi]), (ctypes.c_int32 * 3)(*[int(v) for v in res]),
                         int(first), int(n), int(channel), int(bool(shift)), ptr(out), stream()))
 
-    def render_forward_subset(self, o, d, z, depth_scale, rot, subset_idxs, obj_idxs):
+    def render_forward_subset(self, o, d, z, depth_scale, rot, subset_idxs, obj_idxs, slot=SLOT_MAIN, detach_rgb=False):
         """hsb_render_forward_subset: (rgb_values [R,3], depth_values [R,1], normal_map [R,3], opacity [R,1], semantic [R,n_subset])."""
         R, S = z.shape
         dev = z.device
@@ -259,9 +266,28 @@ class StepEngine:
         rgbv, depth, nmap = torch.empty(R, 3, device=dev), torch.empty(R, 1, device=dev), torch.empty(R, 3, device=dev)
         opac = torch.empty(R, 1, device=dev)
         sem = torch.empty(R, bin(msub).count("1"), device=dev)
-        check(_render_fwd_subset(self._h, ptr(o), ptr(d), ptr(z), R, S, ptr(depth_scale), ptr(rot), msub, mobj, ptr(rgbv), ptr(depth),
-                                 ptr(nmap), ptr(opac), ptr(sem), stream()))
+        check(_render_fwd_subset(self._h, int(slot), ptr(o), ptr(d), ptr(z), R, S, ptr(depth_scale), ptr(rot), msub, mobj,
+                                 1 if detach_rgb else 0, ptr(rgbv), ptr(depth), ptr(nmap), ptr(opac), ptr(sem), stream()))
         return rgbv, depth, nmap, opac, sem
+
+    def render_backward_subset(self, slot, d_rgb, d_depth, d_normal, d_opacity, d_wsum, d_wzsum):
+        c = lambda t: None if t is None else t.contiguous().float()
+        t = [c(v) for v in (d_rgb, d_depth, d_normal, d_opacity, d_wsum, d_wzsum)]
+        check(_render_bwd_subset(self._h, int(slot), *[ptr(v) for v in t], stream()))
+
+    def points_forward(self, slot, x):
+        """hsb_points_forward: the eikonal pass in a chosen point slot -> (grad_theta [(K+1) N, 3], sample_sdf [N,K], min sdf [N,1])."""
+        N, K = x.shape[0], self.K
+        gt = torch.empty((K + 1) * N, 3, device=x.device)
+        ssdf = torch.empty(N, K, device=x.device)
+        smin = torch.empty(N, 1, device=x.device)
+        check(_pts_fwd(self._h, int(slot), ptr(x), N, ptr(gt), ptr(ssdf), ptr(smin), stream()))
+        return gt, ssdf, smin
+
+    def points_backward(self, slot, d_grad_theta, d_sample_sdf=None):
+        a = d_grad_theta.contiguous()
+        b = None if d_sample_sdf is None else d_sample_sdf.contiguous()
+        check(_pts_bwd(self._h, int(slot), ptr(a), ptr(b), stream()))
 
     def render_forward(self, slot, o, d, z, depth_scale, rot):
         R, S = z.shape

@@ -127,6 +127,11 @@ class ObjectImplicitNetworkGrid(nn.Module):
         return shift
 
 
+    def gradient_obj_i(self, x, obj_i):
+        """network.py:256-271: d sdf_raw[:, obj_i] / d x at the points x, [N,3], differentiable w.r.t. the parameters (needs
+        hsb_max_pts_points in the conf; see HoloSceneNetwork._point_query)."""
+        return self._owner[0]._sdf_and_gradient_obj_i(obj_i, x)[1]
+
     @torch.no_grad()
     def get_outputs_and_indices(self, x):
         """network.py:481-504 as used by plotting: (sdf, feature_vectors, gradients, semantic, sdf_raw, indices) at points x.
@@ -192,6 +197,44 @@ class _StepFn(torch.autograd.Function):
         return None, None, None, None, None
 
 
+class _SubsetFn(torch.autograd.Function):
+    """Autograd node of a Stage-2 object-subset pass (hsb_render_forward_subset has already run in `slot`)."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, slot, outs):
+        ctx.model, ctx.slot = model, slot
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_depth, d_normal, d_opacity, d_wsum, d_wzsum):
+        eng = ctx.model.engine()
+        eng.render_backward_subset(ctx.slot, d_rgb, d_depth, d_normal, d_opacity, d_wsum, d_wzsum)
+        eng.finish()
+        return None, None, None, None
+
+
+class _PointsFn(torch.autograd.Function):
+    """Autograd node of a point query (hsb_points_forward has already run in `slot`): per-channel sdf and its gradients."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, slot, gt, ssdf):
+        ctx.model, ctx.slot, ctx.rows = model, slot, gt.shape[0]
+        ctx.set_materialize_grads(False)
+        return gt, ssdf
+
+    @staticmethod
+    def backward(ctx, d_gt, d_ssdf):
+        eng = ctx.model.engine()
+        if d_gt is not None or d_ssdf is not None:
+            if d_gt is None:
+                d_gt = torch.zeros(ctx.rows, 3, device=eng.device)
+            eng.points_backward(ctx.slot, d_gt, d_ssdf)
+            eng.finish()
+        ctx.model._pts_pending.discard(ctx.slot)
+        return None, None, None, None, None
+
+
 class HoloSceneNetwork(nn.Module):
     def __init__(self, conf, plots_dir=None, graph_node_dict=None, ft_folder=None, num_images=1024):
         super().__init__()
@@ -219,6 +262,11 @@ class HoloSceneNetwork(nn.Module):
         # bench.py measures; deviations from the fp32 reference are stated in DESIGN.md section 2 / INTEGRATION.md).
         self.precise = bool(conf.get_bool("hsb_precise", default=True))
         self.max_rays = conf.get_int("hsb_max_rays", default=1024)
+        # Stage-2 capacities (0 = not allocated): rays of an object-subset pass that must coexist with the scene pass of the same
+        # step, points of a point-constraint loss (include/hsb200.h: HSB_SLOT_AUX / PTS / PTS2)
+        self.max_aux_rays = conf.get_int("hsb_max_aux_rays", default=0)
+        self.max_pts_points = conf.get_int("hsb_max_pts_points", default=0)
+        self._pts_pending = set()
         self._eng = None
         self._flat = None
         self._flat_grad = None
@@ -280,7 +328,9 @@ class HoloSceneNetwork(nn.Module):
                 S=float(np.float32(np.log2(enc.per_level_scale))), H=enc.base_resolution, L=enc.num_levels,
                 beta_min=self.density.beta_min, sigmoid_scale=float(self.implicit_network.sigmoid),
                 max_rays=max(self.max_rays, 1024 if self.use_bg_reg else 1), max_samples=S, max_sampler_samples=rs.N_samples_eval, max_bg_rays=1024,
-                precise=self.precise, flat_params=self._flat, flat_grads=self._flat_grad)
+                precise=self.precise, flat_params=self._flat, flat_grads=self._flat_grad, max_aux_rays=self.max_aux_rays,
+                max_pts_points=self.max_pts_points)
+            self._pts_pending = set()
         return self._eng
 
     # ---- forward (network.py:778-971) --------------------------------------------------------------------
@@ -295,6 +345,7 @@ class HoloSceneNetwork(nn.Module):
         draws = self.draws if self.draws is not None else LiveDraws(dev)
         self.draws = draws
         self.ray_sampler._pending.clear()      # a forward that raised after a speculative sampler call leaves stale entries behind
+        self._pts_pending.clear()              # a new step: point queries whose backward never ran no longer hold their slots
         # Speculative convergence test of the sampler (ray_sampler.get_z_vals): only with live random draws (a replayed log must be
         # consumed exactly once) and in training; the first call of a kind always runs in exact mode.
         speculate = self.training and isinstance(draws, LiveDraws) and self.speculative_sampler
@@ -406,40 +457,58 @@ class HoloSceneNetwork(nn.Module):
         return output
 
     # ---- Stage-2 consumers of the same operator --------------------------------------------------------------
-    @torch.no_grad()
     def forward_multi_obj_rays_subset_all_sdf(self, ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs, iter_step=-1,
-                                              near_far=None):
+                                              near_far=None, detach_rgb=False):
         """Reference model/network.py:1235-1306: render explicit rays with the scene restricted to an object subset.  The sampler
         and the `bg_weights` (colour / depth / normal composites) use the min over `obj_idxs`, the sdf / gradient / `weights` /
-        semantics / opacity the min over `subset_obj_idxs`.  Same output keys as the reference.  Forward only in this
-        implementation (the reference's version is differentiable; Stage 2 calls it for visibility / rendering queries)."""
+        semantics / opacity the min over `subset_obj_idxs`.  Same output keys as the reference.  Differentiable when autograd is
+        enabled (Stage 2 trains through it: calculate_invisible_loss / calculate_background_recon_loss,
+        training/holoscene_train_post.py:458-760): rgb_values, depth_values, normal_map and opacity carry the graph; the per-sample
+        tensors and semantic_values are returned detached.  The pass runs in the AUX slot when the conf sets hsb_max_aux_rays (then it
+        may sit between forward() and backward() of the same step), else in the MAIN slot."""
         dev = self.density.beta.device
         o = ray_origins.reshape(-1, 3).to(dev, torch.float32).contiguous()
         d = torch.nn.functional.normalize(ray_dirs.reshape(-1, 3).to(dev, torch.float32), dim=-1).contiguous()
         rot = pose.to(dev)[..., :3, :3].reshape(3, 3).permute(1, 0).contiguous()
         depth_scale = (rot @ d.permute(1, 0)).permute(1, 0)[:, 2:].contiguous()
         eng = self.engine()
-        if o.shape[0] > eng.max_rays:
-            raise RuntimeError(f"{o.shape[0]} rays exceed hsb_max_rays={eng.max_rays} (set model.hsb_max_rays in the conf)")
+        R = o.shape[0]
+        slot, pre = (_engine.SLOT_AUX, "aux") if 0 < R <= eng.cfg.max_aux_rays else (_engine.SLOT_MAIN, "main")
+        if slot == _engine.SLOT_MAIN and R > eng.max_rays:
+            raise RuntimeError(f"{R} rays exceed hsb_max_rays={eng.max_rays} (set model.hsb_max_rays in the conf)")
+        grad = torch.is_grad_enabled()
+        if grad:
+            self._attach_grads()
         eng.prepare()
         draws = self.draws if self.draws is not None else LiveDraws(dev)
         self.draws = draws
         try:
             obj, sub = [int(k) for k in obj_idxs], [int(k) for k in subset_obj_idxs]
-            z_vals, _ = self.ray_sampler.get_z_vals(d, o, self, idx=obj, near_far=near_far)
-            z_vals = z_vals.contiguous()
-            R, S = z_vals.shape
-            rgbv, depth, nmap, opac, sem = eng.render_forward_subset(o, d, z_vals, depth_scale, rot, sub, obj)
-            P = R * S
-            if len(set(sub)) != len(sub) or sorted(sub) != sub:
-                # the kernel packs the subset's semantics in ascending channel order; restore the caller's order / duplicates
-                order = sorted(set(sub))
-                sem = sem[:, [order.index(k) for k in sub]]
-            return {"rgb": eng.buffer("main.RGB")[:P].view(R, S, 4)[..., :3].clone(), "semantic_values": sem, "opacity": opac,
-                    "rgb_values": rgbv, "depth_values": depth, "z_vals": z_vals, "depth_vals": z_vals * depth_scale,
-                    "sdf": eng.buffer("main.SDF")[:P].view(R, S).clone(), "weights": eng.buffer("main.W")[:P].view(R, S).clone(),
-                    "bg_weights": eng.buffer("main.WB")[:P].view(R, S).clone(), "normal_map": nmap,
-                    **({"_depth_scale": depth_scale} if near_far is not None else {})}
+            with torch.no_grad():
+                z_vals, _ = self.ray_sampler.get_z_vals(d, o, self, idx=obj, near_far=near_far)
+                z_vals = z_vals.contiguous()
+                S = z_vals.shape[1]
+                rgbv, depth, nmap, opac, sem = eng.render_forward_subset(o, d, z_vals, depth_scale, rot, sub, obj, slot, detach_rgb)
+                P = R * S
+                if len(set(sub)) != len(sub) or sorted(sub) != sub:
+                    # the kernel packs the subset's semantics in ascending channel order; restore the caller's order / duplicates
+                    order = sorted(set(sub))
+                    sem = sem[:, [order.index(k) for k in sub]]
+                wsum = eng.buffer(pre + ".WSUM")[:R].reshape(R).clone()
+                wzsum = eng.buffer(pre + ".WZSUM")[:R].reshape(R).clone()
+                out = {"rgb": eng.buffer(pre + ".RGB")[:P].view(R, S, 4)[..., :3].clone(), "semantic_values": sem, "z_vals": z_vals,
+                       "depth_vals": z_vals * depth_scale, "sdf": eng.buffer(pre + ".SDF")[:P].view(R, S).clone(),
+                       "weights": eng.buffer(pre + ".W")[:P].view(R, S).clone(),
+                       "bg_weights": eng.buffer(pre + ".WB")[:P].view(R, S).clone()}
+            if grad:
+                anchor = torch.empty(0, device=dev, requires_grad=True)
+                rgbv, depth, nmap, opac, wsum, wzsum = _SubsetFn.apply(anchor, self, slot, [rgbv, depth, nmap, opac, wsum, wzsum])
+            out.update({"opacity": opac, "rgb_values": rgbv, "depth_values": depth, "normal_map": nmap})
+            if near_far is not None and not detach_rgb:
+                # this variant returns the un-normalised depth and the accumulated bg_weights as opacity (network.py:1347,1353)
+                out["opacity"] = wsum.reshape(-1)
+                out["depth_values"] = depth_scale * wzsum.reshape(R, 1)
+            return out
         finally:
             if isinstance(draws, LiveDraws):
                 self.draws = None
@@ -450,16 +519,113 @@ class HoloSceneNetwork(nn.Module):
         (ray_sampler.get_z_vals_near_far).  This variant differs from the other in two outputs, reproduced: the depth is NOT
         normalised by the accumulated weight (depth_scale * sum bg_w z, :1347) and `opacity` is the accumulated bg_weights, shape [R]
         (:1353)."""
-        out = self.forward_multi_obj_rays_subset_all_sdf(ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs, iter_step,
-                                                         near_far=(float(near), float(far)))
+        return self.forward_multi_obj_rays_subset_all_sdf(ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs, iter_step,
+                                                          near_far=(float(near), float(far)))
+
+    def forward_multi_obj_rays_subset_all_sdf_detach_rgb_for_geometry(self, ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs,
+                                                                      iter_step=-1):
+        """Reference model/network.py:1384-1457: same values as forward_multi_obj_rays_subset_all_sdf; in the backward the render net
+        sees a detached gradient and the colour composite detached bg_weights (colour supervision does not move the geometry)."""
+        return self.forward_multi_obj_rays_subset_all_sdf(ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs, iter_step,
+                                                          detach_rgb=True)
+
+    def forward_multi_obj_rays_subset_all_sdf_detach_rgb_for_geometry_near_far(self, ray_origins, ray_dirs, pose, obj_idxs,
+                                                                               subset_obj_idxs, near, far, iter_step=-1):
+        """Reference model/network.py:1458-1531: explicit [near, far] sampler + detached colour path.  Unlike the plain near/far variant
+        this one keeps the weight-normalised depth and the subset opacity [R,1] (:1498,:1494)."""
+        return self.forward_multi_obj_rays_subset_all_sdf(ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs, iter_step,
+                                                          near_far=(float(near), float(far)), detach_rgb=True)
+
+    # ---- mesh-colouring queries of the export / plotting code (model/network.py:1532-1800; utils/plots.py:162,241) ----------------
+    @torch.no_grad()
+    def _colors_normals(self, points, rays, idxs, pose=None, near_far=None):
+        """Colour (and normal) composited along rays started AT the given points, with the scene restricted to the channels `idxs`:
+        the subset pass with obj_idxs = subset_obj_idxs = idxs, in chunks of hsb_max_rays."""
+        dev = self.density.beta.device
+        points, rays = points.reshape(-1, 3).to(dev, torch.float32), rays.reshape(-1, 3).to(dev, torch.float32)
+        pose = torch.eye(4, device=dev) if pose is None else pose.to(dev).reshape(-1, 4)[:4, :4]
+        step = self.engine().max_rays
+        rgb, nm = [], []
+        for i in range(0, points.shape[0], step):
+            out = self.forward_multi_obj_rays_subset_all_sdf(points[i:i + step], rays[i:i + step], pose, idxs, idxs, near_far=near_far)
+            rgb.append(out["rgb_values"].reshape(-1, 3))
+            nm.append(out["normal_map"].reshape(-1, 3))
+        return torch.cat(rgb, 0), torch.cat(nm, 0)
+
+    def get_colors_from_point_rays(self, points, rays):
+        """network.py:1656-1683"""
+        return self._colors_normals(points, rays, list(range(self.implicit_network.d_out)))[0]
+
+    def get_colors_from_point_rays_obj(self, points, rays, obj_i):
+        """network.py:1685-1712"""
+        return self._colors_normals(points, rays, [int(obj_i)])[0]
+
+    def get_colors_from_point_rays_obj_offset(self, points, rays, obj_i):
+        """network.py:1714-1741 (the same computation as get_colors_from_point_rays_obj)"""
+        return self._colors_normals(points, rays, [int(obj_i)])[0]
+
+    def get_colors_from_point_rays_obj_offset_near_far(self, points, rays, obj_i, near, far):
+        """network.py:1743-1770"""
+        return self._colors_normals(points, rays, [int(obj_i)], near_far=(float(near), float(far)))[0]
+
+    def get_colors_normals_from_point_rays(self, points, rays, pose):
+        """network.py:1532-1569: (rgb_values, normal_map rotated into the camera frame of `pose`)"""
+        return self._colors_normals(points, rays, list(range(self.implicit_network.d_out)), pose=pose)
+
+    # ---- Stage-2 point-constraint losses (model/network.py:973-1013) --------------------------------------------------------------
+    def _point_query(self, points):
+        """sdf_raw [N,K] and the stacked per-channel gradients [(K+1) N, 3] at `points`, both differentiable w.r.t. the parameters
+        (the reference's get_sdf_raw + gradient_obj_i, network.py:256-271,305-318).  Needs hsb_max_pts_points in the conf."""
         eng = self.engine()
-        R = out["z_vals"].shape[0]
-        wsum = eng.buffer("main.WSUM")[:R].clone()
-        wzsum = eng.buffer("main.WZSUM")[:R].clone()
-        out["opacity"] = wsum.reshape(-1)
-        out["depth_values"] = out["_depth_scale"] * wzsum
-        del out["_depth_scale"]
-        return out
+        x = points.reshape(-1, 3).to(eng.device, torch.float32).contiguous()
+        N = x.shape[0]
+        if N > eng.cfg.max_pts_points:
+            raise RuntimeError(f"{N} points exceed hsb_max_pts_points={eng.cfg.max_pts_points} (set model.hsb_max_pts_points in the conf)")
+        free = [sl for sl in (_engine.SLOT_PTS, _engine.SLOT_PTS2) if sl not in self._pts_pending]
+        if not free:
+            raise RuntimeError("two point queries are already waiting for their backward (HSB_SLOT_PTS / PTS2)")
+        slot = free[0]
+        grad = torch.is_grad_enabled()
+        if grad:
+            self._attach_grads()
+        eng.prepare()
+        with torch.no_grad():
+            gt, ssdf, _ = eng.points_forward(slot, x)
+        if grad:
+            self._pts_pending.add(slot)
+            anchor = torch.empty(0, device=eng.device, requires_grad=True)
+            gt, ssdf = _PointsFn.apply(anchor, self, slot, gt, ssdf)
+        return ssdf, gt, N
+
+    def _sdf_and_gradient_obj_i(self, obj_i, points):
+        ssdf, gt, N = self._point_query(points)
+        obj_i = int(obj_i)
+        return ssdf[:, obj_i].reshape(-1), gt[obj_i * N:(obj_i + 1) * N]
+
+    def get_pts_sdf_contraints_loss(self, obj_i, points, sdfs):
+        """network.py:973-987: push object obj_i's sdf above -sdfs at the colliding points + eikonal term."""
+        sample_sdf, grad_theta = self._sdf_and_gradient_obj_i(obj_i, points)
+        delta_sdf = -sample_sdf - sdfs.reshape(-1).to(sample_sdf.device)
+        collision_mask = delta_sdf > 0
+        loss_sdf = torch.mean(delta_sdf[collision_mask]) if torch.any(collision_mask) else torch.zeros((), device=sample_sdf.device)
+        loss_eikonal = ((grad_theta.norm(2, dim=1) - 1) ** 2).mean()
+        return loss_sdf * 5.0 + loss_eikonal * 0.1
+
+    def get_pts_sdf_maintain_loss(self, obj_i, points, sdfs):
+        """network.py:989-1002: keep object obj_i's sdf below sdfs at the given points + eikonal term."""
+        sample_sdf, grad_theta = self._sdf_and_gradient_obj_i(obj_i, points)
+        delta_sdf = sample_sdf - sdfs.reshape(-1).to(sample_sdf.device)
+        collision_mask = delta_sdf > 0
+        loss_sdf = torch.mean(delta_sdf[collision_mask]) if torch.any(collision_mask) else torch.zeros((), device=sample_sdf.device)
+        loss_eikonal = ((grad_theta.norm(2, dim=1) - 1) ** 2).mean()
+        return loss_sdf * 3.0 + loss_eikonal * 0.1
+
+    def get_additional_sdf_loss(self, obj_i, points, sdfs):
+        """network.py:1004-1013: L1 to given sdf values + eikonal term."""
+        sample_sdf, grad_theta = self._sdf_and_gradient_obj_i(obj_i, points)
+        loss_sdf = torch.mean(torch.abs(sdfs.reshape(-1).to(sample_sdf.device) - sample_sdf))
+        loss_eikonal = ((grad_theta.norm(2, dim=1) - 1) ** 2).mean()
+        return loss_sdf * 10.0 + loss_eikonal * 0.1
 
     def get_parameters(self):
         return list(self.parameters())

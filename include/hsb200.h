@@ -108,6 +108,10 @@ int hsb_hash_backward_fused(const float* x_world, const int32_t* offsets, const 
 #define HSB_SLOT_MAIN 0 /* scene pass: colour, opacity, semantics             network.py:799-841,904-913 */
 #define HSB_SLOT_EIK 1  /* eikonal points                                      network.py:843-866 */
 #define HSB_SLOT_BG 2   /* background patch: channel-0 weights, no colour      network.py:915-968 */
+#define HSB_SLOT_AUX 3  /* Stage 2: a second scene slot for the object-subset pass   network.py:1235-1531 */
+#define HSB_SLOT_PTS 4  /* Stage 2: point-constraint losses (sdf + gradient of one channel at given points)  network.py:973-1013 */
+#define HSB_SLOT_PTS2 5 /* ... a second one: two such losses can be pending in one step (holoscene_train_post.py:3680-3707) */
+#define HSB_NUM_SLOTS 6
 
 typedef struct hsb_step_cfg {
     int32_t K;              /* implicit_network.d_out */
@@ -123,6 +127,9 @@ typedef struct hsb_step_cfg {
     int64_t max_bg_points;  /* capacity of the BG slot (1024 * samples); 0 = unused */
     int32_t max_bg_rays;
     int32_t precise;        /* 1: 3xTF32 error-compensated contractions (fp32-grade), 0: single-pass TF32 */
+    int64_t max_aux_points; /* capacity of the AUX slot (rays * samples of a Stage-2 subset pass); 0 = unused */
+    int32_t max_aux_rays;
+    int64_t max_pts_points; /* capacity of each of the PTS / PTS2 slots in points; 0 = unused */
 } hsb_step_cfg;
 
 typedef struct hsb_ctx hsb_ctx;
@@ -146,7 +153,9 @@ int hsb_ctx_buffer(hsb_ctx* ctx, const char* name, int64_t* offset_bytes, int64_
 
 /* weight_norm materialisation (w = g v/|v|), transposes, zero of the effective-weight gradient accumulators. */
 int hsb_prepare(hsb_ctx* ctx, hsb_stream_t stream);
-/* weight_norm backward + bias fix-ups into the flat gradient buffer; call once after all *_backward. */
+/* weight_norm backward + bias fix-ups into the flat gradient buffer; call after the *_backward calls.  Additive: it consumes (and
+ * clears) what the backward calls since the last hsb_prepare / hsb_finish accumulated, so it may be called once per group of
+ * backward calls (one autograd node each) within a step. */
 int hsb_finish(hsb_ctx* ctx, hsb_stream_t stream);
 
 /* Camera rays of one pixel batch (utils/rend_util.py:56-98,112-125 as called twice by model/network.py:788-792).
@@ -203,13 +212,23 @@ int hsb_sdf_grid(hsb_ctx* ctx, const float* lo_host, const float* hi_host, const
  *   hsb_sdf_values_subset:     no-grad min over the channels of `mask` at o + z d (the sampler's queries with idx = list);
  *   hsb_render_forward_subset: scene pass whose sdf / arg-min / gradient run over mask_subset (`weights`, semantics of the subset
  *       channels in ascending order -> semantic [R, popcount(mask_subset)], opacity [R] = sum of weights) while colour, depth and
- *       normals are composited with `bg_weights` from the min over mask_obj.  Per-sample state: "main.SDF", "main.W" (weights),
- *       "main.WB" (bg_weights), "main.RGB".  Forward only (no backward is recorded). */
+ *       normals are composited with `bg_weights` from the min over mask_obj.  slot = MAIN or AUX (AUX: the scene pass recorded in
+ *       MAIN stays valid, as Stage 2's loop needs: model forward -> subset-pass loss -> one backward, holoscene_train_post.py:3590-3718).
+ *       detach_rgb != 0: the *_detach_rgb_for_geometry variants (network.py:1384-1531: the render net sees a detached gradient and
+ *       colour is composited with detached bg_weights; forward values are the same).  Per-sample state: "<slot>.SDF", ".W" (weights),
+ *       ".WB" (bg_weights), ".RGB"; per ray ".WSUM" = sum bg_w, ".WZSUM" = sum bg_w z (what the near/far variant returns as opacity
+ *       and un-normalised depth, network.py:1347,1353);
+ *   hsb_render_backward_subset: its backward from d(loss)/d(rgb_values [R,3], depth_values [R], normal_map [R,3], opacity [R],
+ *       sum bg_w [R], sum bg_w z [R]) (NULL = zero).  The semantic composite is not differentiated (no Stage-2 loss reads it). */
 int hsb_sdf_values_subset(hsb_ctx* ctx, const float* o, const float* d, const float* z, int32_t R, int32_t S, uint64_t mask,
                           float* sdf_out, hsb_stream_t stream);
-int hsb_render_forward_subset(hsb_ctx* ctx, const float* o, const float* d, const float* z, int32_t R, int32_t S,
-                              const float* depth_scale, const float* rot, uint64_t mask_subset, uint64_t mask_obj, float* rgb_values,
-                              float* depth_values, float* normal_map, float* opacity, float* semantic, hsb_stream_t stream);
+int hsb_render_forward_subset(hsb_ctx* ctx, int32_t slot, const float* o, const float* d, const float* z, int32_t R, int32_t S,
+                              const float* depth_scale, const float* rot, uint64_t mask_subset, uint64_t mask_obj, int32_t detach_rgb,
+                              float* rgb_values, float* depth_values, float* normal_map, float* opacity, float* semantic,
+                              hsb_stream_t stream);
+int hsb_render_backward_subset(hsb_ctx* ctx, int32_t slot, const float* d_rgb_values, const float* d_depth_values,
+                               const float* d_normal_map, const float* d_opacity, const float* d_wsum, const float* d_wzsum,
+                               hsb_stream_t stream);
 /* Ray pass backward from d(loss)/d(per-ray outputs) (NULL = zero). */
 int hsb_render_backward(hsb_ctx* ctx, int32_t slot, const float* d_rgb_values, const float* d_depth_values,
                         const float* d_normal_map, const float* d_opacity, hsb_stream_t stream);
@@ -220,6 +239,13 @@ int hsb_eikonal_forward(hsb_ctx* ctx, const float* x, int64_t Ne, float* grad_th
                         hsb_stream_t stream);
 int hsb_eikonal_backward(hsb_ctx* ctx, const float* d_grad_theta, const float* d_sample_sdf /* may be NULL */,
                          hsb_stream_t stream);
+/* The same pass in a chosen point slot (EIK, PTS, PTS2): Stage 2's point-constraint losses evaluate get_sdf_raw(points)[:, obj_i] and
+ * gradient_obj_i(points, obj_i) (model/network.py:256-271,973-1013), both differentiable, while the step's own eikonal pass is still
+ * waiting for its backward. */
+int hsb_points_forward(hsb_ctx* ctx, int32_t slot, const float* x, int64_t N, float* grad_theta, float* sample_sdf,
+                       float* sample_minsdf, hsb_stream_t stream);
+int hsb_points_backward(hsb_ctx* ctx, int32_t slot, const float* d_grad_theta, const float* d_sample_sdf /* may be NULL */,
+                        hsb_stream_t stream);
 
 /* Stage-1 loss terms and d(total)/d(output) in three launches (model/loss.py:181-193,227-346,487-492; see csrc/loss.cu).
  * Inputs: per-ray outputs of hsb_render_forward(MAIN) (rgb_values [R,3], depth_values [R], normal_map [R,3], opacity [R,K]), the

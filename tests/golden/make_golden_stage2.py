@@ -67,5 +67,41 @@ def main():
         print(name, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024), {k: tuple(v.shape) for k, v in out.items() if k in ("opacity", "semantic_values")})
 
 
+def colours():
+    """stage2_colors.npz: the mesh-colouring queries (model/network.py:1532-1569,1656-1770; callers utils/plots.py:162,241) at 40
+    (point, ray) pairs, eval mode."""
+    net, _, _ = ref_shims.reference_modules()
+    K, R, sampler = 4, 40, (16, 32, 8)
+    cfg = om.StepConfig(d_out=K, logmap=LOGMAP, N_samples=sampler[0], N_samples_eval=sampler[1], N_samples_extra=sampler[2])
+    torch.manual_seed(42)
+    model = net.HoloSceneNetwork(make_conf(K, sampler))
+    torch.manual_seed(42)
+    sd = synthetic.perturb_state_dict(om.init_state_dict(cfg))
+    model.load_state_dict(sd)
+    model.eval()
+    gen = torch.Generator().manual_seed(9)
+    pts = (torch.rand(R, 3, generator=gen) * 2 - 1) * 0.6
+    rays = torch.randn(R, 3, generator=gen)
+    _, pose = synthetic.camera()
+    pose = pose.clone()
+    pose[0, :3, :3] = torch.linalg.qr(torch.randn(3, 3, generator=gen))[0]
+    blob = {"meta_K": K, "meta_sampler": np.array(sampler), "meta_logmap": LOGMAP, "in_points": pts.numpy(), "in_rays": rays.numpy(),
+            "in_pose": pose.numpy(), "meta_obj_i": 2, "meta_near_far": np.array((0.05, 1.5))}
+    blob["out_all"] = model.get_colors_from_point_rays(pts.clone(), rays.clone()).detach().numpy()
+    blob["out_obj"] = model.get_colors_from_point_rays_obj(pts.clone(), rays.clone(), 2).detach().numpy()
+    blob["out_obj_offset"] = model.get_colors_from_point_rays_obj_offset(pts.clone(), rays.clone(), 2).detach().numpy()
+    blob["out_obj_near_far"] = model.get_colors_from_point_rays_obj_offset_near_far(pts.clone(), rays.clone(), 2, 0.05, 1.5).detach().numpy()
+    c, n = model.get_colors_normals_from_point_rays(pts.clone(), rays.clone(), pose[0])
+    blob["out_cn_rgb"], blob["out_cn_normal"] = c.detach().numpy(), n.detach().numpy()
+    blob["check_param_sum"] = np.float64(sum(float(v.double().abs().sum()) for v in sd.values() if v.dtype.is_floating_point))
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stage2_colors.npz")
+    np.savez_compressed(path, **blob)
+    print("stage2_colors ->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "colors":
+        colours()
+        sys.exit(0)
     main()
+    colours()
