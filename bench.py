@@ -328,6 +328,62 @@ def grid_benchmark(w, dev, res=256):
     return out
 
 
+def stage2_benchmark(w, dev, rays=1024, points=8192, iters=10):
+    """N1: the differentiable Stage-2 queries at the sizes Stage 2 uses them (training/holoscene_train_post.py: 1024 rays in
+    calculate_background_recon_loss :720, up to 4096 + 4096 points in the collision losses :3680-3707), fast mode, device-timed:
+    (a) forward_multi_obj_rays_subset_all_sdf_near_far + novel-view loss + backward (sampler included), (b) get_pts_sdf_contraints_loss +
+    backward.  Rendered samples/s and points/s."""
+    from holoscene_b200 import synthetic
+    from holoscene_b200.network import HoloSceneNetwork
+    torch.manual_seed(42)
+    c = model_conf(w, precise=False, max_rays=rays)
+    m = HoloSceneNetwork(c)
+    m.max_pts_points = points
+    m.load_state_dict(synthetic.perturb_state_dict(m.state_dict()))
+    m = m.cuda().train()
+    Kmat, pose = synthetic.camera()
+    uv, _ = synthetic.rays_and_gt(rays, w["K"])
+    from holoscene_b200 import engine as E
+    dirs, cam, _ = E.camera_rays(uv.clone().cuda(), pose.cuda(), Kmat.cuda())
+    gen = torch.Generator().manual_seed(3)
+    tgt = [t.cuda() for t in (torch.rand(rays, 3, generator=gen), (torch.rand(rays, generator=gen) > 0.3).float(),
+                              torch.nn.functional.normalize(torch.randn(rays, 3, generator=gen), dim=-1), 0.5 + 2 * torch.rand(rays, generator=gen))]
+    pts = ((torch.rand(points, 3, generator=gen) * 2 - 1) * 0.8).cuda()
+    sdfs = ((torch.rand(points, generator=gen) - 0.5) * 0.6).cuda()
+    objs = list(range(1, min(w["K"], 4)))
+    F = torch.nn.functional
+
+    def subset():
+        out = m.forward_multi_obj_rays_subset_all_sdf_near_far(cam, dirs, pose.cuda(), objs, objs, 0.05, 3.0)
+        loss = F.mse_loss(out["opacity"], tgt[1]) + F.l1_loss(out["rgb_values"], tgt[0]) + F.l1_loss(out["normal_map"], tgt[2]) + \
+            F.l1_loss(out["depth_values"].reshape(-1), tgt[3])
+        loss.backward()
+        return out["z_vals"].shape[1]
+
+    def pointloss():
+        m.get_pts_sdf_contraints_loss(1, pts, sdfs).backward()
+
+    res = {}
+    for name, fn, units in (("subset_pass_fwd_bwd", subset, None), ("point_constraint_loss_fwd_bwd", pointloss, points)):
+        for _ in range(3):
+            S = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        n = units if units is not None else rays * S
+        res[name] = {"ms": ms, "units": n, "units_per_s": n / ms * 1e3,
+                     "unit": "points/s" if units is not None else f"rendered samples/s ({rays} rays x {S} samples, sampler + forward + loss + backward)"}
+    res["finite"] = bool(torch.isfinite(m._flat_grad).all())
+    del m
+    torch.cuda.empty_cache()
+    return res
+
+
 def kernel_roofline(P, dev, precise, peaks):
     """The dominant kernel of the step (most of its time: the 256x256 fc contraction, 28 of ~100 launches): 20 isolated launches timed
     with CUDA events on the launching stream, operands (0.5 GB each) >> L2.  As a contraction its bound is the TENSOR pipe
@@ -509,6 +565,7 @@ def main():
             extra["precise_3xtf32"] = x.result(*x.run(steps=5, warmup=3, e2e=False))
             x.close()
             extra["grid_256"] = grid_benchmark(w, dev)
+            extra["stage2"] = stage2_benchmark(w, dev)
         else:
             for g in (4096, 8192):                                # strong scaling: the global batch is fixed, each GPU renders g / N rays
                 x = Bench(w, g // world, rank, world, dev, graph=not args.no_graph)

@@ -38,6 +38,10 @@ def _load():
 
 lib = _load()
 ABI_VERSION = lib.hsb_abi_version()
+EXPECTED_ABI = 2            # HSB_ABI_VERSION of include/hsb200.h this host code was written against
+if ABI_VERSION != EXPECTED_ABI:
+    raise HsbError(f"{SO_PATH} has ABI version {ABI_VERSION}, the host code expects {EXPECTED_ABI}: rebuild it "
+                   "(`python -m holoscene_b200.build`)")
 lib.hsb_launch_count.restype = ctypes.c_ulonglong
 
 

@@ -47,7 +47,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile(s, hdrs, force), srcs))
     if force or _stale(SO, objs):
-        subprocess.check_call([NVCC, "-shared", "-o", SO, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+        # link next to the target and rename: a reader (or a snapshot of the tree) never sees a half-written library
+        subprocess.check_call([NVCC, "-shared", "-o", SO + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+        os.replace(SO + ".tmp", SO)
     if verbose:
         for o in objs:
             print(open(o + ".log").read())

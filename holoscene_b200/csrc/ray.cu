@@ -16,7 +16,11 @@ __device__ __forceinline__ float beta_of(const float* beta_param, float beta_min
 // d sigma / d s and d sigma / d beta of the Laplace density
 __device__ __forceinline__ void laplace_grads(float s, float beta, float& ds, float& db) {
     const float ib = 1.0f / beta;
-    const float e = expf(-fabsf(s) * ib);                 // exp(-|s|/beta)
+    // exp(-|s|/beta) the way torch's autograd forms it: d expm1(u) = (result + 1), which is EXACTLY 0 once expm1 has rounded to -1
+    // (|s|/beta > 17.3) and a multiple of 2^-24 below that.  A plain expf() here gives a tiny but non-zero d sigma / d s where the fp32
+    // density is exactly 0; times the 1e10 length of the last interval that would be a gradient of order 1e4, which the reference
+    // does not have, on every ray that leaves the scene without saturating (Stage-2 object-subset passes).
+    const float e = expm1f(-fabsf(s) / beta) + 1.0f;
     ds = -0.5f * ib * ib * e;
     if (s >= 0.0f) db = 0.5f * ib * ib * e * (s * ib - 1.0f);
     else db = -ib * ib + 0.5f * ib * ib * e * (1.0f + s * ib);

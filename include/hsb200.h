@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HSB_ABI_VERSION 1
+#define HSB_ABI_VERSION 2 /* 2: hsb_step_cfg grew the Stage-2 capacities; hsb_render_forward_subset takes a slot */
 
 typedef struct CUstream_st* hsb_stream_t; /* == cudaStream_t */
 

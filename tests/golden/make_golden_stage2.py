@@ -86,11 +86,11 @@ def colours():
     pose = pose.clone()
     pose[0, :3, :3] = torch.linalg.qr(torch.randn(3, 3, generator=gen))[0]
     blob = {"meta_K": K, "meta_sampler": np.array(sampler), "meta_logmap": LOGMAP, "in_points": pts.numpy(), "in_rays": rays.numpy(),
-            "in_pose": pose.numpy(), "meta_obj_i": 2, "meta_near_far": np.array((0.05, 1.5))}
+            "in_pose": pose.numpy(), "meta_obj_i": 2, "meta_near_far": np.array((0.05, 3.0))}
     blob["out_all"] = model.get_colors_from_point_rays(pts.clone(), rays.clone()).detach().numpy()
     blob["out_obj"] = model.get_colors_from_point_rays_obj(pts.clone(), rays.clone(), 2).detach().numpy()
     blob["out_obj_offset"] = model.get_colors_from_point_rays_obj_offset(pts.clone(), rays.clone(), 2).detach().numpy()
-    blob["out_obj_near_far"] = model.get_colors_from_point_rays_obj_offset_near_far(pts.clone(), rays.clone(), 2, 0.05, 1.5).detach().numpy()
+    blob["out_obj_near_far"] = model.get_colors_from_point_rays_obj_offset_near_far(pts.clone(), rays.clone(), 2, 0.05, 3.0).detach().numpy()   # far = 3.0: see the note at stage2_near_far
     c, n = model.get_colors_normals_from_point_rays(pts.clone(), rays.clone(), pose[0])
     blob["out_cn_rgb"], blob["out_cn_normal"] = c.detach().numpy(), n.detach().numpy()
     blob["check_param_sum"] = np.float64(sum(float(v.double().abs().sum()) for v in sd.values() if v.dtype.is_floating_point))

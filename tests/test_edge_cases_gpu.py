@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 def _model(K=3, precise=False, max_rays=64, **extra):
     from oracle import model as om
-    cfg = om.StepConfig(d_out=K, logmap=12, N_samples=12, N_samples_eval=32, N_samples_extra=6)
+    cfg = om.StepConfig(d_out=K, logmap=12, N_samples=120, N_samples_eval=32, N_samples_extra=6)   # slots sized for S <= 128
     sd = common.seeded_state_dict(cfg)
     m = build_model(cfg, sd, precise, max_rays=max_rays)
     m.use_bg_reg = False                                          # max_rays is the capacity as given

@@ -87,7 +87,7 @@ def test_library_exports_every_declared_symbol():
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in include/hsb200.h but not exported"
     lib.hsb_abi_version.restype = ctypes.c_int
-    assert lib.hsb_abi_version() == 1
+    assert lib.hsb_abi_version() == 2
 
 
 def test_conf_reader_matches_reference_conf_format():
