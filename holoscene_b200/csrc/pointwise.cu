@@ -549,14 +549,6 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
     }
 }
 
-// dS[p, kstar[p]] += dsdf[p]  (scene-SDF term lands in its arg-min channel)
-__global__ void __launch_bounds__(256) add_min_grad_kernel(const float* __restrict__ dsdf, const int* __restrict__ kstar,
-                                                           long long N, int Kp, float* __restrict__ dS) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
-    dS[p * Kp + kstar[p]] += dsdf[p];
-}
-
 // ---- camera rays (utils/rend_util.py:56-98,112-125 called twice from model/network.py:788-792) -------------------------
 // One thread per pixel.  Reproduces the reference's in-place side effect: get_camera_params adds ray_offset to uv, and the
 // model calls it a second time (identity pose, same offset) to obtain depth_scale = z of the unit camera-space direction,
@@ -716,10 +708,4 @@ int launch_eik_points(const float* uniform, const float* o, const float* d, cons
     eik_points_kernel<<<cdiv(6LL * n, 256), 256, 0, st>>>(uniform, o, d, z_eik, noise, n, out);
     return check_launch("eik_points");
 }
-int launch_add_min_grad(const float* dsdf, const int* kstar, long long N, int Kp, float* dS, cudaStream_t st) {
-    if (N == 0) return HSB_OK;
-    add_min_grad_kernel<<<cdiv(N, 256), 256, 0, st>>>(dsdf, kstar, N, Kp, dS);
-    return check_launch("add_min_grad");
-}
-
 }  // namespace hsb

@@ -69,7 +69,6 @@ int launch_camera_rays(float* uv, const float* offset, const float* pose, const 
                        float* depth_scale, cudaStream_t st);
 int launch_eik_points(const float* uniform, const float* o, const float* d, const float* z_eik, const float* noise, int n, float* out,
                       cudaStream_t st);
-int launch_add_min_grad(const float* dsdf, const int* kstar, long long N, int Kp, float* dS, cudaStream_t st);
 int launch_composite_fwd(const CompositeArgs& a, cudaStream_t st);
 int launch_composite_bwd(const CompositeArgs& a, const CompositeGrads& g, cudaStream_t st);
 
