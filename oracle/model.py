@@ -507,6 +507,55 @@ def model_forward(sd, cfg, uv, pose, intrinsics, training, iter_step, draws: Dra
 # --------------------------------------------------------------------------------------------
 # losses (model/loss.py)
 # --------------------------------------------------------------------------------------------
+def subset_pass(sd, cfg, ray_origins, ray_dirs, pose, obj_idxs, subset_obj_idxs, z_vals, near_far=False, detach_rgb=False):
+    """HoloSceneNetwork.forward_multi_obj_rays_subset_all_sdf and its _near_far / _detach_rgb_for_geometry[_near_far] variants
+    (network.py:1235-1531) AFTER the sampler: z_vals [R,S] are given (the sampler is sample_z_vals with idx = obj_idxs).  Per-point
+    part = get_multi_specific_outputs_subset_objs (network.py:408-435).  Differentiable w.r.t. the (trainable) state dict."""
+    o = ray_origins.reshape(-1, 3)
+    d = F.normalize(ray_dirs.reshape(-1, 3), dim=-1)
+    rot = pose[..., :3, :3].reshape(3, 3).permute(1, 0).contiguous()
+    depth_scale = (rot @ d.permute(1, 0)).permute(1, 0)[:, 2:]
+    R, S = z_vals.shape
+    x = (o.unsqueeze(1) + z_vals.unsqueeze(2) * d.unsqueeze(1)).reshape(-1, 3).detach().requires_grad_(True)
+    dirs = d.unsqueeze(1).repeat(1, S, 1).reshape(-1, 3)
+    sdf_raw, feature = implicit_forward(sd, cfg, x)
+    sub = sdf_raw[:, list(subset_obj_idxs)]
+    semantic = cfg.sigmoid * torch.sigmoid(-cfg.sigmoid * sub)
+    sdf, _ = min_sdf(sub)
+    grads = torch.autograd.grad(sdf, x, torch.ones_like(sdf), create_graph=True, retain_graph=True)[0]
+    sdf_obj, _ = min_sdf(sdf_raw[:, list(obj_idxs)])
+    rgb = rendering_forward(sd, cfg, x, grads.detach() if detach_rgb else grads, dirs, feature).reshape(R, S, 3)
+    beta = get_beta(sd, cfg)
+    weights, _, _ = volume_weights(z_vals, sdf, beta)
+    bg_weights, _, _ = volume_weights(z_vals, sdf_obj, beta)
+    rgb_values = torch.sum((bg_weights.detach() if detach_rgb else bg_weights).unsqueeze(-1) * rgb, 1)
+    wz = torch.sum(bg_weights * z_vals, 1, keepdim=True)
+    normalised = wz / (bg_weights.sum(dim=1, keepdim=True) + 1e-8)
+    plain_nf = near_far and not detach_rgb              # only this variant returns the raw sums (network.py:1347,1353)
+    depth_values = depth_scale * (wz if plain_nf else normalised)
+    opacity = bg_weights.sum(-1).reshape(-1) if plain_nf else weights.sum(-1, keepdim=True)
+    normals = (grads / (grads.norm(2, -1, keepdim=True) + 1e-6)).reshape(R, S, 3)
+    normal_map = (rot @ torch.sum(bg_weights.unsqueeze(-1) * normals, 1).permute(1, 0)).permute(1, 0).contiguous()
+    return {"rgb": rgb, "semantic_values": torch.sum(weights.unsqueeze(-1) * semantic.reshape(R, S, -1), 1), "opacity": opacity,
+            "rgb_values": rgb_values, "depth_values": depth_values, "z_vals": z_vals, "depth_vals": z_vals * depth_scale,
+            "sdf": sdf.reshape(R, S), "weights": weights, "bg_weights": bg_weights, "normal_map": normal_map}
+
+
+def point_constraint_losses(sd, cfg, obj_i, points, sdfs):
+    """get_pts_sdf_contraints_loss, get_pts_sdf_maintain_loss, get_additional_sdf_loss (network.py:973-1013) -> three scalars."""
+    x = points.reshape(-1, 3).detach().requires_grad_(True)
+    y, _ = implicit_forward(sd, cfg, x, with_color=False)
+    s = y[:, obj_i]
+    g = torch.autograd.grad(s, x, torch.ones_like(s), create_graph=True, retain_graph=True)[0]
+    eik = ((g.norm(2, dim=1) - 1) ** 2).mean()
+    sdfs = sdfs.reshape(-1)
+
+    def hinge(delta):
+        m = delta > 0
+        return torch.mean(delta[m]) if bool(m.any()) else torch.zeros(())
+    return hinge(-s - sdfs) * 5.0 + eik * 0.1, hinge(s - sdfs) * 3.0 + eik * 0.1, torch.mean(torch.abs(sdfs - s)) * 10.0 + eik * 0.1
+
+
 def scale_shift(pred, target):
     """compute_scale_and_shift_batch (loss.py:181-193) for B=1: 2x2 normal equations via inverse."""
     d = pred.reshape(-1)

@@ -66,3 +66,24 @@ def grad_tol(name, base, e2e=False):
     if e2e and "embeddings" in name:
         return 5e-2
     return base
+
+
+# ---- Stage 2 (N1): the novel-view loss the subset-pass goldens were recorded under (tests/golden/make_golden_stage2_bwd.py) ----
+NOVEL_VIEW_LAMBDA = {"mask": 2.0, "rgb": 1.0, "nm_l1": 0.5, "nm_cos": 0.5, "depth": 0.7}
+NOVEL_VIEW_BG_COLOR = (1.0, 0.5, 0.25)
+
+
+def novel_view_loss(out, tgt):
+    """calculate_invisible_loss, masked branch with every ray foreground (training/holoscene_train_post.py:558-631)."""
+    F = torch.nn.functional
+    lam = NOVEL_VIEW_LAMBDA
+    rgb_pred, normal_pred = out["rgb_values"].reshape(-1, 3), out["normal_map"].reshape(-1, 3)
+    mask_pred, depth_pred = out["opacity"].reshape(-1), out["depth_values"].reshape(-1)
+    bg = torch.tensor(NOVEL_VIEW_BG_COLOR, device=rgb_pred.device).reshape(1, 3)
+    rgb_pred = rgb_pred * mask_pred.unsqueeze(-1) + (1 - mask_pred.unsqueeze(-1)) * (torch.ones_like(rgb_pred) * bg)
+    loss = lam["mask"] * F.mse_loss(mask_pred, tgt["mask"]).mean()
+    loss = loss + lam["rgb"] * F.l1_loss(rgb_pred, tgt["rgb"]).mean()
+    loss = loss + lam["nm_l1"] * F.l1_loss(normal_pred, tgt["normal"]).mean()
+    loss = loss + lam["nm_cos"] * (1 - F.cosine_similarity(normal_pred, tgt["normal"], dim=-1).mean())
+    loss = loss + lam["depth"] * F.l1_loss(depth_pred, tgt["depth"]).mean()
+    return loss

@@ -206,3 +206,53 @@ def test_shift_sdf_raw_matches_reference_rule(K):
     assert float((got - want).abs().max()) < 2e-4, float((got - want).abs().max())
     assert float((m.implicit_network.get_sdf_raw(x.cuda()).cpu() - raw).abs().max()) < 2e-4
     assert float((m.implicit_network.get_sdf_vals(x.cuda()).cpu() - sdf).abs().max()) < 2e-4
+
+
+# (K, R, S, obj_idxs, subset_obj_idxs, detach_rgb): channel sets with members above bit 31 of the masks, obj != subset (two different
+# arg-min channels per sample), the all-objects set Stage 2 passes as `subset_idxs`, and the Kp = 24 tail
+SUBSET_CASES = [(64, 96, 192, [33, 40, 63, 5], [0, 33, 40, 63, 5, 17], False),
+                (32, 128, 128, list(range(1, 32)), list(range(1, 32)), True),
+                (21, 128, 128, [20], [20, 3], False)]
+
+
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("K,R,S,obj,sub,detach", SUBSET_CASES)
+def test_subset_pass_backward_matches_oracle_at_baseline_K(K, R, S, obj, sub, detach, precise):
+    """N1 at BASELINE's channel counts and the full 2^19-entry tables: hsb_render_forward_subset / hsb_render_backward_subset (composite
+    mode 2, both weight sets, all six cotangents incl. the raw sums of the near/far variant) against autograd on oracle.model.subset_pass
+    (itself pinned to the reference's goldens, tests/test_oracle_model.py) on identical sample positions."""
+    from holoscene_b200 import engine as E
+    from oracle import model as om
+    cfg = _cfg(K, S)
+    sd = common.seeded_state_dict(cfg)
+    m = build_model(cfg, sd, precise, max_rays=R)
+    m.train()
+    eng = m.engine()
+    m._attach_grads()
+    eng.prepare()
+    gen, o, d, z, _, rot = _rays(R, S, 5 + K)
+    pose = torch.eye(4)
+    pose[:3, :3] = rot.t()                                     # subset_pass derives rot = pose[:3,:3]^T and the depth scale from it
+    ds = (rot @ d.t()).t()[:, 2:].contiguous()
+    cot = [torch.randn(R, n, generator=gen) for n in (3, 1, 3, 1)] + [torch.randn(R, generator=gen), torch.randn(R, generator=gen)]
+    p = om.trainable(sd)
+    ref = om.subset_pass(p, cfg, o, d, pose, obj, sub, z, near_far=False, detach_rgb=detach)
+    bw = ref["bg_weights"]
+    outs = [ref["rgb_values"], ref["depth_values"], ref["normal_map"], ref["opacity"], bw.sum(1), (bw * z).sum(1)]
+    sum((a * b).sum() for a, b in zip(outs, cot)).backward()
+    got = eng.render_forward_subset(o.cuda(), d.cuda(), z.cuda(), ds.cuda(), rot.cuda(), sub, obj, E.SLOT_MAIN, detach)
+    wsum, wzsum = eng.buffer("main.WSUM")[:R, 0].clone(), eng.buffer("main.WZSUM")[:R, 0].clone()
+    eng.render_backward_subset(E.SLOT_MAIN, *[c.cuda() for c in cot])
+    eng.finish()
+    torch.cuda.synchronize()
+    ot = 5e-4 if precise else FAST_OUT_TOL
+    rows = [(n, common.rel_err(a.cpu(), b.detach()), ot) for n, a, b in
+            (("rgb_values", got[0], outs[0]), ("depth_values", got[1], outs[1]), ("normal_map", got[2], outs[2]), ("opacity", got[3], outs[3]),
+             ("sum bg_w", wsum, outs[4]), ("sum bg_w z", wzsum, outs[5]), ("semantic_values", got[4], ref["semantic_values"][:, [sub.index(k) for k in sorted(sub)]]))]   # the kernel packs ascending
+    for n, prm in m.named_parameters():
+        g0 = p[n].grad if p[n].grad is not None else torch.zeros_like(p[n])
+        tol = common.grad_tol(n, 2e-3) if precise else (FAST_GRAD_TOL if common.grad_tol(n, 2e-3) == 2e-3 else FAST_GRAD_TOL_COLOUR)
+        rows.append(("grad_" + n, common.rel_err(prm.grad.cpu(), g0), tol))
+    report(f"subset pass K={K} R={R} S={S} obj={obj[:4]} sub={sub[:4]} detach={detach} logmap 19 precise={precise}", rows)
+    bad = [r for r in rows if not (r[1] <= r[2])]
+    assert not bad, bad

@@ -44,3 +44,46 @@ def test_oracle_matches_reference_golden(name):
             got = p[k[5:]].grad
             got = torch.zeros_like(p[k[5:]]) if got is None else got
             assert common.rel_err(got, ref) < common.grad_tol(k, 5e-3), (k, common.rel_err(got, ref))
+
+
+@pytest.mark.parametrize("name", ["stage2_bwd_subset", "stage2_bwd_near_far", "stage2_bwd_detach", "stage2_bwd_detach_near_far"])
+def test_oracle_subset_pass_matches_reference_golden(name):
+    """oracle.model.subset_pass (the Stage-2 object-subset pass after the sampler, all four variants) against the reference's own
+    Python under Stage 2's novel-view loss: outputs, loss and every parameter gradient (tests/golden/make_golden_stage2_bwd.py).
+    The golden's z_vals are fed in, so the bound is re-association noise only."""
+    g = common.load_golden(name)
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    assert abs(common.param_checksum(sd) - float(g["check_param_sum"])) < 1e-6 * float(g["check_param_sum"])
+    p = om.trainable(sd)
+    method = str(g["meta_method"])
+    o, d, pose, z = (torch.from_numpy(g[k]) for k in ("in_ray_origins", "in_ray_dirs", "in_pose", "out_z_vals"))
+    out = om.subset_pass(p, cfg, o, d, pose, [int(k) for k in g["meta_obj_idxs"]], [int(k) for k in g["meta_subset_idxs"]], z,
+                         near_far=method.endswith("near_far"), detach_rgb="detach" in method)
+    for k in ("rgb_values", "normal_map", "opacity", "depth_values"):
+        ref = g["out_" + k]
+        got = out[k].detach().numpy()
+        assert got.shape == ref.shape, (k, got.shape, ref.shape)
+        assert float(np.abs(got - ref).max()) <= 1e-4 * max(1.0, float(np.abs(ref).max())), (k, float(np.abs(got - ref).max()))
+    tgt = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("tgt_")}
+    loss = common.novel_view_loss(out, tgt)
+    loss.backward()
+    assert abs(float(loss) - float(g["loss_total"])) <= 1e-5 * max(1.0, abs(float(g["loss_total"])))
+    for k, ref in g.items():
+        if k.startswith("grad_"):
+            got = p[k[5:]].grad
+            got = torch.zeros_like(p[k[5:]]) if got is None else got
+            assert common.rel_err(got, ref) < 2e-3, (k, common.rel_err(got, ref))
+
+
+def test_oracle_point_constraint_losses_match_reference_golden():
+    g = common.load_golden("stage2_pts_losses")
+    cfg = common.cfg_from_golden(g)
+    p = om.trainable(common.seeded_state_dict(cfg))
+    la, lb, lc = om.point_constraint_losses(p, cfg, int(g["meta_obj_i"]), torch.from_numpy(g["in_points"]), torch.from_numpy(g["in_sdfs"]))
+    (la + lb + lc).backward()
+    for n, v in (("constraints", la), ("maintain", lb), ("additional", lc)):
+        assert abs(float(v) - float(g["loss_" + n])) <= 1e-5 * max(1.0, abs(float(g["loss_" + n]))), n
+    for k, ref in g.items():
+        if k.startswith("grad_") and float(np.abs(ref).max()) > 0:
+            assert common.rel_err(p[k[5:]].grad, ref) < 2e-3, (k, common.rel_err(p[k[5:]].grad, ref))

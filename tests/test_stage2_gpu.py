@@ -10,23 +10,7 @@ from tests.test_step_gpu import build_model, make_loss, report
 
 pytestmark = pytest.mark.gpu
 
-LAMBDA = {"mask": 2.0, "rgb": 1.0, "nm_l1": 0.5, "nm_cos": 0.5, "depth": 0.7}
-BG_COLOR = (1.0, 0.5, 0.25)
-
-
-def novel_view_loss(out, tgt):
-    """calculate_invisible_loss, masked branch with every ray foreground (training/holoscene_train_post.py:558-631)."""
-    F = torch.nn.functional
-    rgb_pred, normal_pred = out["rgb_values"].reshape(-1, 3), out["normal_map"].reshape(-1, 3)
-    mask_pred, depth_pred = out["opacity"].reshape(-1), out["depth_values"].reshape(-1)
-    bg = torch.tensor(BG_COLOR, device=rgb_pred.device).reshape(1, 3)
-    rgb_pred = rgb_pred * mask_pred.unsqueeze(-1) + (1 - mask_pred.unsqueeze(-1)) * (torch.ones_like(rgb_pred) * bg)
-    loss = LAMBDA["mask"] * F.mse_loss(mask_pred, tgt["mask"]).mean()
-    loss = loss + LAMBDA["rgb"] * F.l1_loss(rgb_pred, tgt["rgb"]).mean()
-    loss = loss + LAMBDA["nm_l1"] * F.l1_loss(normal_pred, tgt["normal"]).mean()
-    loss = loss + LAMBDA["nm_cos"] * (1 - F.cosine_similarity(normal_pred, tgt["normal"], dim=-1).mean())
-    loss = loss + LAMBDA["depth"] * F.l1_loss(depth_pred, tgt["depth"]).mean()
-    return loss
+novel_view_loss = common.novel_view_loss
 
 
 def stage2_model(g, precise, **extra):
