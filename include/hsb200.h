@@ -11,6 +11,9 @@
  *     zero features / zero gradients (hashencoder/src/hashencoder.cu:124-149).
  *   - all floating point data is fp32, indices are int32; D = 3 and C = 2 features per level are fixed
  *     (the only instantiation the Stage-1 path uses: float, D=3, C=2, L=16).
+ *   - one CUDA device per process (the one-process-per-GPU model the multi-GPU path uses): per-kernel launch attributes
+ *     (opt-in shared memory sizes, the tcgen05 capability probe) are established once per process on the device current at
+ *     first use; a context (hsb_ctx) is used from one host thread at a time.
  *
  * Section B2 replaces the reference's native FFI
  *     hashencoder/src/hashencoder.h:13-15, bound in hashencoder/src/bindings.cpp:5-9 and called from
