@@ -172,3 +172,27 @@ def test_mesh_colouring_queries_match_reference_golden(precise):
     report(f"stage2_colors precise={precise}", rows)
     bad = [r for r in rows if not (r[1] <= r[2])]
     assert not bad, bad
+
+
+def test_model_survives_a_cpu_round_trip():
+    """Stage 2 moves its per-object models between devices (`local_model.cpu()` after a re-fit, `.cuda()` again later,
+    training/holoscene_train_post.py:3730+): parameters are views of the flat device buffers, so a round trip must re-flatten them and
+    rebuild the context; outputs afterwards are bit-identical and training continues."""
+    g = common.load_golden("stage2_bwd_near_far")
+    m = stage2_model(g, True)
+    out0, loss0 = run_subset(m, g)
+    loss0.backward()
+    sd0 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    m = m.cpu()
+    assert all(not p.is_cuda for p in m.parameters())
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd0[k]), k
+    m = m.cuda()
+    m.zero_grad()
+    out1, loss1 = run_subset(m, g)
+    for k in ("rgb_values", "normal_map", "opacity", "depth_values", "z_vals"):
+        assert torch.equal(out0[k], out1[k]), k
+    loss1.backward()
+    torch.cuda.synchronize()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+    assert float(m.implicit_network.lin1.weight_v.grad.abs().max()) > 0
