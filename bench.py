@@ -554,9 +554,9 @@ def main():
             for name in ("c3", "c5shard", "c1", "trained"):
                 if name == args.workload:
                     continue
-                # "trained": the round count changes from step to step on this synthetic field, every change costs a graph capture or
-                # a discarded replay -- timed kernel by kernel with the speculative sampler instead
-                x = Bench(WORKLOADS[name], WORKLOADS[name]["R"], rank, world, dev, graph=(not args.no_graph) and name != "trained")
+                # "trained": the round count changes from step to step on this synthetic field; TrainStep then runs in split mode
+                # (sampler kernel by kernel, the rest of the step from a graph whose shapes do not depend on the round count)
+                x = Bench(WORKLOADS[name], WORKLOADS[name]["R"], rank, world, dev, graph=not args.no_graph)
                 r = x.result(*x.run(**short))
                 r["step_roofline"] = step_roofline(WORKLOADS[name], x.R, r["sampler_rounds"], int(x.model.engine().total), r["ms_per_step"], peaks)
                 extra[name] = r

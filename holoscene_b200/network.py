@@ -375,7 +375,52 @@ class HoloSceneNetwork(nn.Module):
             if isinstance(draws, LiveDraws):
                 self.draws = None
 
-    def _forward(self, eng, intrinsics, uv, pose, iter_step, draws, dev, speculate=False):
+    # ---- the same forward in two calls (TrainStep's split mode: sampler kernel by kernel, the rest replayed from a CUDA graph) ----
+    def sample_rays(self, input):
+        """Phase 1: camera rays + error-bound sampler for input["uv"] (updated in place like forward does).  The speculative
+        convergence test is verified right here, so a wrong round-count guess costs a repeat of the sampler only.  Training mode,
+        live random draws.  -> the tuple render_rays() takes."""
+        intrinsics, uv, pose = input["intrinsics"], input["uv"], input["pose"]
+        if not (self.training and self.draws is None):
+            raise RuntimeError("sample_rays / render_rays serve the training step with live random draws; use forward() otherwise")
+        dev = uv.device
+        eng = self.engine()
+        if uv.shape[1] > eng.max_rays:
+            raise RuntimeError(f"{uv.shape[1]} rays exceed hsb_max_rays={eng.max_rays} (set model.hsb_max_rays in the conf)")
+        draws = LiveDraws(dev)
+        self.draws = draws
+        self.ray_sampler._pending.clear()
+        self._pts_pending.clear()
+        try:
+            if not self.speculative_sampler:
+                return self._sample(eng, intrinsics, uv, pose, draws, False)
+            uv0 = uv.clone()
+            rng = torch.cuda.get_rng_state(dev)
+            rays = self._sample(eng, intrinsics, uv, pose, draws, True)
+            if self.ray_sampler.verify():
+                return rays
+            uv.copy_(uv0)                                    # start over with the same random numbers, reading the flag every round
+            torch.cuda.set_rng_state(rng, dev)
+            return self._sample(eng, intrinsics, uv, pose, draws, False)
+        finally:
+            self.draws = None
+
+    def render_rays(self, input, rays, iter_step=-1):
+        """Phase 2: scene pass + eikonal pass + autograd node from the sampler's outputs; forward(input) == render_rays(input,
+        sample_rays(input)).  Steps with the background patch (its own sampler call) go through forward()."""
+        if self.use_bg_reg and iter_step % self.render_bg_iter == 0:
+            raise RuntimeError("background-patch step: call forward()")
+        dev = rays[0].device
+        draws = LiveDraws(dev)
+        self.draws = draws
+        try:
+            return self._render(self.engine(), input["intrinsics"], input["uv"].shape, input["pose"], iter_step, draws, dev, rays)
+        finally:
+            self.draws = None
+
+    def _sample(self, eng, intrinsics, uv, pose, draws, speculate=False):
+        """First phase of forward (network.py:778-797): weight materialisation, camera rays of the jittered pixels, the error-bound
+        sampler.  -> (ray_dirs [R,3], cam_loc [R,3], depth_scale [R,1], z_vals [R,S], z_samples_eik [R,1])."""
         training = self.training
         if training:
             self._attach_grads()
@@ -384,9 +429,6 @@ class HoloSceneNetwork(nn.Module):
         # one kernel for both get_camera_params calls of the reference (real pose -> ray_dirs; identity pose on the again-
         # jittered pixel -> depth scale), including the in-place shift of uv (network.py:788-792, rend_util.py:70-75)
         ray_dirs, cam_loc, depth_scale = _engine.camera_rays(uv, pose, intrinsics, ray_offset)
-        batch_size, num_pixels = uv.shape[0], uv.shape[1]
-        R = ray_dirs.shape[0]
-
         if self.phase_ms is not None:
             import time
             torch.cuda.synchronize(); _t0 = time.perf_counter()
@@ -394,6 +436,18 @@ class HoloSceneNetwork(nn.Module):
         z_vals = z_vals.contiguous()
         if self.phase_ms is not None:
             torch.cuda.synchronize(); self.phase_ms["sampler"] = self.phase_ms.get("sampler", 0.0) + (time.perf_counter() - _t0) * 1e3
+        return ray_dirs, cam_loc, depth_scale, z_vals, z_samples_eik
+
+    def _forward(self, eng, intrinsics, uv, pose, iter_step, draws, dev, speculate=False):
+        rays = self._sample(eng, intrinsics, uv, pose, draws, speculate)
+        return self._render(eng, intrinsics, uv.shape, pose, iter_step, draws, dev, rays, speculate)
+
+    def _render(self, eng, intrinsics, uv_shape, pose, iter_step, draws, dev, rays, speculate=False):
+        """Second phase of forward (network.py:799-971): scene pass, eikonal pass, background patch, autograd node."""
+        training = self.training
+        ray_dirs, cam_loc, depth_scale, z_vals, z_samples_eik = rays
+        batch_size, num_pixels = uv_shape[0], uv_shape[1]
+        R = ray_dirs.shape[0]
         S = z_vals.shape[1]
         rot = pose[0, :3, :3].permute(1, 0).contiguous()
         rgbv, depth, nmap, opac, sem = eng.render_forward(_engine.SLOT_MAIN, cam_loc, ray_dirs, z_vals, depth_scale, rot)

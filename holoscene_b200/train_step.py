@@ -9,7 +9,10 @@ outside, after the replay: the host decision of the error-bound sampler (referen
 count the previous step needed, ships the per-round convergence flags to pinned memory right after the sampler, and the host judges
 them while the rest of the graph is still running; on a wrong guess the step's gradients are discarded and the step is repeated kernel
 by kernel in exact mode -- then the gradient all-reduce and Adam (learning rate and bias corrections change every step; three
-launches).  Steps with the background patch (every 10th; its corner is a host-side random draw and its sampler has its own round
+launches).  While the round count is unknown or has just changed (a trained scene with a sharp density needs 1-5 rounds, varying from
+batch to batch) the step runs in SPLIT mode instead: camera rays + sampler kernel by kernel with the guess verified right after the
+sampler (a wrong guess repeats the sampler only, ~1 ms), then everything after the sampler -- whose shapes do not depend on the round
+count -- replayed from a second graph.  Steps with the background patch (every 10th; its corner is a host-side random draw and its sampler has its own round
 count) and everything non-standard (replayed random draws, eval mode, loss-weight decay schedules) run kernel by kernel.
 
 Multi-GPU: one process per GPU, identical replicas, each rank renders its own shard of the rays; after
@@ -35,7 +38,7 @@ class _Captured:
 
 class TrainStep:
     def __init__(self, model, loss_fn, optimizer: StageOneAdam, add_objectvio_iter=25000, world_size=1, use_graph=False,
-                 graph_after=2, union_batch=False):
+                 graph_after=2, union_batch=False, split_only=False):
         self.model, self.loss_fn, self.opt = model, loss_fn, optimizer
         self.add_objectvio_iter = add_objectvio_iter
         self.world_size = world_size
@@ -43,6 +46,7 @@ class TrainStep:
         self.phase_ms = None      # set to {} to collect per-phase device+host times (adds syncs; not for headline numbers)
         self.use_graph = use_graph
         self.graph_after = graph_after          # eager steps before the first capture (allocator / autograd warm-up, round-count guess)
+        self.split_only = split_only            # never bake a round count into a graph (scenes whose count changes from batch to batch)
         self._graphs = {}
         self._static_in = self._static_gt = None
         self._tag = 0
@@ -50,7 +54,8 @@ class TrainStep:
         self._eager_steps = 0
         self._cooldown = 0                      # kernel-by-kernel steps left after a wrong round-count guess (an unstable count makes replays a loss)
         self._graph_kernels = 0                 # libhsb200 kernels executed through graph replays so far
-        self.stats = {"captures": 0, "replays": 0, "misses": 0, "eager": 0}
+        self.stats = {"captures": 0, "replays": 0, "misses": 0, "eager": 0, "split": 0}
+        self._static_rays = None
         # union_batch: the ranks' equal ray shards reproduce the single-process step on the union batch -- the two places where rays
         # couple are exchanged: the depth term's least-squares sums (two 16-double all-reduces inside the loss) and the sampler's global
         # convergence test (one 4-byte MAX all-reduce per refinement round, host-synchronous like the reference's own .item()).
@@ -108,20 +113,24 @@ class TrainStep:
         return out, losses
 
     # ---- graph step ---------------------------------------------------------------------------------------------------------
-    def _graph_ok(self):
+    def _graph_mode(self):
+        """"full": the whole device part of the step from one graph (round count guessed); "split": sampler kernel by kernel, the rest
+        from a graph; None: kernel by kernel."""
         m = self.model
         if not (self.use_graph and self.phase_ms is None and m.training and m.speculative_sampler and m.draws is None):
-            return False
+            return None
         if m.use_bg_reg and self.iter_step % m.render_bg_iter == 0:
-            return False                        # background-patch step: host-side random patch corner, second sampler call
+            return None                         # background-patch step: host-side random patch corner, second sampler call
         if getattr(self.loss_fn, "end_step", -1) > 0:
-            return False                        # loss weights decay with the step count: they would be baked into the graph
+            return None                         # loss weights decay with the step count: they would be baked into the graph
         if self._eager_steps < self.graph_after:
-            return False
-        if self._cooldown > 0:
+            return None
+        if self.split_only:
+            return "split"
+        if self._cooldown > 0:                  # the round count changed recently: a full-graph replay is likely to be discarded
             self._cooldown -= 1
-            return False
-        return m.ray_sampler._rounds_guess.get(-1) is not None
+            return "split"
+        return "full" if m.ray_sampler._rounds_guess.get(-1) is not None else "split"
 
     def _static(self, model_input, ground_truth, dev):
         def same(bufs, src):
@@ -130,6 +139,7 @@ class TrainStep:
             self._static_in = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in model_input.items()}
             self._static_gt = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in ground_truth.items()}
             self._graphs.clear()
+            self._static_rays = None
             n = self.model.ray_sampler.max_total_iters + 1
             self._tag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
             self._tag_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -160,6 +170,41 @@ class TrainStep:
         self._graphs[key] = rec
         self.stats["captures"] += 1
         return rec
+
+    def _split_step(self, model_input, ground_truth, indices):
+        m = self.model
+        dev = m.density.beta.device
+        self._static(model_input, ground_truth, dev)
+        rays = m.sample_rays(self._static_in)                      # kernel by kernel; the guess is verified (and corrected) in here
+        if self._static_rays is None or any(b.shape != r.shape for b, r in zip(self._static_rays, rays)):
+            self._static_rays = [torch.empty_like(r) for r in rays]
+            for k in [k for k in self._graphs if k[0] == "split"]:
+                del self._graphs[k]
+        for b, r in zip(self._static_rays, rays):
+            b.copy_(r)
+        call_reg = self.iter_step >= self.add_objectvio_iter
+        key = ("split", self._static_in["uv"].shape[1], call_reg)
+        rec = self._graphs.get(key)
+        if rec is None:
+            rec = _Captured()
+            self.opt.zero_grad()
+            k0 = _lib.launch_count()
+            rec.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(rec.graph):
+                m.engine().grads.zero_()
+                out = m.render_rays(self._static_in, tuple(self._static_rays), iter_step=self.iter_step)
+                out["iter_step"] = self.iter_step
+                losses = self.loss_fn(out, self._static_gt, call_reg=call_reg)
+                losses["loss"].backward()
+            rec.out, rec.losses, rec.rounds = out, losses, None
+            rec.kernels = _lib.launch_count() - k0
+            self._graphs[key] = rec
+            self.stats["captures"] += 1
+        rec.graph.replay()
+        self._graph_kernels += rec.kernels
+        self.stats["split"] += 1
+        self._finish_step()
+        return rec.out, rec.losses
 
     def _graph_step(self, model_input, ground_truth, indices):
         m = self.model
@@ -192,6 +237,9 @@ class TrainStep:
 
     def __call__(self, model_input, ground_truth, indices=None):
         """model_input / ground_truth may live in (pinned) host memory; they are copied to the device here."""
-        if self._graph_ok():
+        mode = self._graph_mode()
+        if mode == "full":
             return self._graph_step(model_input, ground_truth, indices)
+        if mode == "split":
+            return self._split_step(model_input, ground_truth, indices)
         return self._eager_step(model_input, ground_truth, indices)

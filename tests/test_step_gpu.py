@@ -583,13 +583,50 @@ def test_cuda_graph_step_matches_kernel_by_kernel_step():
         torch.cuda.synchronize()
         runs[use_graph] = (losses, step.graph_stats(), m._flat.clone())
     st = runs[True][1]
-    assert st["captures"] >= 1 and st["replays"] >= 5 and st["misses"] >= 1, st
+    assert st["captures"] >= 2 and st["replays"] >= 5 and st["misses"] >= 1 and st["split"] >= 1, st   # split mode while cooling down
     assert runs[False][1]["replays"] == 0
     a, b = runs[True][0], runs[False][0]
     print("\n[graph vs eager losses]", [f"{x:.5f}/{y:.5f}" for x, y in zip(a, b)], st)
     for x, y in zip(a[:7], b[:7]):                    # identical random streams until the poisoned step repeats (and re-draws)
         assert abs(x - y) <= 2e-3 * abs(y), (a, b)
     assert all(np.isfinite(a))
+
+
+def test_split_graph_step_matches_kernel_by_kernel_step():
+    """TrainStep split mode (sampler kernel by kernel with the round-count guess verified right after it, everything after the sampler
+    replayed from a CUDA graph): the same loss sequence and -- up to the summation order of atomics -- the same parameters as launching
+    every kernel, with a sharp density (beta = 0.01: several refinement rounds) and a poisoned guess in the middle (only the sampler is
+    repeated, nothing is discarded)."""
+    from holoscene_b200.optim import StageOneAdam
+    from holoscene_b200.train_step import TrainStep
+    g = common.load_golden("step_train")
+    cfg = common.cfg_from_golden(g)
+    sd = common.seeded_state_dict(cfg)
+    sd["density.beta"] = torch.tensor(0.01)
+    uv, pose, K, gt, _ = common.golden_inputs(g)
+    runs = {}
+    for split in (False, True):
+        m = build_model(cfg, sd, False).train()
+        step = TrainStep(m, make_loss(), StageOneAdam(m), use_graph=split, split_only=True)
+        step.iter_step = 1
+        torch.manual_seed(78)
+        losses, rounds = [], []
+        for it in range(9):
+            if split and it == 5:
+                m.ray_sampler._rounds_guess[-1] = max(1, m.ray_sampler._rounds_guess[-1] - 1)      # poison the guess once
+            out, lo = step({"uv": uv.clone().cuda(), "intrinsics": K.cuda(), "pose": pose.cuda()}, gt)
+            losses.append(float(lo["loss"]))
+            rounds.append(m.ray_sampler.last_rounds)
+        torch.cuda.synchronize()
+        runs[split] = (losses, rounds, step.graph_stats(), m._flat.clone(), m.ray_sampler.spec_misses)
+    st = runs[True][2]
+    print("\n[split vs eager losses]", [f"{x:.5f}/{y:.5f}" for x, y in zip(runs[True][0], runs[False][0])], runs[True][1], st)
+    assert st["split"] == 7 and st["captures"] == 1 and st["replays"] == 0 and st["misses"] == 0, st
+    assert runs[True][4] >= 1                                   # the poisoned guess was caught by the sampler's own verify()
+    assert runs[True][1] == runs[False][1] and max(runs[True][1]) >= 2, (runs[True][1], runs[False][1])
+    for x, y in zip(runs[True][0], runs[False][0]):
+        assert abs(x - y) <= 2e-3 * abs(y), (runs[True][0], runs[False][0])
+    assert common.rel_err(runs[True][3], runs[False][3]) < 1e-4
 
 
 @pytest.mark.parametrize("K,R,S", [(3, 50, 33), (32, 300, 128), (21, 1024, 128), (64, 150, 192)])
