@@ -557,7 +557,8 @@ def main():
                 # "trained": the round count changes from step to step on this synthetic field; TrainStep then runs in split mode
                 # (sampler kernel by kernel, the rest of the step from a graph whose shapes do not depend on the round count)
                 x = Bench(WORKLOADS[name], WORKLOADS[name]["R"], rank, world, dev, graph=not args.no_graph)
-                r = x.result(*x.run(**short))
+                # (the sharp-density workload first settles its graphs: one per round count it meets + the split-mode graph)
+                r = x.result(*x.run(**(dict(short, warmup=40) if name == "trained" else short)))
                 r["step_roofline"] = step_roofline(WORKLOADS[name], x.R, r["sampler_rounds"], int(x.model.engine().total), r["ms_per_step"], peaks)
                 extra[name] = r
                 x.close()
