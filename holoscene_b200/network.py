@@ -274,6 +274,7 @@ class HoloSceneNetwork(nn.Module):
         self._last_ne = 0
         self.phase_ms = None      # dict -> per-phase timing (debug)
         self.speculative_sampler = bool(conf.get_bool("hsb_speculative_sampler", default=True))
+        self._draws_factory = LiveDraws   # source of the random draws of sample_rays / render_rays (tests inject an order-independent one)
 
     # ---- flat parameter storage -----------------------------------------------------------------------
     def _named_segments(self):
@@ -376,10 +377,12 @@ class HoloSceneNetwork(nn.Module):
                 self.draws = None
 
     # ---- the same forward in two calls (TrainStep's split mode: sampler kernel by kernel, the rest replayed from a CUDA graph) ----
-    def sample_rays(self, input):
-        """Phase 1: camera rays + error-bound sampler for input["uv"] (updated in place like forward does).  The speculative
-        convergence test is verified right here, so a wrong round-count guess costs a repeat of the sampler only.  Training mode,
-        live random draws.  -> the tuple render_rays() takes."""
+    def sample_rays(self, input, iter_step=-1):
+        """Phase 1: camera rays + error-bound sampler for input["uv"] (updated in place like forward does) and, on a background-patch
+        step, for the patch (drawn here, i.e. BEFORE the eikonal points' random numbers -- a different but equally valid order of the
+        random stream than forward()'s).  The speculative convergence tests are verified right here, so a wrong round-count guess
+        costs a repeat of the samplers only.  Training mode, live random draws.  -> the tuple render_rays() takes (5 tensors, 9 on a
+        background-patch step)."""
         intrinsics, uv, pose = input["intrinsics"], input["uv"], input["pose"]
         if not (self.training and self.draws is None):
             raise RuntimeError("sample_rays / render_rays serve the training step with live random draws; use forward() otherwise")
@@ -387,34 +390,44 @@ class HoloSceneNetwork(nn.Module):
         eng = self.engine()
         if uv.shape[1] > eng.max_rays:
             raise RuntimeError(f"{uv.shape[1]} rays exceed hsb_max_rays={eng.max_rays} (set model.hsb_max_rays in the conf)")
-        draws = LiveDraws(dev)
+        draws = self._draws_factory(dev)
         self.draws = draws
         self.ray_sampler._pending.clear()
         self._pts_pending.clear()
+        bg_step = self.use_bg_reg and iter_step % self.render_bg_iter == 0
+
+        def both(speculate):
+            rays = self._sample(eng, intrinsics, uv, pose, draws, speculate)
+            return rays + self._bg_rays(intrinsics, pose, draws, dev, speculate) if bg_step else rays
         try:
             if not self.speculative_sampler:
-                return self._sample(eng, intrinsics, uv, pose, draws, False)
+                return both(False)
             uv0 = uv.clone()
             rng = torch.cuda.get_rng_state(dev)
-            rays = self._sample(eng, intrinsics, uv, pose, draws, True)
+            np_rng = np.random.get_state() if bg_step else None
+            rays = both(True)
             if self.ray_sampler.verify():
                 return rays
             uv.copy_(uv0)                                    # start over with the same random numbers, reading the flag every round
             torch.cuda.set_rng_state(rng, dev)
-            return self._sample(eng, intrinsics, uv, pose, draws, False)
+            if np_rng is not None:
+                np.random.set_state(np_rng)
+            return both(False)
         finally:
             self.draws = None
 
     def render_rays(self, input, rays, iter_step=-1):
-        """Phase 2: scene pass + eikonal pass + autograd node from the sampler's outputs; forward(input) == render_rays(input,
-        sample_rays(input)).  Steps with the background patch (its own sampler call) go through forward()."""
-        if self.use_bg_reg and iter_step % self.render_bg_iter == 0:
-            raise RuntimeError("background-patch step: call forward()")
+        """Phase 2: scene pass + eikonal pass (+ background patch) + autograd node from the samplers' outputs;
+        forward(input, iter_step) == render_rays(input, sample_rays(input, iter_step), iter_step)."""
+        bg_step = self.use_bg_reg and iter_step % self.render_bg_iter == 0
+        if len(rays) != (9 if bg_step else 5):
+            raise RuntimeError("render_rays: `rays` must come from sample_rays(input, iter_step) with the same iter_step")
         dev = rays[0].device
-        draws = LiveDraws(dev)
+        draws = self._draws_factory(dev)
         self.draws = draws
         try:
-            return self._render(self.engine(), input["intrinsics"], input["uv"].shape, input["pose"], iter_step, draws, dev, rays)
+            return self._render(self.engine(), input["intrinsics"], input["uv"].shape, input["pose"], iter_step, draws, dev,
+                                tuple(rays[:5]), bg_rays=tuple(rays[5:]) if bg_step else None)
         finally:
             self.draws = None
 
@@ -442,7 +455,21 @@ class HoloSceneNetwork(nn.Module):
         rays = self._sample(eng, intrinsics, uv, pose, draws, speculate)
         return self._render(eng, intrinsics, uv.shape, pose, iter_step, draws, dev, rays, speculate)
 
-    def _render(self, eng, intrinsics, uv_shape, pose, iter_step, draws, dev, rays, speculate=False):
+    def _bg_rays(self, intrinsics, pose, draws, dev, speculate=False):
+        """Rays and sample depths of the random 32 x 32 background patch (network.py:915-946): channel-0 sampler.
+        -> (cam_loc [1024,3], ray_dirs [1024,3], depth_scale [1024,1], z_vals [1024,S])."""
+        ps = 32
+        cx_2 = float(intrinsics[:, 0, 2].reshape(-1)[0]) * 2.0
+        cy_2 = float(intrinsics[:, 1, 2].reshape(-1)[0]) * 2.0
+        x0 = draws.np_randint("patch_x0", int(cx_2) - ps + 1)
+        y0 = draws.np_randint("patch_y0", int(cy_2) - ps + 1)
+        gx, gy = np.meshgrid(np.arange(ps), np.arange(ps), indexing="xy")
+        uv0 = torch.from_numpy(np.stack([gx + x0, gy + y0], -1).reshape(1, -1, 2)).float().to(dev)
+        d0, c0, ds0 = _engine.camera_rays(uv0.contiguous(), pose, intrinsics)
+        bz, _ = self.ray_sampler.get_z_vals(d0, c0, self, idx=0, speculate=speculate)
+        return c0, d0, ds0, bz.contiguous()
+
+    def _render(self, eng, intrinsics, uv_shape, pose, iter_step, draws, dev, rays, speculate=False, bg_rays=None):
         """Second phase of forward (network.py:799-971): scene pass, eikonal pass, background patch, autograd node."""
         training = self.training
         ray_dirs, cam_loc, depth_scale, z_vals, z_samples_eik = rays
@@ -471,16 +498,7 @@ class HoloSceneNetwork(nn.Module):
             output["sample_minsdf"] = smin
         bg = None
         if self.use_bg_reg and iter_step % self.render_bg_iter == 0:
-            ps = 32
-            cx_2 = float(intrinsics[:, 0, 2].reshape(-1)[0]) * 2.0
-            cy_2 = float(intrinsics[:, 1, 2].reshape(-1)[0]) * 2.0
-            x0 = draws.np_randint("patch_x0", int(cx_2) - ps + 1)
-            y0 = draws.np_randint("patch_y0", int(cy_2) - ps + 1)
-            gx, gy = np.meshgrid(np.arange(ps), np.arange(ps), indexing="xy")
-            uv0 = torch.from_numpy(np.stack([gx + x0, gy + y0], -1).reshape(1, -1, 2)).float().to(dev)
-            d0, c0, ds0 = _engine.camera_rays(uv0.contiguous(), pose, intrinsics)
-            bz, _ = self.ray_sampler.get_z_vals(d0, c0, self, idx=0, speculate=speculate)
-            bz = bz.contiguous()
+            c0, d0, ds0, bz = bg_rays if bg_rays is not None else self._bg_rays(intrinsics, pose, draws, dev, speculate)
             _, bdepth, bnmap, _, bsem = eng.render_forward(_engine.SLOT_BG, c0, d0, bz, ds0, rot)
             output["bg_mask"] = torch.argmax(bsem, dim=-1, keepdim=True)
             bg = (bdepth, bnmap)

@@ -33,7 +33,7 @@ from .rng import LiveDraws
 
 
 class _Captured:
-    __slots__ = ("graph", "out", "losses", "rounds", "kernels")
+    __slots__ = ("graph", "out", "losses", "rounds", "kernels", "rays")
 
 
 class TrainStep:
@@ -55,7 +55,6 @@ class TrainStep:
         self._cooldown = 0                      # kernel-by-kernel steps left after a wrong round-count guess (an unstable count makes replays a loss)
         self._graph_kernels = 0                 # libhsb200 kernels executed through graph replays so far
         self.stats = {"captures": 0, "replays": 0, "misses": 0, "eager": 0, "split": 0}
-        self._static_rays = None
         # union_batch: the ranks' equal ray shards reproduce the single-process step on the union batch -- the two places where rays
         # couple are exchanged: the depth term's least-squares sums (two 16-double all-reduces inside the loss) and the sampler's global
         # convergence test (one 4-byte MAX all-reduce per refinement round, host-synchronous like the reference's own .item()).
@@ -119,12 +118,12 @@ class TrainStep:
         m = self.model
         if not (self.use_graph and self.phase_ms is None and m.training and m.speculative_sampler and m.draws is None):
             return None
-        if m.use_bg_reg and self.iter_step % m.render_bg_iter == 0:
-            return None                         # background-patch step: host-side random patch corner, second sampler call
         if getattr(self.loss_fn, "end_step", -1) > 0:
             return None                         # loss weights decay with the step count: they would be baked into the graph
         if self._eager_steps < self.graph_after:
             return None
+        if m.use_bg_reg and self.iter_step % m.render_bg_iter == 0:
+            return "split"                      # background-patch step: host-side random patch corner, second sampler call
         if self.split_only:
             return "split"
         if self._cooldown > 0:                  # the round count changed recently: a full-graph replay is likely to be discarded
@@ -139,7 +138,6 @@ class TrainStep:
             self._static_in = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in model_input.items()}
             self._static_gt = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in ground_truth.items()}
             self._graphs.clear()
-            self._static_rays = None
             n = self.model.ray_sampler.max_total_iters + 1
             self._tag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
             self._tag_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -171,35 +169,46 @@ class TrainStep:
         self.stats["captures"] += 1
         return rec
 
-    def _split_step(self, model_input, ground_truth, indices):
+    def _split_graph(self, bg_step, call_reg):
+        """The graph of everything after the sampler(s), for steps with / without the background patch.  Recording does not execute
+        anything, so both variants are recorded ahead of their first use (see __call__): the cost lands in the warm-up steps."""
         m = self.model
         dev = m.density.beta.device
-        self._static(model_input, ground_truth, dev)
-        rays = m.sample_rays(self._static_in)                      # kernel by kernel; the guess is verified (and corrected) in here
-        if self._static_rays is None or any(b.shape != r.shape for b, r in zip(self._static_rays, rays)):
-            self._static_rays = [torch.empty_like(r) for r in rays]
-            for k in [k for k in self._graphs if k[0] == "split"]:
-                del self._graphs[k]
-        for b, r in zip(self._static_rays, rays):
-            b.copy_(r)
-        call_reg = self.iter_step >= self.add_objectvio_iter
-        key = ("split", self._static_in["uv"].shape[1], call_reg)
+        R = self._static_in["uv"].shape[1]
+        key = ("split", R, call_reg, bg_step)
         rec = self._graphs.get(key)
-        if rec is None:
-            rec = _Captured()
-            self.opt.zero_grad()
-            k0 = _lib.launch_count()
-            rec.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(rec.graph):
-                m.engine().grads.zero_()
-                out = m.render_rays(self._static_in, tuple(self._static_rays), iter_step=self.iter_step)
-                out["iter_step"] = self.iter_step
-                losses = self.loss_fn(out, self._static_gt, call_reg=call_reg)
-                losses["loss"].backward()
-            rec.out, rec.losses, rec.rounds = out, losses, None
-            rec.kernels = _lib.launch_count() - k0
-            self._graphs[key] = rec
-            self.stats["captures"] += 1
+        if rec is not None:
+            return rec
+        rs = m.ray_sampler
+        S = rs.N_samples + rs.N_samples_extra + 2
+        shapes = [(R, 3), (R, 3), (R, 1), (R, S), (R, 1)] + ([(1024, 3), (1024, 3), (1024, 1), (1024, S)] if bg_step else [])
+        rec = _Captured()
+        rec.rays = [torch.zeros(sh, device=dev) for sh in shapes]
+        # the step number only selects the variant inside render_rays (and is excluded from graph mode where loss weights depend on it)
+        rb = m.render_bg_iter
+        it = (self.iter_step // rb) * rb if bg_step else (self.iter_step + 1 if m.use_bg_reg and self.iter_step % rb == 0 else self.iter_step)
+        self.opt.zero_grad()
+        k0 = _lib.launch_count()
+        rec.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(rec.graph):
+            m.engine().grads.zero_()
+            out = m.render_rays(self._static_in, tuple(rec.rays), iter_step=it)
+            out["iter_step"] = it
+            losses = self.loss_fn(out, self._static_gt, call_reg=call_reg)
+            losses["loss"].backward()
+        rec.out, rec.losses, rec.rounds = out, losses, None
+        rec.kernels = _lib.launch_count() - k0
+        self._graphs[key] = rec
+        self.stats["captures"] += 1
+        return rec
+
+    def _split_step(self, model_input, ground_truth, indices):
+        m = self.model
+        self._static(model_input, ground_truth, m.density.beta.device)
+        rays = m.sample_rays(self._static_in, self.iter_step)      # kernel by kernel; the guesses are verified (and corrected) in here
+        rec = self._split_graph(len(rays) > 5, self.iter_step >= self.add_objectvio_iter)
+        for b, r in zip(rec.rays, rays):
+            b.copy_(r)
         rec.graph.replay()
         self._graph_kernels += rec.kernels
         self.stats["split"] += 1
@@ -238,6 +247,15 @@ class TrainStep:
     def __call__(self, model_input, ground_truth, indices=None):
         """model_input / ground_truth may live in (pinned) host memory; they are copied to the device here."""
         mode = self._graph_mode()
+        if mode is not None and not any(k[0] == "split" for k in self._graphs):
+            # first graph step (or new input shapes): record the split-mode graphs now, so that neither the first background-patch
+            # step nor the first change of the sampler's round count pays for a recording later
+            m = self.model
+            self._static(model_input, ground_truth, m.density.beta.device)
+            call_reg = self.iter_step >= self.add_objectvio_iter
+            self._split_graph(False, call_reg)
+            if m.use_bg_reg:
+                self._split_graph(True, call_reg)
         if mode == "full":
             return self._graph_step(model_input, ground_truth, indices)
         if mode == "split":

@@ -87,3 +87,36 @@ def novel_view_loss(out, tgt):
     loss = loss + lam["nm_cos"] * (1 - F.cosine_similarity(normal_pred, tgt["normal"], dim=-1).mean())
     loss = loss + lam["depth"] * F.l1_loss(depth_pred, tgt["depth"]).mean()
     return loss
+
+
+class NamedDraws:
+    """Order-independent random draws for tests: the i-th draw of a given name is a pure function of (seed, name, i), so two code paths
+    that consume the step's random numbers in a different order (forward() vs sample_rays() + render_rays()) see the same values."""
+
+    def __init__(self, seed, device="cuda"):
+        self.seed, self.device, self._n = seed, device, {}
+
+    def _gen(self, name):
+        import zlib
+        i = self._n.get(name, 0)
+        self._n[name] = i + 1
+        g = torch.Generator()
+        g.manual_seed(zlib.crc32(f"{self.seed}/{name}/{i}".encode()))
+        return g
+
+    def rand(self, name, *shape):
+        if len(shape) == 1 and not isinstance(shape[0], int):
+            shape = tuple(shape[0])
+        return torch.rand(*shape, generator=self._gen(name)).to(self.device)
+
+    def randperm(self, name, n):
+        return torch.rand(n, generator=self._gen(name)).argsort().to(self.device)
+
+    def randint(self, name, high, shape):
+        return torch.randint(high, shape, generator=self._gen(name)).to(self.device)
+
+    def uniform(self, name, shape, lo, hi):
+        return (torch.rand(*shape, generator=self._gen(name)) * (hi - lo) + lo).to(self.device)
+
+    def np_randint(self, name, high):
+        return int(torch.randint(high, (1,), generator=self._gen(name)))
