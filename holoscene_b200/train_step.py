@@ -184,6 +184,14 @@ class TrainStep:
         shapes = [(R, 3), (R, 3), (R, 1), (R, S), (R, 1)] + ([(1024, 3), (1024, 3), (1024, 1), (1024, S)] if bg_step else [])
         rec = _Captured()
         rec.rays = [torch.zeros(sh, device=dev) for sh in shapes]
+        rec.rays[0][:, 2] = 1.0                                       # ray_dirs = +z, cam_loc = 0, depth_scale = 1, z = linspace(0, 1)
+        rec.rays[2].fill_(1.0)
+        rec.rays[3].copy_(torch.linspace(0.0, 1.0, S, device=dev).expand(R, S))
+        rec.rays[4].fill_(0.5)
+        if bg_step:
+            rec.rays[6][:, 2] = 1.0
+            rec.rays[7].fill_(1.0)
+            rec.rays[8].copy_(torch.linspace(0.0, 1.0, S, device=dev).expand(1024, S))
         # the step number only selects the variant inside render_rays (and is excluded from graph mode where loss weights depend on it)
         rb = m.render_bg_iter
         it = (self.iter_step // rb) * rb if bg_step else (self.iter_step + 1 if m.use_bg_reg and self.iter_step % rb == 0 else self.iter_step)
@@ -200,6 +208,11 @@ class TrainStep:
         rec.kernels = _lib.launch_count() - k0
         self._graphs[key] = rec
         self.stats["captures"] += 1
+        # dry run on the placeholder rays: the first launch of a graph pays for its upload (milliseconds for ~150 nodes); pay it here,
+        # in the warm-up, with the random stream put back (the gradients it leaves behind are cleared at the start of every step)
+        rng = torch.cuda.get_rng_state(dev)
+        rec.graph.replay()
+        torch.cuda.set_rng_state(rng, dev)
         return rec
 
     def _split_step(self, model_input, ground_truth, indices):
