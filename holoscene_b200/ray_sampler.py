@@ -145,7 +145,7 @@ class ErrorBoundSampler:
     def _pinned_flags(self):
         """A pinned int32 buffer per outstanding speculative call (two per forward at most: scene + background patch)."""
         i = len(self._pending)
-        while len(self._flag_bufs) <= i:
+        while len(self._flag_bufs) <= max(i, 1):    # both at the first call: a later cudaHostAlloc would drain the device queue mid-training
             self._flag_bufs.append(torch.zeros(max(self.max_total_iters, 1), dtype=torch.int32).pin_memory())
         return self._flag_bufs[i]
 
