@@ -27,6 +27,19 @@ __device__ __forceinline__ void laplace_grads(float s, float beta, float& ds, fl
     if (s == 0.0f) ds = 0.0f;                             // torch: sign(0) = 0, |.|' (0) = 0
 }
 
+// density and both derivatives from ONE expm1f (same expressions as laplace_density / laplace_grads: identical bits)
+__device__ __forceinline__ void laplace_all(float s, float beta, float& sigma, float& ds, float& db) {
+    const float ib = 1.0f / beta;
+    const float em = expm1f(-fabsf(s) / beta);
+    const float sg = (s > 0.0f) ? 1.0f : ((s < 0.0f) ? -1.0f : 0.0f);
+    sigma = (1.0f / beta) * (0.5f + 0.5f * sg * em);
+    const float e = em + 1.0f;
+    ds = -0.5f * ib * ib * e;
+    if (s >= 0.0f) db = 0.5f * ib * ib * e * (s * ib - 1.0f);
+    else db = -ib * ib + 0.5f * ib * ib * e * (1.0f + s * ib);
+    if (s == 0.0f) ds = 0.0f;
+}
+
 __device__ __forceinline__ float warp_scan_incl_rev(float v, int lane) {   // suffix-inclusive scan
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -282,9 +295,9 @@ __global__ void __launch_bounds__(32 * CMP_WARPS) composite_bwd_kernel(Composite
                     for (int j = 0; j < nrows; ++j) {
                         const float sk = tile[j * ldt + k];
                         const float dj = sD[j], Tj = sT[j];
-                        const float ek = expf(-dj * laplace_density(sk, beta));
-                        float dsg, dbt;
-                        laplace_grads(sk, beta, dsg, dbt);
+                        float sig, dsg, dbt;
+                        laplace_all(sk, beta, sig, dsg, dbt);      // one expm1f for the density and both of its derivatives
+                        const float ek = expf(-dj * sig);
                         const float common = b * Tj * dj * ek;     // dL/d sigma_k
                         ctile[j * ldt + k] = b * (1.0f - ek) * Tj;
                         tile[j * ldt + k] = (common != 0.0f) ? rtf32(common * dsg, g.rtf) : 0.0f;
