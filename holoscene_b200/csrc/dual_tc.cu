@@ -15,11 +15,12 @@
 // t+1 runs under the epilogue of half-tile t, as in gemm_tc.cu.  The A operands (dq_in, da_in) are fetched once per half; the
 // second fetch of a tile's rows is an L2 hit (128 rows, issued back to back by the same CTA).  (A first version with 256-column
 // accumulators used the whole TMEM per tile and serialised MMA and epilogue: 10.9 ms/step instead of 10.4.)
-// Warp roles: 0 = TMA producer (the k-blocks of product 1, then of product 2, through one 2-stage ring), 1 = MMA issuer,
+// Warp roles: 0 = TMA producer (the k-blocks of product 1, then of product 2, through one 3-stage ring), 1 = MMA issuer,
 // 2..17 = sixteen epilogue warps (four per TMEM lane quarter, one 32-column chunk of every half-tile each): a chunk's latency
 // chain (operand rows from HBM -> accumulators from TMEM -> stores) is long, throughput comes from sixteen chunks in flight.
 // A lane requests the h rows of its chunk BEFORE waiting for the accumulators; the two accumulator chunks are transposed
-// through two shared pads per warp (147 KB: hence the 2-stage ring of 32 KB stages).
+// through two shared pads per warp (swizzled 4 KB pads, 128 KB in all: a 3-stage ring of 32 KB stages fits beside them; the
+// first version had padded 36-float rows = 147 KB and a 2-stage ring).
 //
 // MEASURED (4096 x 128, one B200, ms/step with / without this kernel): 10.06 / 10.43 with this version.  Two earlier versions
 // were correct but slower than the layer-by-layer path: 256-column accumulators single-buffered over the whole TMEM (10.9), and
@@ -33,14 +34,14 @@
 
 namespace hsb {
 
-constexpr int DU_STAGES = 2;
+constexpr int DU_STAGES = 3;
 constexpr int DU_NH = 128;                                 // output columns per half-tile
 constexpr int DU_A_BYTES = TC_BM * TC_BK * 4;              // 16 KB
 constexpr int DU_B_BYTES = DU_NH * TC_BK * 4;              // 16 KB
 constexpr int DU_STAGE_BYTES = DU_A_BYTES + DU_B_BYTES;
 constexpr int DU_EPI_WARPS = 16;
 constexpr int DU_THREADS = 64 + 32 * DU_EPI_WARPS;
-constexpr int DU_PAD_FLOATS = 2 * 32 * 36;                // two transpose pads per warp: acc1 chunk, acc2 chunk
+constexpr int DU_PAD_FLOATS = 2 * 32 * 32;                // two transpose pads per warp (acc1 chunk, acc2 chunk), XOR-swizzled rows
 constexpr int DU_SMEM_BYTES = DU_STAGES * DU_STAGE_BYTES + DU_EPI_WARPS * DU_PAD_FLOATS * 4 + 256 + 1024;
 
 struct DualArgs {
@@ -55,14 +56,17 @@ struct DualArgs {
     int num_tiles;
 };
 
-// 32x32 accumulator chunk at `taddr` -> this warp's pad (row-major, 36-float rows), as in gemm_tc.cu
-__device__ __forceinline__ void dual_chunk_to_pad(uint32_t taddr, uint32_t pad, int lane) {
+// 32x32 accumulator chunk at `taddr` -> this warp's pad.  Rows are exactly 32 floats (4 KB per pad, so that a third ring stage
+// fits beside the 32 pads); the 16-byte slot f of row r lives at slot f ^ (r & 7), which keeps both the row-wise stores (a
+// quarter-warp = 8 rows, one slot) and the transposed reads (a quarter-warp = one row, 8 slots) free of bank conflicts.
+// `row` = pad + lane * 128 (this lane's row), `l7` = (lane & 7) * 16 (byte offset of slot lane & 7)
+__device__ __forceinline__ void dual_chunk_to_pad(uint32_t taddr, uint32_t row, uint32_t l7) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         float v[16];
         tmem_ld16(taddr + 16 * h, v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sts128(pad + (uint32_t)(lane * 36 + 16 * h + 4 * j) * 4u, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) sts128(row + (l7 ^ (uint32_t)((4 * h + j) * 16)), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
 }
 
@@ -159,6 +163,8 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
         const int rl = lane >> 3;                                 // lane -> rows rl + 4 i (i = 0..7), columns n .. n + 3
         const int cl = 4 * (lane & 7);
         const int ro = a.round_out;
+        const uint32_t st_row = pad + (uint32_t)lane * 128u, st_l7 = (uint32_t)(lane & 7) * 16u;       // pad store: row = lane
+        const uint32_t ld_base = pad + (uint32_t)rl * 128u, ld_sw = (uint32_t)((lane & 7) ^ rl) * 16u;  // pad read: row rl + 4 i
         float4 cs0 = make_float4(0.f, 0.f, 0.f, 0.f), cs1 = cs0;                              // column sums per half
         int t = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -183,8 +189,8 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
                 mbar_wait(tfull + b, use & 1);
                 tc_fence_after();
                 // (2) both accumulator chunks: TMEM -> the warp's two pads (read back transposed: this lane's 8 rows x 4 columns)
-                dual_chunk_to_pad(tbase + (uint32_t)(c * 32), pad, lane);
-                dual_chunk_to_pad(tbase + (uint32_t)(DU_NH + c * 32), pad + 32 * 36 * 4, lane);
+                dual_chunk_to_pad(tbase + (uint32_t)(c * 32), st_row, st_l7);
+                dual_chunk_to_pad(tbase + (uint32_t)(DU_NH + c * 32), st_row + 32 * 32 * 4, st_l7);
                 tc_fence_before();                                // last read of this buffer by this warp
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty + b);
@@ -203,8 +209,10 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
                     for (int i = 0; i < 4; ++i) {
                         const int r = rl + 4 * (4 * hh + i);
                         if (r < rows) {
-                            const float4 a1 = lds128(pad + (uint32_t)(r * 36 + cl) * 4u);
-                            const float4 a2 = lds128(pad + (uint32_t)(32 * 36 + r * 36 + cl) * 4u);
+                            // row r = rl + 4 (4 hh + i), rl < 4  =>  r & 7 = rl | 4 (i & 1): two swizzle patterns per lane
+                            const uint32_t off = ld_base + (uint32_t)(4 * (4 * hh + i)) * 128u + ((i & 1) ? (ld_sw ^ 64u) : ld_sw);
+                            const float4 a1 = lds128(off);
+                            const float4 a2 = lds128(off + 32 * 32 * 4);
                             const float4 h4 = hx[4 * hh + i];
                             const float a1v[4] = {a1.x, a1.y, a1.z, a1.w};
                             const float a2v[4] = {a2.x, a2.y, a2.z, a2.w};

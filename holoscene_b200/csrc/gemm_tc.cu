@@ -21,7 +21,8 @@
 
 namespace hsb {
 
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 3;                               // ring depth at the full 48 KB stage (N = 256)
+constexpr int TC_MAX_STAGES = 8;                           // narrower B tiles: more, smaller stages in the same 144 KB (see gemm_tn_tc)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;              // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BK * 4;                // 32 KB (max N)
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;    // 48 KB
@@ -101,8 +102,10 @@ __device__ __forceinline__ void tc_epilogue_chunk(const Epi& e, uint32_t taddr, 
                 long long ma = ma0 + r;
                 while (ma >= wrap) ma -= wrap;
                 if (KIND == EPI_BWD_RELU && e.aux_bits) {      // ReLU mask as bits: 4 bytes per (row, 32 columns) instead of 128
-                    const uint32_t b = __ldg(e.aux_bits + ma * 8 + c) >> cl;
-                    ax[i] = make_float4((float)(b & 1u), (float)((b >> 1) & 1u), (float)((b >> 2) & 1u), (float)((b >> 3) & 1u));
+                    // the raw word stays in a register and is decoded where it is used (step 4): decoding it here makes the
+                    // warp wait for the load BEFORE it waits for the accumulator -- one HBM latency per chunk, serialised
+                    // (measured: 320 us per launch against 272 us with the fp32 tensor and ~200 us for a plain layer)
+                    ax[i].x = __uint_as_float(__ldg(e.aux_bits + ma * 8 + c));
                 } else {
                     ax[i] = __ldg(reinterpret_cast<const float4*>(e.aux + ma * e.lda + n));
                 }
@@ -149,7 +152,12 @@ __device__ __forceinline__ void tc_epilogue_chunk(const Epi& e, uint32_t taddr, 
             if (FULL || (col_ok && r < rows)) {
                 const float4 acc = lds128(pad + (uint32_t)(r * 36 + cl) * 4u);
                 float4 o2;
-                const float4 o = epi_math4<KIND>(acc, AUX ? ax[PRE ? half * 4 + i : i] : make_float4(0.f, 0.f, 0.f, 0.f), a2[i], bias4, o2);
+                float4 x4 = AUX ? ax[PRE ? half * 4 + i : i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (KIND == EPI_BWD_RELU && e.aux_bits) {
+                    const uint32_t b = __float_as_uint(x4.x) >> cl;
+                    x4 = make_float4((b & 1u) ? 1.f : 0.f, (b & 2u) ? 1.f : 0.f, (b & 4u) ? 1.f : 0.f, (b & 8u) ? 1.f : 0.f);
+                }
+                const float4 o = epi_math4<KIND>(acc, x4, a2[i], bias4, o2);
                 cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
                 *reinterpret_cast<float4*>(e.out + (m_first + r) * e.ldo + n) = make_float4(rtf32(o.x, ro), rtf32(o.y, ro), rtf32(o.z, ro), rtf32(o.w, ro));
                 if (KIND == EPI_BWD_CHAIN) {
@@ -240,13 +248,13 @@ __device__ __forceinline__ void tc_epilogue_role(const Epi& e, long long M, int 
 template <int KIND>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, long long M, int N,
-                  int K, int n_mma, uint32_t idesc, Epi epi, int num_tiles) {
+                  int K, int n_mma, uint32_t idesc, Epi epi, int num_tiles, int stages, int stage_bytes) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* pads = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES + TC_PAD_BYTES);
-    uint64_t* empty = full + TC_STAGES;
-    uint64_t* tfull = empty + TC_STAGES;
+    uint64_t* empty = full + TC_MAX_STAGES;
+    uint64_t* tfull = empty + TC_MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -256,7 +264,7 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         const uint32_t active = 4u * (uint32_t)(nchunk < TC_EPI_GROUPS ? nchunk : TC_EPI_GROUPS);   // epilogue warps that own chunks
         for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, active); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -274,24 +282,23 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         // ===== TMA producer =====
         if (lane == 0) {
             const uint32_t bytes = TC_A_BYTES + (uint32_t)n_mma * TC_BK * 4;
-            uint32_t it = 0;
+            uint32_t s = 0, ph = 0;                               // ring slot and its phase parity
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = tile * TC_BM;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t s = it % TC_STAGES;
-                    const uint32_t ph = (it / TC_STAGES) & 1;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(empty + s, ph ^ 1);
                     mbar_expect_tx(full + s, bytes);
-                    uint8_t* st = smem + s * TC_STAGE_BYTES;
+                    uint8_t* st = smem + s * stage_bytes;
                     tma_load_2d(&mapA, full + s, st, kb * TC_BK, m0);
                     tma_load_2d(&mapB, full + s, st + TC_A_BYTES, kb * TC_BK, 0);
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t s = 0, ph = 0;
             int t = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
                 const int b = t & 1;
@@ -299,17 +306,16 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 mbar_wait(tempty + b, (use & 1) ^ 1);          // epilogue has drained this accumulator (free on first use)
                 tc_fence_after();
                 const uint32_t acc = tmem + (uint32_t)(b * 256);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t s = it % TC_STAGES;
-                    const uint32_t ph = (it / TC_STAGES) & 1;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(full + s, ph);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(smem + s * TC_STAGE_BYTES);
+                    const uint32_t a0 = smem_u32(smem + s * stage_bytes);
                     const uint64_t ad = smem_desc_k_sw128(a0), bd = smem_desc_k_sw128(a0 + TC_A_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k)          // 8 tf32 = 32 bytes = +2 in the (addr >> 4) field
                         umma_tf32(acc, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
                     umma_commit(empty + s);                       // smem slot free once these MMAs retire
+                    if (++s == (uint32_t)stages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(tfull + b);                           // accumulator complete
             }
@@ -469,7 +475,15 @@ template <int KIND> static bool tn_set_smem() {
 template <int KIND>
 static void tn_launch(unsigned grid, cudaStream_t stream, const CUtensorMap& mapA, const CUtensorMap& mapB, long long M, int N, int K,
                       int n_mma, uint32_t idesc, const Epi& epi, int num_tiles) {
-    gemm_tn_tc_kernel<KIND><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles);
+    // A stage = the 16 KB A tile + the B tile of this call (n_mma rows of 128 B, rounded up to the 1 KB swizzle period).  The ring
+    // region is fixed at 144 KB (3 stages of the widest B tile); a narrow B tile (N = 27 / 32 data-gradient contractions, whose
+    // only traffic is the A stream) gets up to eight stages in it -- with three, 48 KB of loads in flight per SM do not cover the
+    // HBM latency (measured 136 us for one [P,256] read against 82 us at the roofline).
+    const int stage_bytes = TC_A_BYTES + (n_mma * TC_BK * 4 + 1023) / 1024 * 1024;
+    int stages = TC_STAGES * TC_STAGE_BYTES / stage_bytes;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    gemm_tn_tc_kernel<KIND><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(mapA, mapB, M, N, K, n_mma, idesc, epi, num_tiles, stages,
+                                                                         stage_bytes);
 }
 
 static bool tc_init() {
