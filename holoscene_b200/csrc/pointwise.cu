@@ -24,18 +24,20 @@ __device__ __forceinline__ void pe_write(float* __restrict__ dst, float x, float
 
 // points of a ray batch: x = o + z d;  H0[:, 0:39] = PE6(x), H0[:,71] = 0;
 // RIN[:, 256:283] = PE4(x), RIN[:, 283:310] = PE4(d), RIN[:, 337:344] = 0   (RIN may be null: SDF-only use; layout: step.cuh)
-// A CTA owns 128 points.  Phase 1: thread = point, 18 (+12) sincosf into a shared tile (PE4(x) is the first 27 columns of
-// PE6(x)).  Phase 2: thread = (point, 16-byte slot); consecutive threads write consecutive float4s of a row, so every store
-// instruction covers whole sectors (a per-point scalar walk writes 4 bytes into 32 different rows per instruction).
+// A CTA owns 128 points.  Phase 1: thread = point, 18 (+12) sincosf into a shared row [PE6(x) 39 | pad | PE4(d) 27] (PE4(x) is
+// the first 27 columns of PE6(x)); the row stride of 67 floats keeps these scalar writes free of bank conflicts.  Phase 2:
+// warp = 32 rows, lane = one 16-byte slot of the output row, so every store instruction writes whole sectors of ONE row and a
+// lane's source columns / destination offset are fixed for the whole kernel (the first version walked (point, slot) pairs with
+// a division and a four-way branch per slot: 4 800 instructions per warp, issue-bound at 125 us; ncu r02b_pointwise).
 // Slots: 0..9 = H0 columns 0..39, 10 = H0 columns 68..71, 11..24 = RIN columns 256..311, 25..26 = RIN columns 336..343.  Columns
 // zero-filled inside those slots but not owned here (H0 39, 68..70: hash features; RIN 310, 311, 336: PE4(g)) are
 // written by later kernels of the same pass.
 constexpr int RP_PTS = 128;
+constexpr int RP_LD = 67;                                  // shared row: [0,39) PE6(x), 39 zero, [40,67) PE4(d); 67 is odd on purpose
 __global__ void __launch_bounds__(RP_PTS) ray_points_kernel(const float* __restrict__ o, const float* __restrict__ d,
                                                             const float* __restrict__ z, int R, int S, float* __restrict__ X,
                                                             float* __restrict__ H0, float* __restrict__ RIN, int rtf) {
-    __shared__ __align__(16) float sx[RP_PTS][40];      // PE6(x), column 39 = 0
-    __shared__ __align__(16) float sd[RP_PTS][28];      // PE4(d), column 27 = 0
+    __shared__ float sx[RP_PTS * RP_LD];
     const int P = R * S;
     const int p0 = blockIdx.x * RP_PTS;
     {
@@ -46,41 +48,49 @@ __global__ void __launch_bounds__(RP_PTS) ray_points_kernel(const float* __restr
             const float dx = d[r * 3 + 0], dy = d[r * 3 + 1], dz = d[r * 3 + 2];
             const float x = o[r * 3 + 0] + zz * dx, y = o[r * 3 + 1] + zz * dy, w = o[r * 3 + 2] + zz * dz;
             X[p * 3 + 0] = x; X[p * 3 + 1] = y; X[p * 3 + 2] = w;
-            pe_write(sx[threadIdx.x], x, y, w, 6, rtf);
-            sx[threadIdx.x][39] = 0.0f;
-            if (RIN) {
-                pe_write(sd[threadIdx.x], dx, dy, dz, 4, rtf);
-                sd[threadIdx.x][27] = 0.0f;
-            }
+            float* row = sx + threadIdx.x * RP_LD;
+            pe_write(row, x, y, w, 6, rtf);
+            row[39] = 0.0f;
+            if (RIN) pe_write(row + 40, dx, dy, dz, 4, rtf);
         }
     }
     __syncthreads();
-    const int nslot = RIN ? 27 : 11;
-    const int npts = min(RP_PTS, P - p0);
-    for (int idx = threadIdx.x; idx < npts * nslot; idx += RP_PTS) {
-        const int lp = idx / nslot, slot = idx - lp * nslot;
-        const long long p = p0 + lp;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        float* dst;
-        if (slot < 10) {
-            v = *reinterpret_cast<const float4*>(&sx[lp][4 * slot]);
-            dst = H0 + p * LD_H0 + 4 * slot;
-        } else if (slot == 10) {
-            dst = H0 + p * LD_H0 + 68;
-        } else if (slot < 25) {
-            const int j = 4 * (slot - 11);
-            float e[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= (RIN ? 27 : 11)) return;
+    // this lane's slot: four source columns of the shared row (-1 = zero) and the destination of its float4
+    int src[4];
+    float* dst;
+    long long ld;
+    if (lane < 10) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int c = j + k;
-                e[k] = c < 27 ? sx[lp][c] : (c < 54 ? sd[lp][c - 27] : 0.0f);
-            }
-            v = make_float4(e[0], e[1], e[2], e[3]);
-            dst = RIN + p * LD_RIN + RIN_PE + j;
-        } else {
-            dst = RIN + p * LD_RIN + 336 + 4 * (slot - 25);
+        for (int k = 0; k < 4; ++k) src[k] = 4 * lane + k;
+        dst = H0 + 4 * lane; ld = LD_H0;
+    } else if (lane == 10) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) src[k] = -1;
+        dst = H0 + 68; ld = LD_H0;
+    } else if (lane < 25) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = 4 * (lane - 11) + k;              // column of [PE4(x) 27 | PE4(d) 27 | 0 0]
+            src[k] = c < 27 ? c : (c < 54 ? c + 13 : -1);
         }
-        *reinterpret_cast<float4*>(dst) = v;
+        dst = RIN + RIN_PE + 4 * (lane - 11); ld = LD_RIN;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) src[k] = -1;
+        dst = RIN + 336 + 4 * (lane - 25); ld = LD_RIN;
+    }
+    const int lp0 = warp * 32;
+    const int nrow = min(32, P - p0 - lp0);
+    dst += (long long)(p0 + lp0) * ld;
+    const float* row = sx + lp0 * RP_LD;
+#pragma unroll 4
+    for (int rr = 0; rr < nrow; ++rr, dst += ld, row += RP_LD) {
+        float e[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = src[k] >= 0 ? row[src[k]] : 0.0f;
+        *reinterpret_cast<float4*>(dst) = make_float4(e[0], e[1], e[2], e[3]);
     }
 }
 
@@ -240,8 +250,9 @@ __global__ void __launch_bounds__(32 * CE_WARPS) chain_end_kernel(const float* _
     const long long nwarps = (long long)gridDim.x * CE_WARPS;
     const ChainCol c0 = chain_col(lane), c1 = chain_col(lane + 32), c2 = chain_col(lane < 8 ? lane + 64 : 71);
 #pragma unroll 2
+    const bool one_seed = rows == N;
     for (long long m = warp; m < rows; m += nwarps) {
-        const long long p = m % N;
+        const long long p = one_seed ? m : m % N;          // (a 64-bit modulo costs ~60 instructions per row)
         const float* q = Q0 + m * LD_H0;
         const float* h = H0 + p * LD_H0;
         const float* dy = DY + p * 96;
@@ -431,48 +442,59 @@ __global__ void __launch_bounds__(256) rgb_head_kernel(const float* __restrict__
 // 0..3, float4 column group 0..63), 32 rows per thread, four rows in flight; partial sums meet in shared memory, one atomic
 // per column per CTA.
 constexpr int RHB_ROWS = 128;
-template <bool FOLD>
-__global__ void __launch_bounds__(256) rgb_head_bwd_kernel(const float* __restrict__ dO, const float* __restrict__ R2e,
-                                                           const float* __restrict__ U2, long long N, float* __restrict__ dU2, int rtf,
+constexpr int RHB_FLIGHT = 8;                             // rows of U2 in flight per thread
+template <bool FOLD, int RTF>
+__global__ void __launch_bounds__(256, 3) rgb_head_bwd_kernel(const float* __restrict__ dO, const float* __restrict__ R2e,
+                                                           const float* __restrict__ U2, long long N, float* __restrict__ dU2,
                                                            float* __restrict__ colsum, float* __restrict__ dR2e,
                                                            float* __restrict__ dRB2e) {
+    constexpr int rtf = RTF;                             // compile-time: a runtime flag put a branch around every rounding
+    // The kernel holds ~80 registers (three weight rows and, with FOLD, four accumulator rows per thread), so three CTAs fit an
+    // SM; with four rows in flight per thread that was 48 KB of loads per SM -- not enough to cover the HBM latency (ncu: 6.7
+    // warps stalled on the long scoreboard per issue, 4.2 TB/s).  The dO rows of the CTA are staged in shared memory once (2 KB)
+    // instead of being prefetched per row, which frees the registers for eight U2 rows in flight.
+    __shared__ float4 sg[RHB_ROWS];
     __shared__ float4 red[FOLD ? 4 * 256 : 1];
     __shared__ float redb[FOLD ? 4 * 4 : 1];
     const int j = threadIdx.x & 63, ry = threadIdx.x >> 6;
+    const long long p0 = (long long)blockIdx.x * RHB_ROWS;
+    const long long p1 = min(N, p0 + RHB_ROWS);
+    if (threadIdx.x < RHB_ROWS) {
+        const long long p = p0 + threadIdx.x;
+        sg[threadIdx.x] = p < p1 ? __ldg(reinterpret_cast<const float4*>(dO) + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const float4 w0 = reinterpret_cast<const float4*>(R2e)[j];
     const float4 w1 = reinterpret_cast<const float4*>(R2e + 256)[j];
     const float4 w2 = reinterpret_cast<const float4*>(R2e + 512)[j];
-    const long long p0 = (long long)blockIdx.x * RHB_ROWS;
-    const long long p1 = min(N, p0 + RHB_ROWS);
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 a0 = cs, a1 = cs, a2 = cs;                    // dR2e rows 0..2, columns 4j..4j+3
     float b0 = 0.f, b1 = 0.f, b2 = 0.f;                   // dRB2e (lanes with j == 0 only)
-    for (long long pb = p0 + ry; pb < p1; pb += 16) {
-        float4 g[4], u[4];
+    __syncthreads();
+    for (int lr0 = ry; lr0 < RHB_ROWS; lr0 += 4 * RHB_FLIGHT) {
+        float4 u[RHB_FLIGHT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long p = pb + 4 * i;
-            if (p < p1) {
-                g[i] = __ldg(reinterpret_cast<const float4*>(dO) + p);
-                u[i] = __ldg(reinterpret_cast<const float4*>(U2 + p * 256) + j);
-            }
+        for (int i = 0; i < RHB_FLIGHT; ++i) {
+            const long long p = p0 + lr0 + 4 * i;
+            if (p < p1) u[i] = __ldg(reinterpret_cast<const float4*>(U2 + p * 256) + j);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long p = pb + 4 * i;
+        for (int i = 0; i < RHB_FLIGHT; ++i) {
+            const int lr = lr0 + 4 * i;
+            const long long p = p0 + lr;
             if (p < p1) {
+                const float4 g = sg[lr];
                 float4 r;
-                r.x = u[i].x > 0.f ? rtf32(g[i].x * w0.x + g[i].y * w1.x + g[i].z * w2.x, rtf) : 0.f;
-                r.y = u[i].y > 0.f ? rtf32(g[i].x * w0.y + g[i].y * w1.y + g[i].z * w2.y, rtf) : 0.f;
-                r.z = u[i].z > 0.f ? rtf32(g[i].x * w0.z + g[i].y * w1.z + g[i].z * w2.z, rtf) : 0.f;
-                r.w = u[i].w > 0.f ? rtf32(g[i].x * w0.w + g[i].y * w1.w + g[i].z * w2.w, rtf) : 0.f;
+                r.x = u[i].x > 0.f ? rtf32(g.x * w0.x + g.y * w1.x + g.z * w2.x, rtf) : 0.f;
+                r.y = u[i].y > 0.f ? rtf32(g.x * w0.y + g.y * w1.y + g.z * w2.y, rtf) : 0.f;
+                r.z = u[i].z > 0.f ? rtf32(g.x * w0.z + g.y * w1.z + g.z * w2.z, rtf) : 0.f;
+                r.w = u[i].w > 0.f ? rtf32(g.x * w0.w + g.y * w1.w + g.z * w2.w, rtf) : 0.f;
                 reinterpret_cast<float4*>(dU2 + p * 256)[j] = r;
                 if (FOLD) {
                     cs.x += r.x; cs.y += r.y; cs.z += r.z; cs.w += r.w;
-                    a0.x += g[i].x * u[i].x; a0.y += g[i].x * u[i].y; a0.z += g[i].x * u[i].z; a0.w += g[i].x * u[i].w;
-                    a1.x += g[i].y * u[i].x; a1.y += g[i].y * u[i].y; a1.z += g[i].y * u[i].z; a1.w += g[i].y * u[i].w;
-                    a2.x += g[i].z * u[i].x; a2.y += g[i].z * u[i].y; a2.z += g[i].z * u[i].z; a2.w += g[i].z * u[i].w;
-                    b0 += g[i].x; b1 += g[i].y; b2 += g[i].z;
+                    a0.x += g.x * u[i].x; a0.y += g.x * u[i].y; a0.z += g.x * u[i].z; a0.w += g.x * u[i].w;
+                    a1.x += g.y * u[i].x; a1.y += g.y * u[i].y; a1.z += g.y * u[i].z; a1.w += g.y * u[i].w;
+                    a2.x += g.z * u[i].x; a2.y += g.z * u[i].y; a2.z += g.z * u[i].z; a2.w += g.z * u[i].w;
+                    b0 += g.x; b1 += g.y; b2 += g.z;
                 }
             }
         }
@@ -518,8 +540,10 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const float* __restri
             const long long m = mb + 4 * i;
             key[i] = -1;
             if (m < m1) {
-                const long long sd = m / N, p = m - sd * N;
-                key[i] = (nseed > 1 && sd < K) ? (int)sd : kstar[p];
+                if (nseed > 1) {                            // 64-bit division only where there are seed blocks (eikonal slots)
+                    const long long sd = m / N, p = m - sd * N;
+                    key[i] = sd < K ? (int)sd : kstar[p];
+                } else key[i] = kstar[m];
                 v[i] = __ldg(reinterpret_cast<const float4*>(dQ2 + m * 256 + c4));
             }
         }
@@ -660,8 +684,14 @@ int launch_rgb_head(const float* U2, const float* R2e, const float* bias, long l
 int launch_rgb_head_bwd(const float* dO, const float* R2e, const float* U2, long long N, float* dU2, int rtf, float* colsum,
                         float* dR2e, float* dRB2e, cudaStream_t st) {
     if (N == 0) return HSB_OK;
-    if (colsum && dR2e && dRB2e) rgb_head_bwd_kernel<true><<<cdiv(N, RHB_ROWS), 256, 0, st>>>(dO, R2e, U2, N, dU2, rtf, colsum, dR2e, dRB2e);
-    else rgb_head_bwd_kernel<false><<<cdiv(N, RHB_ROWS), 256, 0, st>>>(dO, R2e, U2, N, dU2, rtf, nullptr, nullptr, nullptr);
+    const unsigned grid = (unsigned)cdiv(N, RHB_ROWS);
+    if (colsum && dR2e && dRB2e) {
+        if (rtf) rgb_head_bwd_kernel<true, 1><<<grid, 256, 0, st>>>(dO, R2e, U2, N, dU2, colsum, dR2e, dRB2e);
+        else rgb_head_bwd_kernel<true, 0><<<grid, 256, 0, st>>>(dO, R2e, U2, N, dU2, colsum, dR2e, dRB2e);
+    } else {
+        if (rtf) rgb_head_bwd_kernel<false, 1><<<grid, 256, 0, st>>>(dO, R2e, U2, N, dU2, nullptr, nullptr, nullptr);
+        else rgb_head_bwd_kernel<false, 0><<<grid, 256, 0, st>>>(dO, R2e, U2, N, dU2, nullptr, nullptr, nullptr);
+    }
     return check_launch("rgb_head_bwd");
 }
 int launch_scatter_rows(const float* dQ2, const int* kstar, long long N, int K, int Kp, int nseed, float* dW2e,
