@@ -188,6 +188,15 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
                 }
                 mbar_wait(tfull + b, use & 1);
                 tc_fence_after();
+                // the first four rows of p: requested here, before the transposition (requesting them before the wait as well makes
+                // the compiler spill LOADED registers, i.e. wait for them early; ptxas issues them during the tail of the transposition)
+                float4 px[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = rl + 4 * i;
+                    px[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < rows) px[i] = __ldg(reinterpret_cast<const float4*>(a.aux2 + (m_first + r) * a.lda2 + n));
+                }
                 // (2) both accumulator chunks: TMEM -> the warp's two pads (read back transposed: this lane's 8 rows x 4 columns)
                 dual_chunk_to_pad(tbase + (uint32_t)(c * 32), st_row, st_l7);
                 dual_chunk_to_pad(tbase + (uint32_t)(DU_NH + c * 32), st_row + 32 * 32 * 4, st_l7);
@@ -195,15 +204,24 @@ gemm_dual_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty + b);
                 __syncwarp();
-                // (3) math + coalesced 16-byte stores, four rows at a time (p is fetched per group: register budget)
+                // The compiler otherwise hoists sigma(h) above the accumulator wait, i.e. the warp blocks on its h loads BEFORE it waits
+                // for the accumulator and before the transposition (ncu source page: 20 % of the kernel's stall samples on the first
+                // use of h, another 20 % on the first uses of p): pin the first use of the prefetched rows here, so that the wait and
+                // the transposition run under the loads.
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("" : "+f"(hx[i].x), "+f"(hx[i].y), "+f"(hx[i].z), "+f"(hx[i].w));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) asm volatile("" : "+f"(px[i].x), "+f"(px[i].y), "+f"(px[i].z), "+f"(px[i].w));
+                // (3) math + coalesced 16-byte stores, four rows at a time (the second group of p rows is fetched here: register budget)
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    float4 px[4];
+                    if (hh == 1) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = rl + 4 * (4 * hh + i);
-                        px[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r < rows) px[i] = __ldg(reinterpret_cast<const float4*>(a.aux2 + (m_first + r) * a.lda2 + n));
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = rl + 4 * (4 + i);
+                            px[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (r < rows) px[i] = __ldg(reinterpret_cast<const float4*>(a.aux2 + (m_first + r) * a.lda2 + n));
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {

@@ -40,6 +40,7 @@ struct TrunkArgs {
     float* sdf;             // [N] (may be null)
     float* sr;              // [N, Kp] raw per-object values (may be null)
     int num_tiles;
+    int handoff;            // chunk-level hand-off from the hidden-layer epilogues to the next layer's MMA (see the kernel)
 };
 
 // softplus epilogue of one hidden layer, in place in tensor memory: columns [32c, 32c+32) of the accumulator at `tbase`
@@ -68,7 +69,11 @@ sdf_trunk_tc_kernel(const __grid_constant__ CUtensorMap mapH0, const __grid_cons
     uint64_t* empty = full + TR_STAGES;
     uint64_t* acc_full = empty + TR_STAGES;      // MMA -> epilogue: an accumulator is complete (3 uses per tile)
     uint64_t* a_ready = acc_full + 1;            // epilogue -> MMA: next A operand written / region free (3 uses per tile)
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(a_ready + 1);
+    // hand-off mode: the epilogue publishes every 32-column chunk of the next A operand on its own barrier (four arrivals: the
+    // lane-quarter warps that own the chunk) and the MMA warp issues k-block c of the next layer as soon as chunk c is there, so
+    // the contraction overlaps the second half of the softplus epilogue; a_ready then only says "X drained" (1 use per tile)
+    uint64_t* chunk_rdy = a_ready + 1;           // [8], 2 uses per tile: parity 0 = X chunks (layer 1), parity 1 = Y chunks (layer 2)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(chunk_rdy + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NKB0 = 3;                      // ceil(72 / 32): the third k-block's columns 72..95 are zero-filled by TMA
     constexpr int NKB = 8;                       // 256 / 32
@@ -88,6 +93,7 @@ sdf_trunk_tc_kernel(const __grid_constant__ CUtensorMap mapH0, const __grid_cons
         for (int s = 0; s < TR_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         mbar_init(acc_full, 1);
         mbar_init(a_ready, TR_EPI_WARPS);
+        for (int c = 0; c < 8; ++c) mbar_init(chunk_rdy + c, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -132,6 +138,7 @@ sdf_trunk_tc_kernel(const __grid_constant__ CUtensorMap mapH0, const __grid_cons
             int t = 0;
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++t) {
                 if (t > 0) { mbar_wait(a_ready, ar & 1); ++ar; tc_fence_after(); }      // previous tile's result drained from X
+                const bool ho = a.handoff != 0;
                 // layer 0: both operands from shared memory
                 for (int kb = 0; kb < NKB0; ++kb, ++it) {
                     const uint32_t s = it % TR_STAGES, ph = (it / TR_STAGES) & 1;
@@ -145,11 +152,12 @@ sdf_trunk_tc_kernel(const __grid_constant__ CUtensorMap mapH0, const __grid_cons
                 }
                 umma_commit(acc_full);
                 // layer 1: A = X (tensor memory, written by the epilogue), D = Y
-                mbar_wait(a_ready, ar & 1); ++ar;
+                if (!ho) { mbar_wait(a_ready, ar & 1); ++ar; }
                 tc_fence_after();
                 for (int kb = 0; kb < NKB; ++kb, ++it) {
                     const uint32_t s = it % TR_STAGES, ph = (it / TR_STAGES) & 1;
                     mbar_wait(full + s, ph);
+                    if (ho) mbar_wait(chunk_rdy + kb, 0);
                     tc_fence_after();
                     const uint64_t bd = smem_desc_k_sw128(smem_u32(smem + s * TR_STAGE_BYTES) + TR_A_BYTES);
 #pragma unroll
@@ -159,11 +167,12 @@ sdf_trunk_tc_kernel(const __grid_constant__ CUtensorMap mapH0, const __grid_cons
                 }
                 umma_commit(acc_full);
                 // layer 2: A = Y, D = X[0 : n2)
-                mbar_wait(a_ready, ar & 1); ++ar;
+                if (!ho) { mbar_wait(a_ready, ar & 1); ++ar; }
                 tc_fence_after();
                 for (int kb = 0; kb < NKB; ++kb, ++it) {
                     const uint32_t s = it % TR_STAGES, ph = (it / TR_STAGES) & 1;
                     mbar_wait(full + s, ph);
+                    if (ho) mbar_wait(chunk_rdy + kb, 1);
                     tc_fence_after();
                     const uint64_t bd = smem_desc_k_sw128(smem_u32(smem + s * TR_STAGE_BYTES) + TR_A_BYTES);
 #pragma unroll
@@ -188,11 +197,17 @@ sdf_trunk_tc_kernel(const __grid_constant__ CUtensorMap mapH0, const __grid_cons
                 const uint32_t base = (layer == 0 ? X : Y) + lane_off;
                 const uint32_t sb = smem_u32(sbias) + (uint32_t)layer * 1024u;
                 trunk_hidden_chunk(base + (uint32_t)(g * 32), sb + (uint32_t)g * 128u);
+                if (a.handoff) {                 // publish chunk g now: k-block g of the next layer can be issued
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(chunk_rdy + g);
+                }
                 trunk_hidden_chunk(base + (uint32_t)((g + 4) * 32), sb + (uint32_t)(g + 4) * 128u);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_ready);
+                if (lane == 0) mbar_arrive(a.handoff ? chunk_rdy + g + 4 : a_ready);
             }
             mbar_wait(acc_full, u & 1); ++u;
             tc_fence_after();
@@ -265,6 +280,8 @@ int sdf_trunk_tc(const float* H0, long long N, const float* W0e, const float* W1
     TrunkArgs a{};
     a.N = N; a.K = K; a.Kp = Kp; a.n2 = n2; a.channel = channel; a.mask = mask; a.b0 = b0; a.b1 = b1; a.b2 = b2; a.sdf = sdf; a.sr = sr;
     a.num_tiles = (int)((N + TC_BM - 1) / TC_BM);
+    static const int handoff = [] { const char* e = getenv("HSB_TRUNK_HANDOFF"); return e ? atoi(e) : 1; }();   // on; =0: layer-level hand-off
+    a.handoff = handoff;
     const unsigned grid = (unsigned)(a.num_tiles < num_sms() ? a.num_tiles : num_sms());
     sdf_trunk_tc_kernel<<<grid, TR_THREADS, TR_SMEM_BYTES, stream>>>(mH0, mW0, mW1, mW2, a, idesc256, idesc2);
     return check_launch("sdf_trunk");
