@@ -115,20 +115,34 @@ def algorithmic_work(w, R, rounds, n_params):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs.
+
+    nvidia-smi is started (and its first sample awaited) BEFORE the warm-up: its start-up -- NVML initialisation and device
+    enumeration, 0.1-0.5 s -- takes driver locks that stall kernel / graph launches of the process being measured; started right
+    before the timed region it put one-off stalls of 5-100 ms into the first timed steps (8.8 ms/step measured as 9.2 and 13.7 in
+    two of six runs, with the end-to-end figure of the same run, taken a second later, unaffected).  The periodic samples that
+    follow are single NVML queries and do not show up in the step times."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, str(gpu_index)
+        self.rows, self.proc, self.gpu, self.begin = [], None, str(gpu_index), 0
 
-    def start(self):
+    def start(self, ready_timeout=5.0):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", self.gpu], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+            return
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < ready_timeout and self.proc.poll() is None:
+            time.sleep(0.01)
+
+    def mark(self):
+        """the region of interest starts here: samples taken before (idle GPU) are not reported"""
+        self.begin = len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -137,12 +151,15 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        rows = self.rows[self.begin:]
+        if not rows:                                # a region shorter than one sampling interval: take the next sample
+            time.sleep(0.15)
+            rows = self.rows[self.begin:] or list(self.rows)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -522,7 +539,10 @@ def main():
     b = Bench(w, R, rank, world, dev, precise=args.precise, exact_sampler=args.exact_sampler, graph=not args.no_graph)
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()                  # returns once nvidia-smi delivers samples (see the class docstring)
+    if world > 1:
+        dist.barrier()                  # the other ranks wait for rank 0's sampler too
+    clocks.mark()
     ms_dev, ms_e2e, launches = b.run(args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
     head = b.result(ms_dev, ms_e2e, launches)

@@ -3,7 +3,7 @@
 // One CTA owns a 128-row tile of A and the whole N extent (UMMA M = 128, N = ceil16(N) <= 256, so the
 // activation tile is read from HBM/L2 exactly once).  fp32 operands are staged by TMA
 // (cp.async.bulk.tensor, 128-byte swizzle, out-of-range rows / K-tail zero-filled by the copy engine)
-// into a 2-stage ring, consumed as TF32 by tcgen05.mma (kind::tf32, K = 8 per instruction, 4 per
+// into a ring of 3 to 8 stages (by the width of the B tile), consumed as TF32 by tcgen05.mma (kind::tf32, K = 8 per instruction, 4 per
 // 128-byte k-block) with the fp32 accumulator in tensor memory (256 columns), and drained by eight
 // epilogue warps: tcgen05.ld 32 lanes x 32 columns -> per-warp transpose through the (by then idle)
 // stage buffers -> fused epilogue (bias / softplus / ReLU / sigmoid / chain terms) with fully
@@ -520,9 +520,16 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, int co
     cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
+    // A k-block of an activation tile is 128 rows x 128 B, the rows 288 B .. 1.4 KB apart: every TMA request touches 128 DRAM pages
+    // and the next k-block of the same rows arrives a few hundred ns later.  With 256-byte L2 promotion the neighbouring k-block
+    // comes along with the request: measured -5 .. -11 us on every [P,256] data-gradient launch, -8 / -10 us on the two fused
+    // forward kernels, 57 us per step in all (HSB_TMA_L2_PROMO=128 restores the 128-byte promotion for an A/B run).
+    static const CUtensorMapL2promotion promo = [] {
+        const char* e = getenv("HSB_TMA_L2_PROMO");
+        return (e && atoi(e) == 128) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }();
     CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
