@@ -149,7 +149,11 @@ void hsb_ctx_destroy(hsb_ctx* ctx);
  * SDF-net backward through the dual-accumulator layer kernel (csrc/dual_tc.cu), 0 = EPI_BWD_CHAIN + EPI_BWD_SP launches; env HSB_DUAL_BWD.
  * "fused_fwd": 1 (default in the fast mode) = scene-pass forward through the two TMEM-chained kernels (csrc/sdfchain_tc.cu,
  * csrc/render_tc.cu), 0 = one launch per layer; env HSB_FUSED_FWD.  "fused_bwd": 1 = render / colour data-gradient chain of the backward
- * as one kernel (csrc/render_bwd_tc.cu), default 0 (measured slower than the launches it replaces); env HSB_FUSED_BWD. */
+ * as one kernel (csrc/render_bwd_tc.cu), default 0 (measured slower than the launches it replaces); env HSB_FUSED_BWD.
+ * Process-wide A/B switches read from the environment once (no set_option counterpart): HSB_TRUNK_HANDOFF=0 = layer-level instead of
+ * chunk-level hand-off in the sampler's fused trunk (csrc/trunk_tc.cu); HSB_TMA_L2_PROMO=128 = 128-byte instead of 256-byte L2
+ * promotion of the TMA tensor maps (csrc/gemm_tc.cu); HSB_DISABLE_TCGEN05 / HSB_DISABLE_FUSED_TRUNK / _SDFCHAIN / _RENDER / _RENDER_BWD =
+ * leave a tcgen05 kernel family out (the fast mode then takes the next more general path). */
 int hsb_ctx_set_option(hsb_ctx* ctx, const char* name, int64_t value);
 /* Introspection for tests: byte offset / rows / row stride (floats) of a named workspace buffer, e.g. "main.H1". */
 int hsb_ctx_buffer(hsb_ctx* ctx, const char* name, int64_t* offset_bytes, int64_t* rows, int64_t* ld);
