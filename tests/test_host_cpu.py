@@ -274,3 +274,32 @@ def test_pixel_sampler_matches_reference_semantics():
     s2, gt2 = pixel_sampler.gather_batch(sample, gt, got)
     assert s2["uv"].shape == (got.numel(), 2) and gt2["rgb"].shape == (got.numel(), 3) and gt2["full_rgb"].shape == (H * W, 3)
     assert torch.equal(gt2["segs"][:, 0], segs[got, 0])
+
+
+def test_bench_clock_sampler_reports_only_the_marked_region():
+    """bench.py's nvidia-smi sampler: samples taken before mark() (sampler start-up, idle GPU) are not part of the clocks record,
+    throttle reasons are picked up by name, and a missing nvidia-smi is reported instead of raising."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("hsb_bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+
+    class _Proc:
+        def terminate(self):
+            pass
+
+    row = lambda sm, cap: ["0", str(sm), "1965", "700.0", "0x0", "Not Active", "Not Active", "Not Active", cap]
+    c = bench.ClockSampler(0)
+    c.proc = _Proc()
+    c.rows = [row(345, "Not Active"), row(900, "Not Active")]            # idle samples while nvidia-smi starts up
+    c.mark()
+    c.rows += [row(1965, "Not Active"), row(1950, "Active"), row(1965, "Not Active")]
+    rec = c.stop()
+    assert rec == {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3}
+    none = bench.ClockSampler(0)
+    assert none.stop()["reasons"] == ["nvidia-smi unavailable"]
